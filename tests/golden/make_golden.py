@@ -1,0 +1,254 @@
+"""Generate the golden fixtures by EXECUTING THE UPSTREAM REFERENCE CODE.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every array below is an output of the reference's own functions/modules
+(imported unmodified from /root/reference; matplotlib stubbed because it is
+only used for plotting) on seeded inputs.  Inputs and weights are NOT stored:
+they are regenerated from PCG64 seeds by ``oracle.*.make_weights`` /
+``oracle.egonet_ref.synth_*`` (a digest of the regenerated weights is stored to
+detect drift).  Library versions used are recorded in ``versions.json``.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+from _refimport import import_reference  # noqa: E402
+from oracle import configs, egonet_ref, hrnet_ref, lifter_ref  # noqa: E402
+
+
+def rng(seed):
+    return np.random.Generator(np.random.PCG64(seed))
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print('%-28s %7.1f KB' % (name, os.path.getsize(path) / 1024))
+
+
+def golden_hrnet(ref, tag, cfgs, batch, seed_w, seed_x, map_row_stride):
+    model = ref['hrnet'].get_pose_net(cfgs, is_train=False).eval()
+    sd = hrnet_ref.make_weights(cfgs, seed_w)
+    model.load_state_dict(sd)                       # strict: key set must match upstream
+    x = egonet_ref.synth_crops(batch, cfgs, seed_x)
+    taps = {}
+    hooks = []
+    # per-stage activation statistics from the upstream module (forward hooks)
+    def stat_hook(name):
+        def fn(_m, _i, out):
+            o = out[0] if isinstance(out, (list, tuple)) else out
+            taps[name] = np.array([o.double().mean().item(), o.double().std().item(),
+                                   o.double().abs().max().item()])
+        return fn
+    for name in ('layer1', 'stage2', 'stage3', 'stage4'):
+        hooks.append(getattr(model, name).register_forward_hook(stat_hook(name)))
+    with torch.no_grad():
+        out = model(x)
+    for h in hooks:
+        h.remove()
+    arrays = {'seed_w': seed_w, 'seed_x': seed_x, 'batch': batch,
+              'weights_digest': hrnet_ref.weights_digest(sd),
+              'map_row_stride': map_row_stride}
+    for k, v in taps.items():
+        arrays['stat_' + k] = v
+    if isinstance(out, tuple):
+        maps, coords = out
+        arrays['coords'] = coords.numpy()
+    else:
+        maps = out
+    maps = maps.numpy()
+    arrays['maps_sub'] = maps[:, :, ::map_row_stride, :]
+    flat = maps.reshape(maps.shape[0], maps.shape[1], -1)
+    arrays['maps_argmax'] = flat.argmax(2).astype(np.int32)
+    arrays['maps_max'] = flat.max(2)
+    arrays['maps_sum'] = flat.astype(np.float64).sum(2)
+    save('hrnet_%s.npz' % tag, **arrays)
+
+
+def golden_decode(ref):
+    ip = ref['img_proc']
+    g = rng(3)
+    hm = g.standard_normal((3, 33, 64, 64), dtype=np.float32)
+    # adversarial maps: duplicated maxima, all-negative, all-zero, plateau, single spike, non-square
+    hm[0, 0, 10, 20] = hm[0, 0, 40, 5] = 9.0
+    hm[0, 1] = -np.abs(hm[0, 1]) - 0.1
+    hm[0, 2] = 0.0
+    hm[0, 3, :, :] = 1.5
+    hm[0, 4] = 0.0
+    hm[0, 4, 63, 63] = 2.0
+    hm[0, 5, 0, 0] = hm[0, 5, 0, 1] = 7.0
+    pos = np.abs(g.standard_normal((2, 5, 12, 20), dtype=np.float32)) + 0.01   # H != W, positive
+    arrays = {'hm': hm, 'pos': pos}
+    for tag, arr in (('hm', hm), ('pos', pos)):
+        p, m = ip.get_max_preds(arr.copy())
+        arrays[tag + '_max_preds'], arrays[tag + '_max_vals'] = p, m
+        p, m = ip.soft_arg_max_np(arr.copy())       # divides its argument in place upstream
+        arrays[tag + '_softnp_preds'], arrays[tag + '_softnp_vals'] = p, m
+        # upstream soft_arg_max is CUDA-only (img_proc.py:696-700); run it unmodified on CPU by
+        # pointing the two CUDA-only names it touches at their CPU equivalents
+        import torch.cuda.comm  # noqa: F401  (lazy sub-module in current torch)
+        saved = (torch.cuda.FloatTensor, torch.cuda.comm.broadcast)
+        torch.cuda.FloatTensor = torch.FloatTensor
+        torch.cuda.comm.broadcast = lambda t, devices: [t]
+        try:
+            p, m = ip.soft_arg_max(torch.from_numpy(arr.copy()))
+        finally:
+            torch.cuda.FloatTensor, torch.cuda.comm.broadcast = saved
+        arrays[tag + '_soft_preds'], arrays[tag + '_soft_vals'] = p.numpy(), m.numpy()
+    save('decode.npz', **arrays)
+
+
+def golden_affine(ref):
+    ip = ref['img_proc']
+    g = rng(5)
+    n = 24
+    boxes = np.stack([g.uniform(0, 1100, n), g.uniform(0, 300, n)], 1)
+    boxes = np.concatenate([boxes, boxes + np.stack([g.uniform(20, 420, n), g.uniform(15, 260, n)], 1)], 1)
+    ars = np.where(np.arange(n) % 3 == 0, 256 / 192, 1.0)
+    centers, scales, bbs, tinv, tfwd, screens = [], [], [], [], [], []
+    coords = g.uniform(0, 1, (n, 33, 2)).astype(np.float32)
+    for i in range(n):
+        ret = ip.modify_bbox(boxes[i], ars[i])
+        res = (256, 256) if ars[i] == 1.0 else (192, 256)   # (width, height)
+        centers.append(ret['c']); scales.append(ret['s']); bbs.append(ret['bbox'])
+        ti = ip.get_affine_transform(ret['c'], ret['s'], 0., (res[1], res[0]), inv=1)
+        tf = ip.get_affine_transform(ret['c'], ret['s'], 0., (res[1], res[0]), inv=0)
+        local = coords[i].copy()
+        local *= np.array(res).reshape(1, 2)
+        screens.append(ip.affine_transform_modified(local, ti))
+        tinv.append(ti); tfwd.append(tf)
+    save('affine.npz', boxes=boxes, ars=ars, centers=np.array(centers), scales=np.array(scales),
+         bbox_resize=np.array(bbs), trans_inv=np.array(tinv), trans_fwd=np.array(tfwd),
+         coords=coords, screen=np.array(screens))
+
+
+def golden_lifter(ref):
+    for tag, cfgs in (('demo', configs.demo_cfgs()), ('tiny', configs.tiny_cfgs())):
+        model = ref['fcmodel'].get_fc_model(1, cfgs, cfgs['FCModel']['input_size'],
+                                            cfgs['FCModel']['output_size']).eval()
+        sd = lifter_ref.make_weights(cfgs, 11)
+        model.load_state_dict(sd)
+        stats = lifter_ref.make_stats(cfgs, 12)
+        g = rng(13)
+        n = 19
+        kpts = stats['mean_in'] + stats['std_in'] * g.standard_normal((n, cfgs['FCModel']['input_size']))
+        # the upstream dtype chain of EgoNet.lift_2d_to_3d (egonet.py:473-485)
+        nop = ref['operations']
+        data = nop.normalize_1d(kpts, stats['mean_in'], stats['std_in']).astype(np.float32)
+        with torch.no_grad():
+            raw = model(torch.from_numpy(data)).numpy()
+        pred = nop.unnormalize_1d(raw, stats['mean_out'], stats['std_out'])
+        save('lifter_%s.npz' % tag, kpts=kpts, raw=raw, kpts_3d=pred.reshape(n, -1, 3),
+             digest=hrnet_ref.weights_digest(sd))
+
+
+def _cuboid(l, h, w):
+    x = np.array([l, l, l, l, 0, 0, 0, 0]) - l / 2
+    y = np.array([0, h, 0, h, 0, h, 0, h]) - h
+    z = np.array([w, w, 0, 0, w, w, 0, 0]) - w / 2
+    c = np.array([x, y, z])
+    par = np.array([1, 3, 5, 7, 1, 2, 3, 4, 1, 2, 5, 6]) - 1
+    chi = np.array([2, 4, 6, 8, 5, 6, 7, 8, 3, 4, 7, 8]) - 1
+    seg = c[:, chi] - c[:, par]
+    return np.hstack([c, c[:, par] + 0.332 * seg, c[:, par] + 0.667 * seg]).T   # [32,3]
+
+
+def golden_pose(ref):
+    from scipy.spatial.transform import Rotation
+    ego = ref['egonet'].EgoNet.__new__(ref['egonet'].EgoNet)   # methods only use their arguments
+    g = rng(7)
+    n = 64
+    preds = np.zeros((n, 32, 3))
+    true_angles = np.zeros((n, 3))
+    for i in range(n):
+        l, h, w = g.uniform(3, 5), g.uniform(1.2, 2), g.uniform(1.4, 2)
+        ry, rx, rz = g.uniform(-np.pi, np.pi), g.uniform(-0.3, 0.3), g.uniform(-0.3, 0.3)
+        if i < 4:
+            ry, rx, rz = [(0.7, 0, 0), (-2.5, 0.1, 0.05), (3.0, 0, 0), (0, 0, 0)][i]
+        R = Rotation.from_euler('yxz', [ry, rx, rz]).as_matrix()
+        pts = (R @ _cuboid(l, h, w).T).T + np.array([g.uniform(-20, 20), g.uniform(0, 3), g.uniform(5, 60)])
+        noise = 0.0 if i < 8 else (0.05 if i < 40 else 0.4)
+        preds[i] = pts + noise * g.standard_normal((32, 3))
+        true_angles[i] = [rx, ry, rz]
+    # two reflected (mirrored) clouds force the det(R) < 0 branch of the Kabsch solve
+    preds[-1, :, 0] *= -1
+    preds[-2, :, 2] *= -1
+    angles, trans = ego.get_6d_rep(preds.reshape(n, -1))
+    templates = np.array([ego.get_template(p) for p in preds])
+    Rs = np.array([ref['transformation'].compute_rigid_transform(templates[i], preds[i].T)[0] for i in range(n)])
+    a_trans = ego.get_observation_angle_trans(angles, trans)
+    kx = g.uniform(0, 1242, n)
+    kpts = [np.concatenate([[kx[i]], g.uniform(0, 375, 65)]).reshape(1, 66) for i in range(n)]
+    a_proj = ego.get_observation_angle_proj(angles, kpts, egonet_ref.KITTI_K)
+    save('pose.npz', preds=preds, true_angles=true_angles, angles=angles, translation=trans,
+         templates=templates, R=Rs, alpha_trans=a_trans, alpha_proj=a_proj,
+         kpts=np.concatenate(kpts, 0), K=egonet_ref.KITTI_K,
+         ka_trans=ego.get_observation_angle_trans(np.array([[0, 0.7, 0.]]), np.array([[2., 1, 20]])),
+         ka_proj=ego.get_observation_angle_proj(np.array([[0, 0.7, 0.]]), [np.array([[700.0]])],
+                                                np.array([[707., 0, 604], [0, 707, 180], [0, 0, 1]])))
+
+
+def golden_pipeline(ref):
+    """EgoNet.get_keypoints -> lift_2d_to_3d -> gather_lifting_results on the tiny config."""
+    cfgs = configs.tiny_cfgs()
+    ego = ref['egonet'].EgoNet(cfgs, pre_trained=False).eval()
+    hc_sd = hrnet_ref.make_weights(cfgs, 1)
+    l_sd = lifter_ref.make_weights(cfgs, 11)
+    ego.HC.load_state_dict(hc_sd)
+    ego.L.load_state_dict(l_sd)
+    ego.LS = lifter_ref.make_stats(cfgs, 12)
+    n = 6
+    crops = egonet_ref.synth_crops(n, cfgs, 0)
+    recs = egonet_ref.synth_boxes(n, cfgs, 2)
+    paths = ['img_a.png'] * 2 + ['img_b.png'] * 3 + ['img_c.png']
+    for r, p in zip(recs, paths):
+        r.update(path=p, label=-1, score=-1.0)
+    with torch.no_grad():
+        records = ego.get_keypoints(crops, [dict(r) for r in recs], is_cuda=False)
+        records = ego.lift_2d_to_3d(records, cuda=False)
+    out = {'kpts_2d': [], 'kpts_3d': [], 'euler': [], 'translation': [], 'alpha_trans': [], 'alpha_proj': []}
+    for p in ('img_a.png', 'img_b.png', 'img_c.png'):
+        rec = records[p]
+        rec['K'] = egonet_ref.KITTI_K
+        for mode in ('trans', 'proj'):
+            rec = ego.gather_lifting_results(rec, None, None, alpha_mode=mode)
+            out['alpha_' + mode].append(rec['alphas'].copy())
+        out['kpts_2d'].append(np.concatenate(rec['kpts_2d_pred'], 0))
+        out['kpts_3d'].append(rec['kpts_3d_pred'])
+        out['euler'].append(rec['euler_angles'])
+        out['translation'].append(rec['translation'])
+    save('pipeline_tiny.npz', **{k: np.concatenate(v, 0) for k, v in out.items()},
+         centers=np.array([r['center'] for r in recs]), scales=np.array([r['scale'] for r in recs]))
+
+
+def main():
+    ref = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    golden_hrnet(ref, 'tiny', configs.tiny_cfgs(), 3, 1, 0, 1)
+    golden_hrnet(ref, 'tiny_heatmap', configs.tiny_cfgs('heatmap'), 2, 1, 0, 1)
+    golden_hrnet(ref, 'ped', configs.ped_cfgs(), 1, 1, 0, 8)
+    golden_hrnet(ref, 'demo', configs.demo_cfgs(), 2, 1, 0, 4)
+    golden_decode(ref)
+    golden_affine(ref)
+    golden_lifter(ref)
+    golden_pose(ref)
+    golden_pipeline(ref)
+    import cv2, scipy
+    with open(os.path.join(HERE, 'versions.json'), 'w') as f:
+        json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,
+                   'cv2': cv2.__version__, 'python': sys.version.split()[0],
+                   'reference': 'Nicholasli1995/EgoNet @ 13e3758 (/root/reference)'}, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
