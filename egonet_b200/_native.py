@@ -1,0 +1,110 @@
+"""ctypes binding of ``include/egonet_b200.h`` (the C-ABI drop-in boundary).
+
+PyTorch is used for device memory and streams only; every computation goes
+through ``libegonet_b200.so``.  There is deliberately no fallback: if the
+library is missing, or a compute entry is called on a machine without an
+sm_100 device, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libegonet_b200.so')
+
+EGN_MAX_BRANCHES = 4
+HEAD_HEATMAP, HEAD_COORDINATES = 0, 1
+PREC_FP32, PREC_FP16 = 0, 1
+CONV_AUTO, CONV_SIMT = 0, 1
+SOFTARGMAX_SOFTMAX, SOFTARGMAX_SUM = 0, 1
+ALPHA_TRANS, ALPHA_PROJ = 0, 1
+
+
+class EgnError(RuntimeError):
+    """A C-ABI entry returned a negative status (message from egn_last_error)."""
+
+
+class HRNetCfg(ctypes.Structure):
+    _fields_ = [
+        ('in_channels', c_int), ('input_w', c_int), ('input_h', c_int),
+        ('heatmap_w', c_int), ('heatmap_h', c_int), ('num_joints', c_int),
+        ('head_type', c_int), ('final_conv_kernel', c_int), ('num_stages', c_int),
+        ('stage_modules', c_int * 3), ('stage_branches', c_int * 3),
+        ('stage_blocks', (c_int * EGN_MAX_BRANCHES) * 3),
+        ('stage_channels', (c_int * EGN_MAX_BRANCHES) * 3),
+        ('precision', c_int), ('conv_impl', c_int), ('keep_taps', c_int),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/egonet_b200.h
+SIGNATURES = {
+    'egn_version': (c_int, []),
+    'egn_last_error': (c_char_p, []),
+    'egn_device_ok': (c_int, []),
+    'egn_hrnet_create': (c_int, [POINTER(HRNetCfg), POINTER(c_void_p)]),
+    'egn_hrnet_destroy': (None, [c_void_p]),
+    'egn_hrnet_num_weights': (c_int, [c_void_p]),
+    'egn_hrnet_weight_key': (c_char_p, [c_void_p, c_int]),
+    'egn_hrnet_weight_shape': (c_int, [c_void_p, c_int, POINTER(c_int64)]),
+    'egn_hrnet_set_weight': (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    'egn_hrnet_finalize': (c_int, [c_void_p]),
+    'egn_hrnet_workspace_bytes': (c_size_t, [c_void_p, c_int]),
+    'egn_hrnet_forward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
+    'egn_hrnet_read_tap': (c_int, [c_void_p, c_char_p, c_int, c_void_p, c_void_p, POINTER(c_int), c_void_p]),
+    'egn_hrnet_macs_per_crop': (c_int64, [c_void_p]),
+    'egn_hrnet_num_launches': (c_int, [c_void_p]),
+    'egn_hrnet_num_tc_launches': (c_int, [c_void_p]),
+    'egn_hrnet_act_bytes_per_crop': (c_int64, [c_void_p]),
+    'egn_hrnet_weight_bytes': (c_int64, [c_void_p]),
+    'egn_argmax2d': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_soft_argmax2d': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'egn_local_to_screen': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p]),
+    'egn_lifter_create': (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    'egn_lifter_destroy': (None, [c_void_p]),
+    'egn_lifter_set_weight': (c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int]),
+    'egn_lifter_set_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_lifter_finalize': (c_int, [c_void_p]),
+    'egn_lifter_workspace_bytes': (c_size_t, [c_void_p, c_int]),
+    'egn_lifter_forward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'egn_pose_solve': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double, c_int,
+                               c_void_p, c_void_p, c_void_p]),
+    'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the native library; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EgnError('native library %s is missing: run `python -m egonet_b200.build` '
+                           '(there is no Python/CPU fallback)' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EgnError('egonet_b200 error %d: %s' % (rc, lib().egn_last_error().decode()))
+
+
+def current_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device/host pointer of a contiguous tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return c_void_p(t.data_ptr())

@@ -1,0 +1,368 @@
+// CUDA-core kernels of the HC network: generic fused conv (implicit GEMM),
+// stem conv, cross-resolution fuse, head tail, layout conversion.
+//
+// These are (1) the fp32 "exact" precision mode that holds the 1e-4 parity bound
+// against the reference's fp32 arithmetic, (2) the on-device comparator for the
+// tcgen05 kernels in conv_tc.cu (same layouts, same folded weights, same
+// epilogue), and (3) the home of the shapes tensor cores do not fit (stem Cin=3,
+// the 4x4 head tail).  upstream: libs/model/heatmapModel/hrnet.py (conv+BN+ReLU
+// chains :63-133, fuse :282-300, heads :427-467,601-608).
+#include "common.h"
+#include "kernels.h"
+
+namespace egn {
+
+// ---------------------------------------------------------------------------
+// element helpers
+// ---------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ void load4(const float* p, float v[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  static __device__ __forceinline__ void store4(float* p, const float v[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Elem<__half> {
+  static __device__ __forceinline__ void load4(const __half* p, float v[4]) {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    const __half2 a = *reinterpret_cast<const __half2*>(&q.x);
+    const __half2 b = *reinterpret_cast<const __half2*>(&q.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store4(__half* p, const float v[4]) {
+    const __half2 a = __floats2half2_rn(v[0], v[1]);
+    const __half2 b = __floats2half2_rn(v[2], v[3]);
+    uint2 q;
+    q.x = *reinterpret_cast<const uint32_t*>(&a);
+    q.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = q;
+  }
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+// ---------------------------------------------------------------------------
+// generic conv: 64 pixels x 64 output channels per CTA, K chunks of 16
+// ---------------------------------------------------------------------------
+constexpr int CBM = 64, CBN = 64, CBK = 16, CTHREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(CTHREADS)
+conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
+  __shared__ __align__(16) float As[CBK][CBM + 4];
+  __shared__ __align__(16) float Bs[CBK][CBN];
+  const int t = threadIdx.x;
+  const int64_t M = (int64_t)p.B * p.OH * p.OW;
+  const int64_t m0 = (int64_t)blockIdx.x * CBM;
+  const int n0 = blockIdx.y * CBN;
+  const T* __restrict__ in = static_cast<const T*>(p.in);
+
+  // A-load role: pixel lp = t/4, channel quad lq = t%4
+  const int lp = t >> 2, lq = t & 3;
+  const int64_t lm = m0 + lp;
+  const bool lvalid = lm < M;
+  int lb = 0, loh = 0, low = 0;
+  if (lvalid) {
+    lb = (int)(lm / ((int64_t)p.OH * p.OW));
+    const int r = (int)(lm - (int64_t)lb * p.OH * p.OW);
+    loh = r / p.OW;
+    low = r - loh * p.OW;
+  }
+  // B-load role: row t/16, float4 column t%16
+  const int bk = t >> 4, bc = (t & 15) * 4;
+  // compute role
+  const int tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int taps = p.ksize * p.ksize;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int r = tap / p.ksize, s = tap - r * p.ksize;
+    const int ih = loh * p.stride + r - p.pad, iw = low * p.stride + s - p.pad;
+    const bool pv = lvalid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+    const T* src = in + (((int64_t)lb * p.H + ih) * p.W + iw) * p.Cin_p;
+    const float* wt = wp + (size_t)tap * p.Cin_p * p.Cout_p;
+    for (int c0 = 0; c0 < p.Cin_p; c0 += CBK) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pv) Elem<T>::load4(src + c0 + lq * 4, a);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) As[lq * 4 + c][lp] = a[c];
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + bc < p.Cout_p) b = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(c0 + bk) * p.Cout_p + n0 + bc));
+      *reinterpret_cast<float4*>(&Bs[bk][bc]) = b;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CBK; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float aa[4] = {av.x, av.y, av.z, av.w};
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias (+ residual) (+ ReLU), 4 consecutive channels per store
+  const int n = n0 + tx * 4;
+  if (n >= p.Cout_p) return;
+  const float4 bias = *reinterpret_cast<const float4*>(p.bias + n);
+  const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
+  T* __restrict__ out = static_cast<T*>(p.out);
+  const T* __restrict__ res = static_cast<const T*>(p.res);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
+    if (res) {
+      float rv[4];
+      Elem<T>::load4(res + m * p.Cout_p + n, rv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += rv[j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.heatmap || p.coord_maps) {
+      const int b = (int)(m / ((int64_t)p.OH * p.OW));
+      const int rr = (int)(m - (int64_t)b * p.OH * p.OW);
+      const int oh = rr / p.OW, ow = rr - oh * p.OW;
+      if (p.heatmap) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.Cout) p.heatmap[(((int64_t)b * p.Cout + n + j) * p.OH + oh) * p.OW + ow] = v[j];
+      }
+      if (p.coord_maps) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n + j == p.Cout) v[j] = p.xs[ow];
+          if (n + j == p.Cout + 1) v[j] = p.ys[oh];
+        }
+      }
+    }
+    Elem<T>::store4(out + m * p.Cout_p + n, v);
+  }
+}
+
+int launch_conv_simt(Dtype dt, const ConvArgs& a, const float* w_packed, cudaStream_t st) {
+  const int64_t M = (int64_t)a.B * a.OH * a.OW;
+  dim3 grid((unsigned)ceil_div64(M, CBM), (unsigned)ceil_div(a.Cout_p, CBN));
+  if (dt == Dtype::F32)
+    conv_simt_kernel<float><<<grid, CTHREADS, 0, st>>>(a, w_packed);
+  else
+    conv_simt_kernel<__half><<<grid, CTHREADS, 0, st>>>(a, w_packed);
+  EGN_LAUNCH_CHECK("conv_simt_kernel");
+  return EGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// stem conv1: fp32 NCHW input, 3x3 s2 p1, Cin in {3,5} -> 64 channels NHWC
+// ---------------------------------------------------------------------------
+constexpr int ST = 16;              // 16x16 output pixels per CTA
+constexpr int SP = 2 * ST + 1;      // input patch edge
+constexpr int STEM_MAX_CIN = 5;
+
+template <typename T>
+__global__ void __launch_bounds__(ST * ST)
+stem_kernel(StemArgs p) {
+  extern __shared__ float sm[];
+  float* patch = sm;                                  // [Cin][SP][SP]
+  float* w = sm + p.Cin * SP * SP;                    // [9*Cin][64]
+  float* bias = w + 9 * p.Cin * 64;                   // [64]
+  const int t = threadIdx.x;
+  const int tiles_x = (p.OW + ST - 1) / ST;
+  const int b = blockIdx.y;
+  const int oy0 = (blockIdx.x / tiles_x) * ST, ox0 = (blockIdx.x % tiles_x) * ST;
+  const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+  for (int e = t; e < p.Cin * SP * SP; e += ST * ST) {
+    const int c = e / (SP * SP), r = (e / SP) % SP, q = e % SP;
+    const int iy = iy0 + r, ix = ix0 + q;
+    float v = 0.f;
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+      v = __ldg(p.x + (((int64_t)b * p.Cin + c) * p.H + iy) * p.W + ix);
+    patch[e] = v;
+  }
+  for (int e = t; e < 9 * p.Cin * 64; e += ST * ST) w[e] = __ldg(p.w + e);
+  if (t < 64) bias[t] = __ldg(p.bias + t);
+  __syncthreads();
+  const int ty = t / ST, tx = t % ST;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy >= p.OH || ox >= p.OW) return;
+  T* out = static_cast<T*>(p.out) + (((int64_t)b * p.OH + oy) * p.OW + ox) * 64;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int c = 0; c < p.Cin; ++c) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const float xv = patch[(c * SP + 2 * ty + r) * SP + 2 * tx + s];
+          const float* wr = w + ((r * 3 + s) * p.Cin + c) * 64 + pass * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(acc[q * 4 + j] + bias[pass * 16 + q * 4 + j], 0.f);
+      Elem<T>::store4(out + pass * 16 + q * 4, v);
+    }
+  }
+}
+
+int launch_stem(Dtype dt, const StemArgs& a, cudaStream_t st) {
+  EGN_REQUIRE(a.Cin >= 1 && a.Cin <= STEM_MAX_CIN, "stem: unsupported input channel count %d", a.Cin);
+  const size_t smem = ((size_t)a.Cin * SP * SP + 9 * a.Cin * 64 + 64) * sizeof(float);
+  dim3 grid(ceil_div(a.OW, ST) * ceil_div(a.OH, ST), a.B);
+  if (dt == Dtype::F32) {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_kernel<float><<<grid, ST * ST, smem, st>>>(a);
+  } else {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_kernel<__half><<<grid, ST * ST, smem, st>>>(a);
+  }
+  EGN_LAUNCH_CHECK("stem_kernel");
+  return EGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fuse: out = relu(sum_j up(term_j)), 4 channels per thread
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void fuse_kernel(FuseArgs p) {
+  const int cq = p.Cp / 4;
+  const int64_t total = (int64_t)p.B * p.H * p.W * cq;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cq) * 4;
+    int64_t pix = e / cq;
+    const int w = (int)(pix % p.W);
+    pix /= p.W;
+    const int h = (int)(pix % p.H);
+    const int b = (int)(pix / p.H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= p.nterms) break;
+      const int sh = p.shift[j];
+      const int Hs = p.H >> sh, Ws = p.W >> sh;
+      const T* src = static_cast<const T*>(p.term[j]) +
+                     (((int64_t)b * Hs + (h >> sh)) * Ws + (w >> sh)) * p.Cp + c;
+      float v[4];
+      Elem<T>::load4(src, v);
+      if (j == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = v[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += v[q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = fmaxf(acc[q], 0.f);
+    Elem<T>::store4(static_cast<T*>(p.out) + (((int64_t)b * p.H + h) * p.W + w) * p.Cp + c, acc);
+  }
+}
+
+int launch_fuse(Dtype dt, const FuseArgs& a, cudaStream_t st) {
+  const int64_t total = (int64_t)a.B * a.H * a.W * (a.Cp / 4);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 16);
+  if (dt == Dtype::F32)
+    fuse_kernel<float><<<blocks, threads, 0, st>>>(a);
+  else
+    fuse_kernel<__half><<<blocks, threads, 0, st>>>(a);
+  EGN_LAUNCH_CHECK("fuse_kernel");
+  return EGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// head tail: full-map valid conv + bias + sigmoid; one CTA per crop
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_tail_kernel(HeadTailArgs p) {
+  extern __shared__ float xin[];
+  const T* in = static_cast<const T*>(p.in) + (int64_t)blockIdx.x * p.L;
+  for (int e = threadIdx.x; e < p.L; e += blockDim.x) xin[e] = Elem<T>::to_f(in[e]);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < p.Cout; j += blockDim.x / 32) {
+    const float* w = p.w + (size_t)j * p.L;
+    float s = 0.f;
+    for (int e = lane; e < p.L; e += 32) s = fmaf(xin[e], __ldg(w + e), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += p.bias[j];
+      if (p.logits) p.logits[(int64_t)blockIdx.x * p.Cout + j] = s;
+      if (p.coords) p.coords[(int64_t)blockIdx.x * p.Cout + j] = 1.0f / (1.0f + expf(-s));
+    }
+  }
+}
+
+int launch_head_tail(Dtype dt, const HeadTailArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)a.L * sizeof(float);
+  EGN_REQUIRE(smem <= 200 * 1024, "head tail: map too large (%d elements)", a.L);
+  if (dt == Dtype::F32) {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_tail_kernel<float><<<a.B, 256, smem, st>>>(a);
+  } else {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_tail_kernel<__half><<<a.B, 256, smem, st>>>(a);
+  }
+  EGN_LAUNCH_CHECK("head_tail_kernel");
+  return EGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// NHWC (padded) -> fp32 NCHW, for debug taps
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int H,
+                                    int W, int Cp, int C) {
+  const int64_t total = (int64_t)B * C * H * W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(e % W);
+    int64_t r = e / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    out[e] = Elem<T>::to_f(in[(((int64_t)b * H + h) * W + w) * Cp + c]);
+  }
+}
+
+int launch_nhwc_to_nchw(Dtype dt, const void* in, float* out, int B, int H, int W, int Cp, int C,
+                        cudaStream_t st) {
+  const int64_t total = (int64_t)B * C * H * W;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16);
+  if (dt == Dtype::F32)
+    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(in), out, B, H, W, Cp, C);
+  else
+    nhwc_to_nchw_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), out, B, H, W, Cp, C);
+  EGN_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return EGN_OK;
+}
+
+}  // namespace egn

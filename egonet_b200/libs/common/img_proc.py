@@ -1,0 +1,144 @@
+"""B200-native drop-ins for the hot-path functions of the reference's
+``libs/common/img_proc.py``: the three heat-map decoders and the crop geometry.
+
+Decoders take a CUDA fp32 tensor ``[B, K, H, W]`` and return CUDA tensors (the
+reference's ``get_max_preds`` / ``soft_arg_max_np`` take numpy arrays on the host
+after a full D2H copy of the maps; here the maps never leave the device).
+"""
+import numpy as np
+import torch
+
+from ... import _native as N
+
+SIZE = 200.0  # [img_proc.py:14]
+
+
+def _maps(batch_heatmaps):
+    if not isinstance(batch_heatmaps, torch.Tensor):
+        raise TypeError('batch_heatmaps must be a CUDA torch.Tensor (no host path; the reference '
+                        'version of this function takes numpy)')
+    if batch_heatmaps.dim() != 4:
+        raise AssertionError('batch_images should be 4-ndim')
+    if not batch_heatmaps.is_cuda:
+        raise RuntimeError('native decoders have no CPU path: input must be a CUDA tensor')
+    return batch_heatmaps.detach().float().contiguous()
+
+
+def get_max_preds(batch_heatmaps, return_index=False):
+    """[img_proc.py:608-637] hard arg-max -> (preds [B,K,2] float32, maxvals [B,K,1])."""
+    hm = _maps(batch_heatmaps)
+    B, K, H, W = hm.shape
+    preds = torch.empty((B, K, 2), device=hm.device, dtype=torch.float32)
+    maxvals = torch.empty((B, K, 1), device=hm.device, dtype=torch.float32)
+    idx = torch.empty((B, K), device=hm.device, dtype=torch.int32)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().egn_argmax2d(N.ptr(hm), B, K, H, W, N.ptr(idx), N.ptr(preds), N.ptr(maxvals),
+                                     N.current_stream()))
+    return (preds, maxvals, idx) if return_index else (preds, maxvals)
+
+
+def _soft(batch_heatmaps, mode):
+    hm = _maps(batch_heatmaps)
+    B, K, H, W = hm.shape
+    preds = torch.empty((B, K, 2), device=hm.device, dtype=torch.float32)
+    maxvals = torch.empty((B, K, 1), device=hm.device, dtype=torch.float32)
+    with torch.cuda.device(hm.device):
+        N.check(N.lib().egn_soft_argmax2d(N.ptr(hm), B, K, H, W, mode, N.ptr(preds), N.ptr(maxvals),
+                                          N.current_stream()))
+    return preds, maxvals
+
+
+def soft_arg_max(batch_heatmaps):
+    """[img_proc.py:678-707] soft-max normalised expectation, raw-map max, no mask."""
+    return _soft(batch_heatmaps, N.SOFTARGMAX_SOFTMAX)
+
+
+def soft_arg_max_np(batch_heatmaps):
+    """[img_proc.py:639-676] sum-normalised expectation, zeroed where max <= 0
+    (does not modify its argument, unlike the reference's in-place division)."""
+    return _soft(batch_heatmaps, N.SOFTARGMAX_SUM)
+
+
+# ---- crop geometry (host, float64 numpy; a few flops per box) -----------------
+def enlarge_bbox(left, top, right, bottom, enlarge):
+    """[img_proc.py:437-451]"""
+    w, h = (right - left) * enlarge[0], (bottom - top) * enlarge[1]
+    cx, cy = (left + right) / 2, (top + bottom) / 2
+    return [cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h]
+
+
+def resize_bbox(left, top, right, bottom, target_ar=1.):
+    """[img_proc.py:411-435]"""
+    w, h = right - left, bottom - top
+    cx, cy = (left + right) / 2, (top + bottom) / 2
+    if h / w > target_ar:
+        nw = h * (1 / target_ar)
+        box = [cx - 0.5 * nw, top, cx + 0.5 * nw, bottom]
+    else:
+        nh = w * target_ar
+        box = [left, cy - 0.5 * nh, right, cy + 0.5 * nh]
+    return {'bbox': box, 'c': np.array([cx, cy]),
+            's': np.array([(box[2] - box[0]) / SIZE, (box[3] - box[1]) / SIZE])}
+
+
+def modify_bbox(bbox, target_ar, enlarge=1.1):
+    """[img_proc.py:453-459]"""
+    b = enlarge_bbox(bbox[0], bbox[1], bbox[2], bbox[3], [enlarge, enlarge])
+    return resize_bbox(b[0], b[1], b[2], b[3], target_ar=target_ar)
+
+
+def get_affine_transform(center, scale, rot, output_size, shift=None, inv=0):
+    """[img_proc.py:26-64] host-side crop affine for ``cv2.warpAffine`` (crop_instances
+    is host code upstream as well).  Three float32 reference points per side exactly
+    as upstream builds them, then the exact 3-point affine in float64 (what
+    ``cv2.getAffineTransform`` computes).  The device path uses
+    ``egn_local_to_screen`` for the inverse transform instead."""
+    center = np.asarray(center, dtype=np.float64)
+    src_w = float(np.asarray(scale, dtype=np.float64)[0]) * SIZE
+    dst_h, dst_w = output_size
+    ang = np.pi * rot / 180
+    direction = np.array([src_w * 0.5 * np.sin(ang), src_w * -0.5 * np.cos(ang)])
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0] = center
+    src[1] = center + direction
+    dst[0] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1] = np.array([dst_w * 0.5, dst_h * 0.5]) + np.array([0, dst_w * -0.5], np.float32)
+    for pts in (src, dst):
+        d = pts[0] - pts[1]
+        pts[2] = pts[1] + np.array([-d[1], d[0]], dtype=np.float32)
+    a, b = (dst, src) if inv else (src, dst)
+    A = np.hstack([a.astype(np.float64), np.ones((3, 1))])
+    return np.linalg.solve(A, b.astype(np.float64)).T
+
+
+def local_to_screen(coords, centers, scales, resolution, rots=None):
+    """Batched form of the per-instance loop in ``EgoNet.get_keypoints``
+    [egonet.py:436-453]: ``get_affine_transform(..., inv=1)`` [img_proc.py:26-64]
+    followed by ``affine_transform_modified`` [img_proc.py:71-78].
+
+    coords: CUDA fp32 [N,K,2] in (0,1); centers/scales: [N,2] fp64 (tensor or
+    array); resolution = (width, height).  Returns CUDA fp64 [N,K,2]."""
+    if not coords.is_cuda:
+        raise RuntimeError('native local_to_screen has no CPU path')
+    dev = coords.device
+    c = coords.detach().float().contiguous()
+    n, k = c.shape[0], c.shape[1]
+    ce = torch.as_tensor(np.asarray(centers, dtype=np.float64) if not torch.is_tensor(centers) else centers,
+                         dtype=torch.float64).to(dev).contiguous()
+    sc = torch.as_tensor(np.asarray(scales, dtype=np.float64) if not torch.is_tensor(scales) else scales,
+                         dtype=torch.float64).to(dev).contiguous()
+    ro = None
+    if rots is not None:
+        ro = torch.as_tensor(np.asarray(rots, dtype=np.float64), dtype=torch.float64).to(dev).contiguous()
+    out = torch.empty((n, k, 2), device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        N.check(N.lib().egn_local_to_screen(N.ptr(c), N.ptr(ce), N.ptr(sc), N.ptr(ro), n, k,
+                                            int(resolution[0]), int(resolution[1]), N.ptr(out),
+                                            N.current_stream()))
+    return out
+
+
+def to_npy(tensor):
+    """[img_proc.py:722-728]"""
+    return tensor if isinstance(tensor, np.ndarray) else tensor.data.cpu().numpy()

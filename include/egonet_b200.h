@@ -1,0 +1,226 @@
+/*
+ * egonet_b200 -- C ABI of the B200-native EgoNet per-crop inference hot path.
+ *
+ * The upstream project (Nicholasli1995/EgoNet) is pure Python/PyTorch and has no
+ * FFI of its own; the boundary it exposes for this path is the Python class
+ * surface of libs/model.  This header is the C level
+ * inserted one step below that surface: each entry point replaces the body of
+ * one reference function, named in its comment (paths relative to the upstream
+ * repository root).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns EGN_OK (0) or a negative egn_status; the message
+ *     of the last failure on the calling thread is egn_last_error().
+ *   - all device pointers are caller-owned (e.g. torch tensors); the library
+ *     never frees or retains them past the call.  Handles own only their
+ *     repacked weights.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     entry point synchronises the device except egn_*_create/finalize/destroy
+ *     and the *_host convenience calls.
+ *   - there is no CPU fallback: on a machine without an sm_100 device every
+ *     compute entry returns EGN_ERR_NO_DEVICE.
+ */
+#ifndef EGONET_B200_H_
+#define EGONET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGN_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define EGN_API __attribute__((visibility("default")))
+#else
+#define EGN_API
+#endif
+
+typedef enum {
+  EGN_OK = 0,
+  EGN_ERR_INVALID = -1,   /* bad argument / unsupported configuration        */
+  EGN_ERR_NO_DEVICE = -2, /* no CUDA device, or device is not sm_100         */
+  EGN_ERR_CUDA = -3,      /* a CUDA runtime/driver call failed               */
+  EGN_ERR_STATE = -4,     /* call order violated (e.g. forward before finalize) */
+  EGN_ERR_MISSING = -5,   /* a required weight was never set                 */
+  EGN_ERR_WORKSPACE = -6  /* workspace too small                              */
+} egn_status;
+
+EGN_API int egn_version(void);
+EGN_API const char* egn_last_error(void);
+/* 1 if cuda:current is an sm_100 (B200) device, 0 otherwise. Never fails. */
+EGN_API int egn_device_ok(void);
+
+/* ------------------------------------------------------------------------- */
+/* HC: the HRNet heat-map / coordinate network                               */
+/* replaces libs/model/heatmapModel/hrnet.py:563-614                         */
+/*   (PoseHighResolutionNet.forward and every module it calls)               */
+/* ------------------------------------------------------------------------- */
+
+#define EGN_MAX_BRANCHES 4
+
+typedef enum { EGN_HEAD_HEATMAP = 0, EGN_HEAD_COORDINATES = 1 } egn_head_type;
+
+typedef enum {
+  EGN_PREC_FP32 = 0, /* fp32 storage + fp32 CUDA-core convs: the 1e-4 parity mode */
+  EGN_PREC_FP16 = 1  /* fp16 NHWC storage, fp32 accumulation, tcgen05 tensor cores */
+} egn_precision;
+
+typedef enum {
+  EGN_CONV_AUTO = 0, /* tcgen05 kernels wherever the layer shape allows (fp16 mode) */
+  EGN_CONV_SIMT = 1  /* force the CUDA-core kernels (debug comparator)            */
+} egn_conv_impl;
+
+/* Mirrors cfgs['heatmapModel'] of the reference YAML (configs/KITTI_inference:demo.yml:72-151). */
+typedef struct {
+  int in_channels;                 /* 3, or 5 with add_xy (hrnet.py:649-659)          */
+  int input_w, input_h;            /* input_size = [w, h]                             */
+  int heatmap_w, heatmap_h;        /* heatmap_size = [w, h]                           */
+  int num_joints;                  /* 33                                              */
+  int head_type;                   /* egn_head_type                                   */
+  int final_conv_kernel;           /* extra.final_conv_kernel (heatmap head), 1 or 3  */
+  int num_stages;                  /* 3 (stage2..stage4)                              */
+  int stage_modules[3];            /* extra.stageN.num_modules                        */
+  int stage_branches[3];           /* extra.stageN.num_branches                       */
+  int stage_blocks[3][EGN_MAX_BRANCHES];   /* extra.stageN.num_blocks                */
+  int stage_channels[3][EGN_MAX_BRANCHES]; /* extra.stageN.num_channels              */
+  int precision;                   /* egn_precision                                   */
+  int conv_impl;                   /* egn_conv_impl                                   */
+  int keep_taps;                   /* 1: never recycle activation buffers so that     */
+                                   /*    egn_hrnet_read_tap works after a forward     */
+} egn_hrnet_cfg;
+
+typedef struct egn_hrnet egn_hrnet;
+
+EGN_API int egn_hrnet_create(const egn_hrnet_cfg* cfg, egn_hrnet** out);
+EGN_API void egn_hrnet_destroy(egn_hrnet* h);
+
+/* Number of state_dict entries the network expects and the i-th key / shape
+ * (same names, shapes and order as PoseHighResolutionNet(cfgs).state_dict(),
+ * hrnet.py:311-469).  shape receives up to 4 dims; returns ndim. */
+EGN_API int egn_hrnet_num_weights(const egn_hrnet* h);
+EGN_API const char* egn_hrnet_weight_key(const egn_hrnet* h, int i);
+EGN_API int egn_hrnet_weight_shape(const egn_hrnet* h, int i, int64_t shape[4]);
+
+/* Copy one fp32 state_dict tensor (HOST pointer, contiguous, torch OIHW for
+ * convs) into the handle.  `*.num_batches_tracked` keys are accepted and
+ * ignored.  Invalidates a previous finalize. */
+EGN_API int egn_hrnet_set_weight(egn_hrnet* h, const char* key, const float* host_data,
+                         const int64_t* shape, int ndim);
+
+/* Fold eval-mode BatchNorm into the convolutions, repack for the kernels,
+ * upload.  Fails with EGN_ERR_MISSING (message names the key) if a tensor was
+ * never set. */
+EGN_API int egn_hrnet_finalize(egn_hrnet* h);
+
+/* Bytes of caller-provided device workspace a forward of `batch` crops needs. */
+EGN_API size_t egn_hrnet_workspace_bytes(const egn_hrnet* h, int batch);
+
+/* x: device fp32 [B, in_channels, input_h, input_w] (NCHW, as the reference feeds HC).
+ * heatmap_out: device fp32 [B, num_joints, heatmap_h, heatmap_w] or NULL.
+ * coords_out : device fp32 [B, num_joints, 2] (coordinate head only) or NULL.
+ * logits_out : device fp32 [B, 2*num_joints] pre-sigmoid values or NULL. */
+EGN_API int egn_hrnet_forward(egn_hrnet* h, const float* x, int batch, float* heatmap_out,
+                      float* coords_out, float* logits_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Debug/parity: copy a named intermediate activation of the LAST forward
+ * (needs keep_taps=1) to device fp32 NCHW `out`.  Names: "stem1", "stem2",
+ * "layer1", "stage<S>.<M>.out<B>", "head2.<K>".  dims receives [C,H,W]. */
+EGN_API int egn_hrnet_read_tap(egn_hrnet* h, const char* name, int batch, const void* workspace,
+                       float* out, int dims[3], void* stream);
+
+/* Introspection for bench/roofline accounting. */
+EGN_API int64_t egn_hrnet_macs_per_crop(const egn_hrnet* h);
+EGN_API int egn_hrnet_num_launches(const egn_hrnet* h);        /* kernels per forward          */
+EGN_API int egn_hrnet_num_tc_launches(const egn_hrnet* h);     /* of which tcgen05 convs       */
+EGN_API int64_t egn_hrnet_act_bytes_per_crop(const egn_hrnet* h); /* algorithmic activation bytes */
+EGN_API int64_t egn_hrnet_weight_bytes(const egn_hrnet* h);
+
+/* ------------------------------------------------------------------------- */
+/* Heat-map decoders (device fp32 NCHW heat-maps [B,K,H,W])                  */
+/* ------------------------------------------------------------------------- */
+
+/* replaces libs/common/img_proc.py:608-637 get_max_preds.
+ * idx [B*K] int32 (flat arg-max, first occurrence on ties) or NULL,
+ * preds [B*K*2] fp32 (x = idx % W, y = floor(idx / W); zeroed where max <= 0),
+ * maxvals [B*K] fp32. */
+EGN_API int egn_argmax2d(const float* hm, int B, int K, int H, int W, int32_t* idx, float* preds,
+                 float* maxvals, void* stream);
+
+typedef enum {
+  EGN_SOFTARGMAX_SOFTMAX = 0, /* img_proc.py:678-707 soft_arg_max (torch)        */
+  EGN_SOFTARGMAX_SUM = 1      /* img_proc.py:639-676 soft_arg_max_np (sum-normalised, max>0 mask) */
+} egn_softargmax_mode;
+
+EGN_API int egn_soft_argmax2d(const float* hm, int B, int K, int H, int W, int mode, float* preds,
+                      float* maxvals, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Local -> screen coordinates                                               */
+/* replaces the per-instance loop of EgoNet.get_keypoints, egonet.py:436-453 */
+/*   (get_affine_transform(inv=1) img_proc.py:26-64 +                        */
+/*    affine_transform_modified img_proc.py:71-78)                           */
+/* coords [N,K,2] fp32 in (0,1); center/scale [N,2] fp64; rot [N] fp64       */
+/* degrees or NULL (= 0); screen [N,K,2] fp64.                               */
+/* ------------------------------------------------------------------------- */
+EGN_API int egn_local_to_screen(const float* coords, const double* center, const double* scale,
+                        const double* rot, int N, int K, int res_w, int res_h,
+                        double* screen, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* L: the 2D->3D lifter                                                      */
+/* replaces EgoNet.lift_2d_to_3d egonet.py:469-486 (normalize_1d,            */
+/* FCModel.forward FCmodel.py:92-105, unnormalize_1d)                        */
+/* ------------------------------------------------------------------------- */
+typedef struct egn_lifter egn_lifter;
+
+EGN_API int egn_lifter_create(int input_size, int output_size, int num_neurons, int num_blocks,
+                      egn_lifter** out);
+EGN_API void egn_lifter_destroy(egn_lifter* l);
+/* state_dict keys of FCModel (FCmodel.py:72-83): w1.*, batch_norm1.*,
+ * res_blocks.<i>.{w1,batch_norm1,w2,batch_norm2}.*, w2.*  (host fp32). */
+EGN_API int egn_lifter_set_weight(egn_lifter* l, const char* key, const float* host_data,
+                          const int64_t* shape, int ndim);
+/* LS statistics (host fp64): mean_in/std_in [input_size], mean_out/std_out [output_size]. */
+EGN_API int egn_lifter_set_stats(egn_lifter* l, const double* mean_in, const double* std_in,
+                         const double* mean_out, const double* std_out);
+EGN_API int egn_lifter_finalize(egn_lifter* l);
+EGN_API size_t egn_lifter_workspace_bytes(const egn_lifter* l, int n);
+/* kpts_2d device fp64 [n, input_size] -> kpts_3d device fp64 [n, output_size];
+ * raw_out (device fp32 [n, output_size], network output before un-normalisation) or NULL. */
+EGN_API int egn_lifter_forward(egn_lifter* l, const double* kpts_2d, int n, double* kpts_3d,
+                       float* raw_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Per-instance pose solve                                                   */
+/* replaces EgoNet.get_6d_rep egonet.py:279-295 (get_template :238-263,      */
+/* compute_rigid_transform transformation.py:99-134, Rotation.as_euler('yxz')*/
+/* egonet.py:274-276) and get_observation_angle_{trans,proj} egonet.py:203-236 */
+/* ------------------------------------------------------------------------- */
+typedef enum { EGN_ALPHA_TRANS = 0, EGN_ALPHA_PROJ = 1 } egn_alpha_mode;
+
+/* kpts_3d device fp64 [N, P, 3], P = 8 or 32.
+ * kpts_2d device fp64 [N, stride_2d] (element 0 of each row = first key-point's
+ *   screen x) -- needed for EGN_ALPHA_PROJ only, else NULL.
+ * fx, cx: K[0,0], K[0,2] (proj mode).
+ * pose_out device fp64 [N, 7] = euler x,y,z | translation x,y,z | alpha.
+ * rot_out  device fp64 [N, 9] row-major Kabsch rotation, or NULL. */
+EGN_API int egn_pose_solve(const double* kpts_3d, int N, int P, const double* kpts_2d, int stride_2d,
+                   double fx, double cx, int alpha_mode, double* pose_out, double* rot_out,
+                   void* stream);
+
+/* replaces the loops of EgoNet.get_observation_angle_trans / _proj (egonet.py:203-236):
+ * alpha[n] = wrap(ry[n] - atan2(-z[n*stride_z], x[n*stride_x] - x_offset) - pi/2).
+ * trans: x = translation[:,0], z = translation[:,2], x_offset = 0.
+ * proj : x = first key-point's screen x, x_offset = K[0,2], z = &K[0,0] with stride_z = 0.
+ * All pointers device fp64. */
+EGN_API int egn_observation_angle(const double* ry, const double* x3d, int stride_x, const double* z3d,
+                          int stride_z, double x_offset, int N, double* alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGONET_B200_H_ */

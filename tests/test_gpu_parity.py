@@ -1,0 +1,313 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).
+
+Every test drives the CUDA path through the C-ABI (via the reference-shaped
+Python mirror) and checks it against (a) golden vectors produced by the upstream
+reference code and/or (b) the CPU oracle on the same seeded inputs.
+Tolerances are written next to each assertion.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import configs, decode_ref, egonet_ref, hrnet_ref, lifter_ref, pose_ref
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from egonet_b200.libs.common import img_proc, transformation
+    from egonet_b200.libs.model.egonet import EgoNet
+    from egonet_b200.libs.model.FCmodel import get_fc_model
+    from egonet_b200.libs.model.heatmapModel.hrnet import get_pose_net
+
+DEV = 'cuda'
+
+
+def cuda(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype else t).to(DEV)
+
+
+# --------------------------------------------------------------------------- decoders
+def test_argmax_index_exact_vs_reference_golden(golden):
+    g = golden('decode.npz')
+    for tag in ('hm', 'pos'):
+        preds, maxvals, idx = img_proc.get_max_preds(cuda(g[tag]), return_index=True)
+        ref_idx = g[tag].reshape(g[tag].shape[0], g[tag].shape[1], -1).argmax(2)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ref_idx)              # index-exact
+        np.testing.assert_array_equal(preds.cpu().numpy(), g[tag + '_max_preds'])
+        np.testing.assert_array_equal(maxvals.cpu().numpy(), g[tag + '_max_vals'])
+
+
+def test_soft_argmax_vs_reference_golden(golden):
+    g = golden('decode.npz')
+    for tag in ('hm', 'pos'):
+        p, m = img_proc.soft_arg_max(cuda(g[tag]))
+        np.testing.assert_allclose(p.cpu().numpy(), g[tag + '_soft_preds'], rtol=0, atol=1e-4)
+        np.testing.assert_array_equal(m.cpu().numpy(), g[tag + '_soft_vals'])
+    # sum-normalised variant: well-conditioned (positive) maps at 1e-4; the zero-mean random
+    # maps divide by a near-zero sum (upstream is ill-conditioned there), so only NaN pattern + loose
+    p, m = img_proc.soft_arg_max_np(cuda(g['pos']))
+    np.testing.assert_allclose(p.cpu().numpy(), g['pos_softnp_preds'], rtol=0, atol=1e-4)
+    p, m = img_proc.soft_arg_max_np(cuda(g['hm']))
+    ref = g['hm_softnp_preds']
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(p.cpu().numpy()), ok)
+    np.testing.assert_allclose(p.cpu().numpy()[ok], ref[ok], rtol=5e-3, atol=5e-3)
+    np.testing.assert_array_equal(m.cpu().numpy(), g['hm_softnp_vals'])
+
+
+def test_argmax_ties_nan_and_large_batch():
+    rng = np.random.Generator(np.random.PCG64(5))
+    hm = rng.standard_normal((64, 33, 64, 64), dtype=np.float32)
+    hm[0, 0] = 0.5                      # full plateau -> index 0
+    hm[1, 1, 7, 9] = np.nan             # numpy: NaN wins
+    hm[2, 2] = -1.0                     # all negative -> masked preds
+    hm[3, 3, 63, 63] = hm[3, 3, 0, 1] = 50.0
+    preds, maxvals, idx = img_proc.get_max_preds(cuda(hm), return_index=True)
+    rp, rm, ri = decode_ref.get_max_preds(hm)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+    np.testing.assert_array_equal(preds.cpu().numpy(), rp)
+    np.testing.assert_array_equal(maxvals.cpu().numpy(), rm)
+    # size-independent property: decoded value at the returned index is the max
+    flat = torch.as_tensor(hm).reshape(64, 33, -1)
+    picked = torch.gather(flat, 2, idx.cpu().long().unsqueeze(-1))
+    assert torch.equal(torch.nan_to_num(picked, nan=7.0), torch.nan_to_num(torch.as_tensor(rm), nan=7.0))
+    e = img_proc.get_max_preds(torch.zeros((0, 33, 64, 64), device=DEV))
+    assert e[0].shape == (0, 33, 2)
+
+
+# --------------------------------------------------------------------------- geometry
+def test_local_to_screen_vs_reference_golden(golden):
+    g = golden('affine.npz')
+    for ar, res in ((1.0, (256, 256)), (256 / 192, (192, 256))):
+        sel = np.where(g['ars'] == ar)[0]
+        out = img_proc.local_to_screen(cuda(g['coords'][sel]), g['centers'][sel], g['scales'][sel], res)
+        np.testing.assert_allclose(out.cpu().numpy(), g['screen'][sel], rtol=0, atol=1e-9)
+
+
+def test_pose_solve_vs_reference_golden(golden):
+    g = golden('pose.npz')
+    for mode in ('trans', 'proj'):
+        pose, rot = transformation.pose_solve(cuda(g['preds']), cuda(g['kpts']), g['K'], mode, want_rotation=True)
+        pose = pose.cpu().numpy()
+        np.testing.assert_allclose(pose[:, :3], g['angles'], rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(pose[:, 3:6], g['translation'])
+        np.testing.assert_allclose(pose[:, 6], g['alpha_' + mode], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(rot.cpu().numpy(), g['R'], rtol=0, atol=1e-10)
+    # 8-point cuboids and empty batches
+    p8 = transformation.pose_solve(cuda(g['preds'][:, :8])).cpu().numpy()
+    a8, t8 = pose_ref.get_6d_rep(g['preds'][:, :8])
+    np.testing.assert_allclose(p8[:, :3], a8, atol=1e-9)
+    assert transformation.pose_solve(torch.zeros((0, 32, 3), device=DEV, dtype=torch.float64)).shape == (0, 7)
+
+
+@pytest.mark.parametrize('tag', ['demo', 'tiny'])
+def test_lifter_vs_reference_golden(golden, tag):
+    g = golden('lifter_%s.npz' % tag)
+    cfgs = configs.demo_cfgs() if tag == 'demo' else configs.tiny_cfgs()
+    fc = cfgs['FCModel']
+    L = get_fc_model(1, cfgs, fc['input_size'], fc['output_size']).eval()
+    L.load_state_dict(lifter_ref.make_weights(cfgs, 11))
+    stats = lifter_ref.make_stats(cfgs, 12)
+    L.set_stats(stats)
+    out, raw = L.lift(cuda(g['kpts']), want_raw=True)
+    np.testing.assert_allclose(raw.cpu().numpy(), g['raw'], rtol=0, atol=1e-4)          # 1e-4 on fp32 net output
+    np.testing.assert_allclose(out.cpu().numpy().reshape(g['kpts_3d'].shape), g['kpts_3d'], rtol=0, atol=2e-4)
+    # reference-style forward(): already normalised fp32 in, raw fp32 out
+    x = ((g['kpts'] - stats['mean_in']) / stats['std_in']).astype(np.float32)
+    np.testing.assert_allclose(L(cuda(x)).cpu().numpy(), g['raw'], rtol=0, atol=1e-4)
+    assert L.lift(torch.zeros((0, fc['input_size']), device=DEV, dtype=torch.float64)).shape == (0, fc['output_size'])
+
+
+# --------------------------------------------------------------------------- HC
+def _hc(cfgs, precision, conv_impl='auto', keep_taps=False, seed=1):
+    m = get_pose_net(cfgs, is_train=False, precision=precision, conv_impl=conv_impl, keep_taps=keep_taps).eval()
+    m.load_state_dict(hrnet_ref.make_weights(cfgs, seed))
+    return m.to(DEV)
+
+
+HC_CASES = [('tiny', configs.tiny_cfgs), ('tiny_heatmap', lambda: configs.tiny_cfgs('heatmap')),
+            ('ped', configs.ped_cfgs), ('demo', configs.demo_cfgs)]
+
+
+@pytest.mark.parametrize('tag,mk', HC_CASES, ids=[c[0] for c in HC_CASES])
+def test_hc_fp32_mode_vs_reference_golden(golden, tag, mk):
+    """fp32 precision mode against the upstream module's outputs: 1e-4 on coordinates."""
+    cfgs = mk()
+    g = golden('hrnet_%s.npz' % tag)
+    m = _hc(cfgs, 'fp32')
+    x = egonet_ref.synth_crops(int(g['batch']), cfgs, int(g['seed_x'])).to(DEV)
+    out = m(x)
+    maps = (out[0] if isinstance(out, tuple) else out).cpu().numpy()
+    rs = int(g['map_row_stride'])
+    scale = float(np.abs(g['maps_sub']).max())
+    np.testing.assert_allclose(maps[:, :, ::rs, :], g['maps_sub'], rtol=0, atol=2e-5 * max(scale, 1.0))
+    flat = maps.reshape(maps.shape[0], maps.shape[1], -1)
+    np.testing.assert_array_equal(flat.argmax(2), g['maps_argmax'])          # index-exact arg-max
+    if isinstance(out, tuple):
+        np.testing.assert_allclose(out[1].cpu().numpy(), g['coords'], rtol=0, atol=1e-4)
+
+
+def test_hc_fp32_per_stage_taps_vs_oracle():
+    cfgs = configs.tiny_cfgs()
+    m = _hc(cfgs, 'fp32', keep_taps=True)
+    sd = hrnet_ref.make_weights(cfgs, 1)
+    x = egonet_ref.synth_crops(3, cfgs, 0)
+    taps = {}
+    hrnet_ref.hrnet_forward(sd, cfgs, x, taps)
+    xd = x.to(DEV).contiguous()
+    m(xd)                                            # folds + uploads the weights
+    maps, coords, logits = m.run(xd, want_logits=True)
+    for name in ('stem1', 'stem2', 'layer1', 'stage2.0.out0', 'stage2.0.out1', 'stage3.0.out2',
+                 'stage4.0.out0', 'head2.0', 'head2.3'):
+        got = m.read_tap(name, 3).cpu()
+        ref = taps[name]
+        assert got.shape == ref.shape, name
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (name, err)
+    # pre-sigmoid logits (a saturated sigmoid could hide errors)
+    np.testing.assert_allclose(logits.cpu().numpy(), taps['logits'].numpy(), rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('tag,mk', [HC_CASES[0], HC_CASES[2], HC_CASES[3]], ids=['tiny', 'ped', 'demo'])
+def test_hc_fp16_mode_vs_quantized_oracle(tag, mk, impl):
+    """fp16 path vs the oracle's arithmetic model of it (same rounding points): what differs is
+    accumulation order and rare 1-ulp fp16 rounding flips.  Also the stated error vs fp32."""
+    cfgs = mk()
+    m = _hc(cfgs, 'fp16', conv_impl=impl)
+    sd = hrnet_ref.make_weights(cfgs, 1)
+    x = egonet_ref.synth_crops(2, cfgs, 0)
+    maps_q, coords_q = hrnet_ref.hrnet_forward(sd, cfgs, x, ctx=hrnet_ref.Quantized(torch.float16))
+    maps_e, coords_e = hrnet_ref.hrnet_forward(sd, cfgs, x)
+    maps, coords = m(x.to(DEV))
+    maps, coords = maps.cpu(), coords.cpu()
+    scale = maps_e.abs().max().item()
+    assert (maps - maps_q).abs().max().item() <= 4e-3 * scale        # vs same-rounding model
+    assert (coords - coords_q).abs().max().item() <= 1.5e-3
+    assert (maps - maps_e).abs().max().item() <= 1.5e-2 * scale      # stated fp16 error vs fp32 reference
+    assert (coords - coords_e).abs().max().item() <= 4e-3
+    # arg-max of the fp16 heat-maps vs the fp32 reference maps: report flips, require < 2 %
+    flips = (maps.flatten(2).argmax(2) != maps_e.flatten(2).argmax(2)).float().mean().item()
+    assert flips <= 0.02
+
+
+def test_hc_tc_matches_simt_per_stage():
+    """tcgen05 kernels vs the CUDA-core kernels on identical fp16 inputs/weights, tap by tap."""
+    cfgs = configs.tiny_cfgs()
+    a = _hc(cfgs, 'fp16', conv_impl='auto', keep_taps=True)
+    b = _hc(cfgs, 'fp16', conv_impl='simt', keep_taps=True)
+    if a.stats()['tc_launches'] == 0:
+        pytest.skip('no tcgen05 layers in this build')
+    x = egonet_ref.synth_crops(3, cfgs, 0).to(DEV)
+    a(x), b(x)
+    for name in ('stem2', 'layer1', 'stage2.0.out0', 'stage2.0.out1', 'stage3.0.out2', 'stage4.0.out0', 'head2.3'):
+        ta, tb = a.read_tap(name, 3), b.read_tap(name, 3)
+        tol = 6e-3 * max(1.0, tb.abs().max().item())
+        assert (ta - tb).abs().max().item() <= tol, name
+
+
+def test_hc_batch_edge_cases_and_invariance():
+    """Ragged tiles (B=1,3,5 at 8x8 / 4x4 maps), empty batch, and batch invariance: a crop's result
+    does not depend on its neighbours (size-independent property used at full batch sizes)."""
+    cfgs = configs.demo_cfgs()
+    m = _hc(cfgs, 'fp16')
+    x = egonet_ref.synth_crops(5, cfgs, 0).to(DEV)
+    maps5, coords5 = m(x)
+    for sel in ([0], [1, 3, 4]):
+        mp, cd = m(x[sel].contiguous())
+        assert torch.equal(mp, maps5[sel]) and torch.equal(cd, coords5[sel])
+    mp, cd = m(x[:0])
+    assert mp.shape[0] == 0 and cd.shape == (0, 33, 2)
+    assert float(coords5.min()) > 0.0 and float(coords5.max()) < 1.0
+
+
+def test_hc_full_batch_properties():
+    """BASELINE configs[1] size (batch 64): duplicate crops give identical rows, results equal the
+    small-batch results, decode of the device heat-maps is index-exact vs torch."""
+    cfgs = configs.demo_cfgs()
+    m = _hc(cfgs, 'fp16')
+    base = egonet_ref.synth_crops(4, cfgs, 0).to(DEV)
+    x = base.repeat(16, 1, 1, 1)
+    maps, coords = m(x)
+    ref_maps, ref_coords = m(base)
+    assert torch.equal(maps.view(16, 4, *maps.shape[1:]), ref_maps.unsqueeze(0).expand(16, -1, -1, -1, -1))
+    assert torch.equal(coords.view(16, 4, 33, 2), ref_coords.unsqueeze(0).expand(16, -1, -1, -1))
+    preds, maxvals, idx = img_proc.get_max_preds(maps, return_index=True)
+    assert torch.equal(idx.long(), maps.flatten(2).argmax(2))
+    assert torch.equal(maxvals.squeeze(-1), maps.flatten(2).max(2)[0])
+
+
+# --------------------------------------------------------------------------- whole path
+def _egonet(cfgs, precision):
+    cfgs = configs.clone(cfgs)
+    cfgs['heatmapModel']['b200_precision'] = precision
+    ego = EgoNet(cfgs, pre_trained=False).eval()
+    ego.HC.load_state_dict(hrnet_ref.make_weights(cfgs, 1))
+    ego.L.load_state_dict(lifter_ref.make_weights(cfgs, 11))
+    ego.LS = lifter_ref.make_stats(cfgs, 12)
+    return ego.to(DEV)
+
+
+def test_pipeline_vs_reference_golden(golden):
+    """EgoNet.get_keypoints -> lift_2d_to_3d -> gather_lifting_results against the upstream class
+    (fp32 mode): 1e-4 on angles / alpha, screen key-points and 3D key-points."""
+    g = golden('pipeline_tiny.npz')
+    cfgs = configs.tiny_cfgs()
+    ego = _egonet(cfgs, 'fp32')
+    n = len(g['centers'])
+    crops = egonet_ref.synth_crops(n, cfgs, 0)
+    recs = egonet_ref.synth_boxes(n, cfgs, 2)
+    paths = ['img_a.png'] * 2 + ['img_b.png'] * 3 + ['img_c.png']
+    for r, p in zip(recs, paths):
+        r.update(path=p, label=-1, score=-1.0)
+    records = ego.get_keypoints(crops, recs)
+    records = ego.lift_2d_to_3d(records)
+    got = {k: [] for k in ('kpts_2d', 'kpts_3d', 'euler', 'translation', 'alpha_trans', 'alpha_proj')}
+    for p in ('img_a.png', 'img_b.png', 'img_c.png'):
+        rec = records[p]
+        rec['K'] = egonet_ref.KITTI_K
+        for mode in ('trans', 'proj'):
+            rec = ego.gather_lifting_results(rec, None, None, alpha_mode=mode)
+            got['alpha_' + mode].append(rec['alphas'].copy())
+        got['kpts_2d'].append(np.concatenate(rec['kpts_2d_pred'], 0))
+        got['kpts_3d'].append(rec['kpts_3d_pred'])
+        got['euler'].append(rec['euler_angles'])
+        got['translation'].append(rec['translation'])
+    got = {k: np.concatenate(v, 0) for k, v in got.items()}
+    # screen key-points are coords * (crop size in px): 1e-4 on coords -> ~5e-2 px at 400 px boxes
+    np.testing.assert_allclose(got['kpts_2d'], g['kpts_2d'], rtol=0, atol=5e-2)
+    np.testing.assert_allclose(got['kpts_3d'], g['kpts_3d'], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(got['translation'], g['translation'], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(got['euler'], g['euler'], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(got['alpha_trans'], g['alpha_trans'], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(got['alpha_proj'], g['alpha_proj'], rtol=0, atol=1e-4)
+    # methods with the reference's signatures
+    ang, tr = ego.get_6d_rep(got['kpts_3d'])
+    np.testing.assert_allclose(ang, got['euler'], atol=1e-12)
+    np.testing.assert_allclose(ego.get_observation_angle_trans(ang, tr), got['alpha_trans'], atol=1e-12)
+
+
+def test_forward_crops_matches_stepwise_and_oracle():
+    """The fused device path (what bench.py times) equals the step-by-step methods, and the oracle
+    pipeline fed with the SAME coordinates agrees to 1e-9 downstream (lifter fp32 aside)."""
+    cfgs = configs.tiny_cfgs()
+    ego = _egonet(cfgs, 'fp16')
+    n = 9
+    crops = egonet_ref.synth_crops(n, cfgs, 3).to(DEV)
+    recs = egonet_ref.synth_boxes(n, cfgs, 4)
+    centers = np.array([r['center'] for r in recs])
+    scales = np.array([r['scale'] for r in recs])
+    out = ego.forward_crops(crops, centers, scales, K=egonet_ref.KITTI_K, alpha_mode='proj', return_all=True)
+    coords = out['coords'].cpu().numpy()
+    kp = np.concatenate([k.reshape(1, -1) for k in
+                         __import__('oracle.affine_ref', fromlist=['x']).local_to_screen(
+                             coords, centers, scales, [0.0] * n, cfgs['heatmapModel']['input_size'])], 0)
+    np.testing.assert_allclose(out['kpts_2d'].cpu().numpy(), kp, rtol=0, atol=1e-9)
+    k3 = lifter_ref.lift_2d_to_3d(lifter_ref.make_weights(cfgs, 11), cfgs, lifter_ref.make_stats(cfgs, 12), kp)
+    np.testing.assert_allclose(out['kpts_3d'].cpu().numpy().reshape(k3.shape), k3, rtol=0, atol=2e-4)
+    ang, tr = pose_ref.get_6d_rep(out['kpts_3d'].cpu().numpy())
+    pose = out['pose'].cpu().numpy()
+    np.testing.assert_allclose(pose[:, :3], ang, atol=1e-9)
+    np.testing.assert_allclose(pose[:, 6], pose_ref.observation_angle_proj(ang, [k.reshape(1, -1) for k in kp],
+                                                                         egonet_ref.KITTI_K), atol=1e-9)
