@@ -70,6 +70,7 @@ SIGNATURES = {
     'egn_lifter_forward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'egn_pose_solve': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double, c_int,
                                c_void_p, c_void_p, c_void_p]),
+    'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
 

@@ -1,11 +1,553 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 implicit-GEMM convolution for sm_100a (fp16 in, fp32 accumulate in TMEM).
+//
+//   out[b,oh,ow,:] = act( sum_{r,s,c} in[b, oh*st+r-p, ow*st+s-p, c] * w[:, r,s,c] + bias (+ res) )
+//
+// GEMM view: M = output pixels (128 per CTA = one TMEM lane per pixel), N = output
+// channels (one UMMA N tile of up to 256), K = taps x input channels.
+//
+// Data movement -- no im2col buffer, no halo staging, no padding branches:
+//   * A (activations, NHWC fp16): for filter tap (r,s) the 128 x KC operand tile is
+//     just the output tile's window shifted by (r-p, s-p).  One TMA tiled load of
+//     the box {KC ch, TW, TH, TB} at signed coordinates fetches it; out-of-image
+//     elements are zero-filled by the TMA unit, which IS the conv padding.
+//     Stride-2 convs use a 5-D view [B][H/2][2][W/2][2*C] of the same buffer so
+//     that the parity of the input row/column becomes a coordinate (still one
+//     tiled load per tap).
+//   * B (weights, [Cout][tap][Cin] fp16, BN folded): 2-D TMA box {KC, N}.
+//   Both land in shared memory in the canonical K-major swizzled layout that the
+//   UMMA shared-memory descriptors address, so the MMA issuer never touches data.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer (one elected lane issues tcgen05.mma; tcgen05.commit recycles pipeline
+// stages through mbarriers), warps 2-5 = epilogue (tcgen05.ld accumulator rows ->
+// bias / residual / ReLU -> fp16 NHWC stores; optional fp32 NCHW heat-map copy).
+// Several CTAs are resident per SM (small smem/TMEM footprints), so one CTA's
+// epilogue overlaps its neighbours' main loops.
+#include <cuda.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "common.h"
 #include "kernels.h"
+
 namespace egn {
-struct TcConvPlan {};
-bool tc_conv_supported(const ConvArgs&) { return false; }
-int tc_conv_plan_create(const ConvArgs&, const float*, TcConvPlan**) { set_error("tc path not built"); return EGN_ERR_INVALID; }
-void tc_conv_plan_destroy(TcConvPlan*) {}
-int launch_conv_tc(TcConvPlan*, const ConvArgs&, cudaStream_t) { set_error("tc path not built"); return EGN_ERR_INVALID; }
-size_t tc_conv_plan_weight_bytes(const TcConvPlan*) { return 0; }
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Spin with a watchdog: a mis-programmed TMA/MMA pipeline traps (launch failure
+// reported to the host) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled shared-memory matrix descriptor (sm_100 "version 1"):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1)
+//   [32,46) stride byte offset >> 4 = 8 rows * swizzle span | [46,48) = 1 | [61,64) layout type
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t swizzle_bytes) {
+  const uint64_t layout = swizzle_bytes == 128 ? 2 : (swizzle_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * swizzle_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct TcParams {
+  // problem
+  int B, OH, OW, Cout_p, Cout, Cin_p;
+  int taps, ksize, stride, pad, relu;
+  // tiling
+  int TW, TH, TB;            // output tile = TB x TH x TW pixels (<= 128)
+  int tiles_w, tiles_h;      // tiles per image along w / h
+  int n_tile;                // UMMA N (output channels per CTA)
+  int kc;                    // channels per pipeline stage (= swizzle bytes / 2)
+  int kchunks;               // Cin_p / kc
+  int stages;
+  uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
+  uint32_t tmem_cols;
+  // epilogue operands
+  const float* bias;
+  const __half* res;
+  __half* out;
+  float* heatmap;
+  const float* xs;
+  const float* ys;
+  int coord_maps;
+};
+
+template <int SW>
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (swizzle atoms are address based)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_stage = 128u * SW;
+  const uint32_t b_stage = ((uint32_t)p.n_tile * SW + 1023u) & ~1023u;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * a_stage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tw_i = tile % p.tiles_w;
+  tile /= p.tiles_w;
+  const int th_i = tile % p.tiles_h;
+  const int tb_i = tile / p.tiles_h;
+  const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, b0 = tb_i * p.TB;
+  const int n0 = blockIdx.y * p.n_tile;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_iters = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
+        const int tap = it / p.kchunks, kcx = it - tap * p.kchunks;
+        const int r = tap / p.ksize, q = tap - r * p.ksize;
+        const int c0 = kcx * p.kc;
+        if (p.stride == 1) {
+          tma_load_4d(smem_a + (size_t)s * a_stage, &map_a, &full_bar[s], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
+        } else {
+          // input row = 2*(oh + dh) + hp, input col = 2*(ow + dw) + wp
+          const int er = r - p.pad, eq = q - p.pad;
+          const int hp = er & 1, dh = (er - hp) / 2;
+          const int wp = eq & 1, dw = (eq - wp) / 2;
+          tma_load_5d(smem_a + (size_t)s * a_stage, &map_a, &full_bar[s], wp * p.Cin_p + c0, ow0 + dw, hp, oh0 + dh,
+                      b0);
+        }
+        tma_load_2d(smem_b + (size_t)s * b_stage, &map_b, &full_bar[s], tap * p.Cin_p + c0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (size_t)s * a_stage), SW);
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)s * b_stage), SW);
+#pragma unroll
+        for (int k = 0; k < SW / 32; ++k) {
+          // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
+          umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees this stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;     // accumulator row = pixel index inside the tile
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tb = row / (p.TW * p.TH);
+    const int b = b0 + tb, oh = oh0 + th, ow = ow0 + tw;
+    const bool valid = row < p.TW * p.TH * p.TB && b < p.B && oh < p.OH && ow < p.OW;
+    const size_t pix = ((size_t)b * p.OH + oh) * p.OW + ow;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        const int n = n0 + c0;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bq.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bq.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bq.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bq.w;
+        }
+        if (p.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout_p + n);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 rq = __ldg(rp + h);
+            const __half2* r2 = reinterpret_cast<const __half2*>(&rq);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 rf = __half22float2(r2[j]);
+              f[8 * h + 2 * j] += rf.x;
+              f[8 * h + 2 * j + 1] += rf.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.heatmap) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.Cout) p.heatmap[(((size_t)b * p.Cout + n + j) * p.OH + oh) * p.OW + ow] = f[j];
+        }
+        if (p.coord_maps) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (n + j == p.Cout) f[j] = p.xs[ow];
+            if (n + j == p.Cout + 1) f[j] = p.ys[oh];
+          }
+        }
+        uint4 o[2];
+        __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+        uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout_p + n);
+        op[0] = o[0];
+        op[1] = o[1];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: tensor maps + plan
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TcConvPlan {
+  // shape (batch independent)
+  int H, W, Cin_p, OH, OW, Cout_p, Cout, ksize, stride, pad;
+  int sw;          // swizzle bytes 32 / 64 / 128
+  int kc, kchunks, n_tile, n_tiles, stages;
+  int TW, TH, TB;
+  uint32_t tmem_cols;
+  size_t smem_bytes;
+  __half* d_w = nullptr;      // [Cout_p][taps*Cin_p]
+  size_t w_bytes = 0;
+  CUtensorMap map_b;
+  std::map<std::pair<const void*, int>, CUtensorMap> a_maps;  // (input pointer, batch) -> map
+  std::mutex mu;
+};
+
+static CUtensorMapSwizzle swizzle_enum(int sw) {
+  return sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+bool tc_conv_supported(const ConvArgs& a) {
+  if (a.Cin_p % 16 || a.Cout_p % 16) return false;
+  if (a.ksize != 1 && a.ksize != 3) return false;
+  if (a.stride != 1 && a.stride != 2) return false;
+  if (a.stride == 2 && ((a.H | a.W) & 1)) return false;
+  if (a.OW > 128) return false;  // one tile row must fit 128 accumulator lanes
+  if (a.Cout_p > 256 && (a.Cout_p % 2 || a.Cout_p / 2 > 256 || (a.Cout_p / 2) % 16)) return false;
+  return true;
+}
+
+static uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
+  if (!tc_conv_supported(a)) {
+    set_error("tc_conv_plan_create: unsupported conv shape");
+    return EGN_ERR_INVALID;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+    return EGN_ERR_CUDA;
+  }
+  TcConvPlan* p = new TcConvPlan();
+  p->H = a.H; p->W = a.W; p->Cin_p = a.Cin_p; p->OH = a.OH; p->OW = a.OW;
+  p->Cout_p = a.Cout_p; p->Cout = a.Cout; p->ksize = a.ksize; p->stride = a.stride; p->pad = a.pad;
+  p->sw = a.Cin_p % 64 == 0 ? 128 : (a.Cin_p % 32 == 0 ? 64 : 32);
+  p->kc = p->sw / 2;
+  p->kchunks = a.Cin_p / p->kc;
+  p->n_tiles = a.Cout_p > 256 ? 2 : 1;
+  p->n_tile = a.Cout_p / p->n_tiles;
+  p->TW = std::min(a.OW, 128);
+  p->TH = std::min(a.OH, 128 / p->TW);
+  p->TB = p->TH == a.OH ? std::max(1, 128 / (p->TW * p->TH)) : 1;
+  p->tmem_cols = pow2_cols(p->n_tile);
+  const size_t a_stage = 128 * (size_t)p->sw;
+  const size_t b_stage = ((size_t)p->n_tile * p->sw + 1023) & ~(size_t)1023;
+  const size_t stage = a_stage + b_stage;
+  const size_t budget = stage > 24 * 1024 ? 176 * 1024 : 80 * 1024;
+  const int n_iters = a.ksize * a.ksize * p->kchunks;
+  size_t st_count = std::min<size_t>((size_t)kMaxStages, budget / stage);
+  st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
+  p->stages = (int)std::max<size_t>(2, st_count);
+  p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+  // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_p] fp16
+  const int taps = a.ksize * a.ksize;
+  const size_t K = (size_t)taps * a.Cin_p;
+  std::vector<__half> w((size_t)a.Cout_p * K);
+  for (int o = 0; o < a.Cout_p; ++o)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < a.Cin_p; ++c)
+        w[(size_t)o * K + (size_t)t * a.Cin_p + c] = __float2half_rn(wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o]);
+  p->w_bytes = w.size() * sizeof(__half);
+  if (cudaMalloc(&p->d_w, p->w_bytes) != cudaSuccess ||
+      cudaMemcpy(p->d_w, w.data(), p->w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("tc_conv_plan_create: weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    tc_conv_plan_destroy(p);
+    return EGN_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)a.Cout_p};
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)p->kc, (cuuint32_t)p->n_tile};
+  const cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->d_w, gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p->sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    tc_conv_plan_destroy(p);
+    return EGN_ERR_CUDA;
+  }
+  *out = p;
+  return EGN_OK;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* p) {
+  if (!p) return;
+  cudaFree(p->d_w);
+  delete p;
+}
+
+size_t tc_conv_plan_weight_bytes(const TcConvPlan* p) { return p ? p->w_bytes : 0; }
+
+static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
+  EncodeTiledFn enc = get_encode_fn();
+  const cuuint64_t C = p->Cin_p, W = p->W, H = p->H;
+  CUresult r;
+  if (p->stride == 1) {
+    const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)p->kc, (cuuint32_t)p->TW, (cuuint32_t)p->TH, (cuuint32_t)p->TB};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p->sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // [B][H/2][2][W/2][2C]: d0 = (col parity, channel), d1 = col/2, d2 = row parity, d3 = row/2, d4 = batch
+    const cuuint64_t gdim[5] = {2 * C, W / 2, 2, H / 2, (cuuint64_t)B};
+    const cuuint64_t gstr[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)p->kc, (cuuint32_t)p->TW, 1, (cuuint32_t)p->TH, (cuuint32_t)p->TB};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(in), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p->sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activations %dx%dx%d, B=%d, stride %d) failed with %d", p->H, p->W, p->Cin_p, B,
+              p->stride, (int)r);
+    return EGN_ERR_CUDA;
+  }
+  return EGN_OK;
+}
+
+template <int SW>
+static int launch_sw(TcConvPlan* p, const CUtensorMap& ma, const TcParams& tp, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<SW><<<grid, kTcThreads, p->smem_bytes, st>>>(ma, p->map_b, tp);
+  EGN_LAUNCH_CHECK("conv_tc_kernel");
+  return EGN_OK;
+}
+
+int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
+  if (!p) {
+    set_error("launch_conv_tc: null plan");
+    return EGN_ERR_STATE;
+  }
+  CUtensorMap ma;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    auto key = std::make_pair(a.in, a.B);
+    auto it = p->a_maps.find(key);
+    if (it == p->a_maps.end()) {
+      if (p->a_maps.size() > 64) p->a_maps.clear();
+      CUtensorMap m;
+      if (int rc = make_a_map(p, a.in, a.B, &m)) return rc;
+      it = p->a_maps.emplace(key, m).first;
+    }
+    ma = it->second;
+  }
+  TcParams tp{};
+  tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
+  tp.taps = p->ksize * p->ksize; tp.ksize = p->ksize; tp.stride = p->stride; tp.pad = p->pad; tp.relu = a.relu;
+  tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
+  tp.tiles_w = ceil_div(p->OW, p->TW);
+  tp.tiles_h = ceil_div(p->OH, p->TH);
+  tp.n_tile = p->n_tile; tp.kc = p->kc; tp.kchunks = p->kchunks; tp.stages = p->stages;
+  tp.a_bytes = (uint32_t)(p->TW * p->TH * p->TB) * (uint32_t)p->sw;
+  tp.b_bytes = (uint32_t)p->n_tile * (uint32_t)p->sw;
+  tp.tmem_cols = p->tmem_cols;
+  tp.bias = a.bias;
+  tp.res = static_cast<const __half*>(a.res);
+  tp.out = static_cast<__half*>(a.out);
+  tp.heatmap = a.heatmap; tp.xs = a.xs; tp.ys = a.ys; tp.coord_maps = a.coord_maps;
+  dim3 grid((unsigned)(tp.tiles_w * tp.tiles_h * ceil_div(a.B, p->TB)), (unsigned)p->n_tiles);
+  switch (p->sw) {
+    case 128: return launch_sw<128>(p, ma, tp, grid, st);
+    case 64: return launch_sw<64>(p, ma, tp, grid, st);
+    default: return launch_sw<32>(p, ma, tp, grid, st);
+  }
+}
+
+}  // namespace egn

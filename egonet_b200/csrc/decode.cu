@@ -173,8 +173,8 @@ extern "C" {
 int egn_argmax2d(const float* hm, int B, int K, int H, int W, int32_t* idx, float* preds,
                  float* maxvals, void* stream) {
   using namespace egn;
-  EGN_REQUIRE(hm && preds && maxvals, "egn_argmax2d: null pointer");
   EGN_REQUIRE(B >= 0 && K > 0 && H > 0 && W > 0, "egn_argmax2d: bad shape B=%d K=%d H=%d W=%d", B, K, H, W);
+  EGN_REQUIRE(B == 0 || (hm && preds && maxvals), "egn_argmax2d: null pointer");
   EGN_REQUIRE((int64_t)H * W < (1 << 24), "egn_argmax2d: map too large for exact float32 indices");
   if (int rc = require_device()) return rc;
   if (B * K == 0) return EGN_OK;
@@ -186,8 +186,8 @@ int egn_argmax2d(const float* hm, int B, int K, int H, int W, int32_t* idx, floa
 int egn_soft_argmax2d(const float* hm, int B, int K, int H, int W, int mode, float* preds,
                       float* maxvals, void* stream) {
   using namespace egn;
-  EGN_REQUIRE(hm && preds && maxvals, "egn_soft_argmax2d: null pointer");
   EGN_REQUIRE(B >= 0 && K > 0 && H > 0 && W > 0, "egn_soft_argmax2d: bad shape");
+  EGN_REQUIRE(B == 0 || (hm && preds && maxvals), "egn_soft_argmax2d: null pointer");
   EGN_REQUIRE(mode == EGN_SOFTARGMAX_SOFTMAX || mode == EGN_SOFTARGMAX_SUM,
               "egn_soft_argmax2d: unknown mode %d", mode);
   if (int rc = require_device()) return rc;

@@ -721,8 +721,9 @@ static char* ws_base(void* workspace) {
 int egn_hrnet_forward(egn_hrnet* h, const float* x, int batch, float* heatmap_out, float* coords_out,
                       float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace egn;
-  EGN_REQUIRE(h && x, "egn_hrnet_forward: null argument");
+  EGN_REQUIRE(h, "egn_hrnet_forward: null handle");
   EGN_REQUIRE(batch >= 0, "egn_hrnet_forward: negative batch");
+  EGN_REQUIRE(batch == 0 || x, "egn_hrnet_forward: null input");
   if (!h->finalized) {
     set_error("egn_hrnet_forward called before egn_hrnet_finalize");
     return EGN_ERR_STATE;
@@ -835,3 +836,76 @@ int64_t egn_hrnet_act_bytes_per_crop(const egn_hrnet* h) { return h ? h->act_byt
 int64_t egn_hrnet_weight_bytes(const egn_hrnet* h) { return h ? h->weight_bytes : 0; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// single fused conv layer (per-layer parity tests; synchronous convenience call)
+// ---------------------------------------------------------------------------
+extern "C" int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w_oihw_host,
+                                const float* bias_host, const void* res, void* out, int B, int H, int W,
+                                int Cin, int Cout, int ksize, int stride, int relu, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(in && w_oihw_host && out, "egn_conv2d_fused: null pointer");
+  EGN_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "egn_conv2d_fused: bad shape");
+  EGN_REQUIRE(ksize == 1 || ksize == 3, "egn_conv2d_fused: ksize must be 1 or 3");
+  EGN_REQUIRE(stride == 1 || stride == 2, "egn_conv2d_fused: stride must be 1 or 2");
+  EGN_REQUIRE(dtype == 0 || dtype == 1, "egn_conv2d_fused: dtype 0 (fp32) or 1 (fp16)");
+  EGN_REQUIRE(impl == 0 || (impl == 1 && dtype == 1), "egn_conv2d_fused: the tcgen05 path is fp16 only");
+  if (int rc = require_device()) return rc;
+  ConvArgs a{};
+  a.B = B; a.H = H; a.W = W;
+  a.Cin_p = round_up(Cin, kChanAlign);
+  a.Cout_p = round_up(Cout, kChanAlign);
+  a.Cout = Cout;
+  a.ksize = ksize; a.stride = stride; a.pad = ksize == 3 ? 1 : 0; a.relu = relu;
+  a.OH = (H + 2 * a.pad - ksize) / stride + 1;
+  a.OW = (W + 2 * a.pad - ksize) / stride + 1;
+  a.in = in; a.out = out; a.res = res;
+  const int taps = ksize * ksize;
+  std::vector<float> wf((size_t)taps * a.Cin_p * a.Cout_p, 0.f), bias(a.Cout_p, 0.f);
+  for (int o = 0; o < Cout; ++o) {
+    if (bias_host) bias[o] = bias_host[o];
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < taps; ++t) {
+        float v = w_oihw_host[((size_t)o * Cin + c) * taps + t];
+        if (dtype == 1) v = __half2float(__float2half_rn(v));
+        wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o] = v;
+      }
+  }
+  float* d_bias = nullptr;
+  EGN_CUDA_CHECK(cudaMalloc(&d_bias, bias.size() * sizeof(float)));
+  cudaMemcpy(d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice);
+  a.bias = d_bias;
+  int rc = EGN_OK;
+  cudaStream_t st = as_stream(stream);
+  if (impl == 1) {
+    if (!tc_conv_supported(a)) {
+      set_error("egn_conv2d_fused: shape not supported by the tcgen05 kernel");
+      rc = EGN_ERR_INVALID;
+    } else {
+      TcConvPlan* plan = nullptr;
+      rc = tc_conv_plan_create(a, wf.data(), &plan);
+      if (!rc) rc = launch_conv_tc(plan, a, st);
+      if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("egn_conv2d_fused(tc): %s", cudaGetErrorString(cudaGetLastError()));
+        rc = EGN_ERR_CUDA;
+      }
+      tc_conv_plan_destroy(plan);
+    }
+  } else {
+    float* d_w = nullptr;
+    if (cudaMalloc(&d_w, wf.size() * sizeof(float)) != cudaSuccess) {
+      set_error("egn_conv2d_fused: cudaMalloc failed");
+      rc = EGN_ERR_CUDA;
+    } else {
+      cudaMemcpy(d_w, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice);
+      rc = launch_conv_simt(dtype == 0 ? Dtype::F32 : Dtype::F16, a, d_w, st);
+      if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("egn_conv2d_fused(simt): %s", cudaGetErrorString(cudaGetLastError()));
+        rc = EGN_ERR_CUDA;
+      }
+      cudaFree(d_w);
+    }
+  }
+  cudaFree(d_bias);
+  return rc;
+}

@@ -276,8 +276,9 @@ size_t egn_lifter_workspace_bytes(const egn_lifter* l, int n) {
 int egn_lifter_forward(egn_lifter* l, const double* kpts_2d, int n, double* kpts_3d, float* raw_out,
                        void* workspace, size_t workspace_bytes, void* stream) {
   using namespace egn;
-  EGN_REQUIRE(l && kpts_2d && kpts_3d, "egn_lifter_forward: null argument");
+  EGN_REQUIRE(l, "egn_lifter_forward: null handle");
   EGN_REQUIRE(n >= 0, "egn_lifter_forward: negative n");
+  EGN_REQUIRE(n == 0 || (kpts_2d && kpts_3d), "egn_lifter_forward: null argument");
   if (!l->finalized) {
     set_error("egn_lifter_forward called before egn_lifter_finalize");
     return EGN_ERR_STATE;

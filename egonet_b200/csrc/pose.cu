@@ -54,8 +54,8 @@ extern "C" {
 int egn_observation_angle(const double* ry, const double* x3d, int stride_x, const double* z3d,
                           int stride_z, double x_offset, int N, double* alpha, void* stream) {
   using namespace egn;
-  EGN_REQUIRE(ry && x3d && z3d && alpha, "egn_observation_angle: null pointer");
   EGN_REQUIRE(N >= 0 && stride_x >= 0 && stride_z >= 0, "egn_observation_angle: bad shape");
+  EGN_REQUIRE(N == 0 || (ry && x3d && z3d && alpha), "egn_observation_angle: null pointer");
   if (int rc = require_device()) return rc;
   if (N == 0) return EGN_OK;
   observation_angle_kernel<<<ceil_div(N, 128), 128, 0, as_stream(stream)>>>(ry, x3d, z3d, stride_x, stride_z,
@@ -68,8 +68,8 @@ int egn_local_to_screen(const float* coords, const double* center, const double*
                         const double* rot, int N, int K, int res_w, int res_h, double* screen,
                         void* stream) {
   using namespace egn;
-  EGN_REQUIRE(coords && center && scale && screen, "egn_local_to_screen: null pointer");
   EGN_REQUIRE(N >= 0 && K > 0 && res_w > 0 && res_h > 0, "egn_local_to_screen: bad shape");
+  EGN_REQUIRE(N == 0 || (coords && center && scale && screen), "egn_local_to_screen: null pointer");
   if (int rc = require_device()) return rc;
   if (N == 0) return EGN_OK;
   const int threads = 128;
@@ -83,13 +83,13 @@ int egn_pose_solve(const double* kpts_3d, int N, int P, const double* kpts_2d, i
                    double fx, double cx, int alpha_mode, double* pose_out, double* rot_out,
                    void* stream) {
   using namespace egn;
-  EGN_REQUIRE(kpts_3d && pose_out, "egn_pose_solve: null pointer");
+  EGN_REQUIRE(N >= 0, "egn_pose_solve: negative N");
+  EGN_REQUIRE(N == 0 || (kpts_3d && pose_out), "egn_pose_solve: null pointer");
   EGN_REQUIRE(P == 8 || P == 32, "egn_pose_solve: P must be 8 or 32 (got %d)", P);
   EGN_REQUIRE(alpha_mode == EGN_ALPHA_TRANS || alpha_mode == EGN_ALPHA_PROJ,
               "egn_pose_solve: unknown alpha_mode %d", alpha_mode);
-  EGN_REQUIRE(alpha_mode != EGN_ALPHA_PROJ || (kpts_2d && stride_2d > 0),
+  EGN_REQUIRE(alpha_mode != EGN_ALPHA_PROJ || N == 0 || (kpts_2d && stride_2d > 0),
               "egn_pose_solve: proj mode needs kpts_2d");
-  EGN_REQUIRE(N >= 0, "egn_pose_solve: negative N");
   if (int rc = require_device()) return rc;
   if (N == 0) return EGN_OK;
   const int threads = 64;

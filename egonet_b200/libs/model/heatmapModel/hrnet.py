@@ -89,8 +89,10 @@ class PoseHighResolutionNet(nn.Module):
         self.pixel_shuffle = hm.get('pixel_shuffle', False)
         self.pretrained_layers = hm['extra'].get('pretrained_layers', ['*'])
         self._precision = _PRECISIONS[kwargs.get('precision', hm.get('b200_precision', 'fp16'))]
-        self._conv_impl = {'auto': N.CONV_AUTO, 'simt': N.CONV_SIMT}[
-            kwargs.get('conv_impl', hm.get('b200_conv_impl', 'auto'))]
+        impl = kwargs.get('conv_impl', hm.get('b200_conv_impl', 'auto'))
+        if os.environ.get('EGN_CONV_IMPL'):        # debugging aid: force 'simt' for a whole process
+            impl = os.environ['EGN_CONV_IMPL']
+        self._conv_impl = {'auto': N.CONV_AUTO, 'simt': N.CONV_SIMT}[impl]
         self._keep_taps = bool(kwargs.get('keep_taps', hm.get('b200_keep_taps', False)))
         self._in_channels = 3
         self._handle = None

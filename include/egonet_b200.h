@@ -132,6 +132,15 @@ EGN_API int egn_hrnet_forward(egn_hrnet* h, const float* x, int batch, float* he
 EGN_API int egn_hrnet_read_tap(egn_hrnet* h, const char* name, int batch, const void* workspace,
                        float* out, int dims[3], void* stream);
 
+/* One fused conv layer, out = act(conv(in, w) + bias [+ res]), for per-layer parity tests
+ * (synchronous).  impl: 0 = CUDA-core kernel, 1 = tcgen05 kernel (fp16 only).  dtype: 0 = fp32,
+ * 1 = fp16 storage.  in/res/out: device NHWC with channels padded to a multiple of 16
+ * (pad lanes zero); w: HOST fp32 torch OIHW; bias: HOST fp32 [Cout] or NULL.
+ * ksize 1 (pad 0) or 3 (pad 1), stride 1 or 2. */
+EGN_API int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w_oihw_host,
+                     const float* bias_host, const void* res, void* out, int B, int H, int W,
+                     int Cin, int Cout, int ksize, int stride, int relu, void* stream);
+
 /* Introspection for bench/roofline accounting. */
 EGN_API int64_t egn_hrnet_macs_per_crop(const egn_hrnet* h);
 EGN_API int egn_hrnet_num_launches(const egn_hrnet* h);        /* kernels per forward          */

@@ -311,3 +311,61 @@ def test_forward_crops_matches_stepwise_and_oracle():
     np.testing.assert_allclose(pose[:, :3], ang, atol=1e-9)
     np.testing.assert_allclose(pose[:, 6], pose_ref.observation_angle_proj(ang, [k.reshape(1, -1) for k in kp],
                                                                          egonet_ref.KITTI_K), atol=1e-9)
+
+
+# --------------------------------------------------------------------------- single conv layers
+def _nhwc16(x_nchw):
+    """NCHW fp32 -> NHWC fp16 with channels padded to a multiple of 16."""
+    B, C, H, W = x_nchw.shape
+    Cp = (C + 15) // 16 * 16
+    out = torch.zeros((B, H, W, Cp), device=x_nchw.device, dtype=torch.float16)
+    out[..., :C] = x_nchw.permute(0, 2, 3, 1).to(torch.float16)
+    return out.contiguous()
+
+
+CONV_CASES = [
+    # (Cin, Cout, H, W, k, stride, B)  -- the four HRNet branch shapes, the 1x1 / stride-2 / ragged ones
+    (64, 64, 64, 64, 1, 1, 2), (64, 64, 64, 64, 3, 1, 2), (48, 48, 64, 64, 3, 1, 3), (96, 96, 32, 32, 3, 1, 3),
+    (192, 192, 16, 16, 3, 1, 3), (384, 384, 8, 8, 3, 1, 3), (256, 48, 64, 64, 3, 1, 1), (64, 256, 64, 64, 1, 1, 1),
+    (384, 48, 8, 8, 1, 1, 5), (64, 64, 128, 128, 3, 2, 1), (256, 96, 64, 64, 3, 2, 2), (48, 384, 16, 16, 3, 2, 3),
+    (35, 66, 64, 64, 3, 2, 2), (35, 66, 64, 64, 1, 2, 2), (66, 66, 4, 4, 3, 1, 5), (48, 33, 64, 64, 1, 1, 2),
+    (32, 32, 64, 48, 3, 1, 2), (64, 64, 32, 24, 3, 1, 3), (128, 256, 16, 12, 3, 2, 3), (16, 16, 32, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
+def test_conv_layer_tc_and_simt_vs_torch(case):
+    """One fused conv (bias + residual + ReLU) through the tcgen05 and the CUDA-core kernels against
+    torch's fp32 conv2d on the same fp16-rounded operands."""
+    import ctypes
+    from egonet_b200 import _native as N
+    Cin, Cout, H, W, k, stride, B = case
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)
+    x = torch.randn((B, Cin, H, W), generator=g).to(DEV)
+    w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5)
+    bias = torch.randn((Cout,), generator=g)
+    xin = _nhwc16(x)
+    pad = 1 if k == 3 else 0
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = _nhwc16(torch.randn((B, Cout, OH, OW), generator=g).to(DEV))
+    Cout_p = res.shape[-1]
+    x16 = xin[..., :Cin].float().permute(0, 3, 1, 2)
+    w16 = w.to(torch.float16).float().to(DEV)
+    ref = torch.nn.functional.conv2d(x16, w16, bias.to(DEV), stride=stride, padding=pad)
+    ref = torch.relu(ref + res[..., :Cout].float().permute(0, 3, 1, 2))
+    wc, bc = w.contiguous(), bias.contiguous()
+    outs = {}
+    for impl in (0, 1):
+        out = torch.full((B, OH, OW, Cout_p), float('nan'), device=DEV, dtype=torch.float16)
+        N.check(N.lib().egn_conv2d_fused(impl, 1, N.ptr(xin), N.ptr(wc), N.ptr(bc), N.ptr(res), N.ptr(out),
+                                         B, H, W, Cin, Cout, k, stride, 1, N.current_stream()))
+        torch.cuda.synchronize()
+        got = out[..., :Cout].float().permute(0, 3, 1, 2)
+        assert torch.isfinite(out).all(), 'impl %d left unwritten / non-finite outputs' % impl
+        assert (out[..., Cout:] == 0).all(), 'pad lanes must stay zero'
+        # fp16 output rounding: half-ulp relative 2^-11, plus fp32 accumulation-order noise
+        tol = 1e-3 * max(1.0, ref.abs().max().item())
+        assert (got - ref).abs().max().item() <= tol, 'impl %d: %g' % (impl, (got - ref).abs().max().item())
+        outs[impl] = out
+    # the two kernels see identical operands: they may differ by fp32 summation order only
+    assert (outs[0].float() - outs[1].float()).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
