@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the EgoNet per-crop inference hot path (BASELINE.json metric: crops/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+One "step" = one pass of the whole per-crop path over one batch of synthetic 256x256 crops:
+HC (HRNet-W48 heat-maps + coordinate head, fp16 tcgen05 convs) -> heat-map decode (hard arg-max and
+soft-argmax of the 33 maps) -> inverse crop affine -> lifter -> pose solve.  Workload = BASELINE.json
+configs[1] extended to the full path of configs[2] ("batch=64 ... 1xB200"), per GPU.
+
+N > 1 is launched by torchrun (one process per GPU): crops are sharded with no data-path collective
+(weak scaling: every rank processes its own batch) and the [B,7] pose records are all-gathered
+over NCCL at the end of every step, as BASELINE.json configs[4] asks.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job crops/s with the inputs resident in HBM;
+`e2e` = the same path through the public API (EgoNet.forward_crops) from pinned HOST memory
+including the H2D copy of the crops and the D2H copy of the pose records; `roofline` = the
+dominant kernel class timed live with CUDA events; `cpu_baseline` = the CPU oracle (a port of the
+reference's algorithm on torch-CPU, the arithmetic the reference itself would run on CPU) on a
+bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'crops/sec (heatmap+lift+pose) on 256x256 synthetic batches'
+L2_BYTES = 126 * 1024 * 1024
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+                'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        reasons = []
+        for i, name in enumerate(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')):
+            if any(s[3 + i].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- workload
+def build_model(cfgs, device):
+    from egonet_b200 import synth
+    from egonet_b200.libs.model.egonet import EgoNet
+    ego = EgoNet(cfgs, pre_trained=False).eval()
+    ego.HC.load_state_dict(synth.hc_weights(ego.HC.state_dict(), 1))
+    ego.L.load_state_dict(synth.lifter_weights(ego.L.state_dict(), 11))
+    ego.LS = synth.lifter_stats(cfgs, 12)
+    return ego.to(device)
+
+
+def launches_per_step(ego):
+    st = ego.HC.stats()
+    lifter = 2 * ego.L.num_blocks + 2
+    return st['launches'] + 2 + 1 + lifter + 1   # HC + (argmax, soft-argmax) + affine + lifter + pose
+
+
+def one_step(ego, x, centers, scales, K):
+    """The device-resident step: everything after the crops are in HBM."""
+    from egonet_b200.libs.common import img_proc, transformation
+    maps, coords = ego.HC(x)
+    img_proc.get_max_preds(maps)
+    img_proc.soft_arg_max(maps)
+    screen = img_proc.local_to_screen(coords, centers, scales, ego.resolution)
+    k2 = screen.view(screen.shape[0], -1)
+    k3 = ego.L.lift(k2)
+    return transformation.pose_solve(k3.view(len(k3), -1, 3), k2, K, 'proj')
+
+
+def profile_hc(ego, x, passes=3):
+    """Per-op device times of the HC engine (CUDA events between launches), grouped by kernel class."""
+    from egonet_b200 import _native as N
+    L = N.lib()
+    h = ego.HC._handle
+    n = L.egn_hrnet_num_launches(h)
+    B = x.shape[0]
+    need = L.egn_hrnet_workspace_bytes(h, B)
+    ws = torch.empty(need, device=x.device, dtype=torch.uint8)
+    acc = np.zeros(n)
+    buf = (ctypes.c_float * n)()
+    for _ in range(passes):
+        N.check(L.egn_hrnet_profile(h, N.ptr(x), B, N.ptr(ws), need, N.current_stream(), buf))
+        acc += np.frombuffer(buf, dtype=np.float32)
+    acc /= passes
+    classes = {}
+    info = N.OpInfo()
+    kinds = {0: 'stem_conv', 1: 'conv', 2: 'fuse', 3: 'head_tail'}
+    for i in range(n):
+        N.check(L.egn_hrnet_op_info(h, i, ctypes.byref(info)))
+        if info.kind == 1:
+            name = '%s %dx%d s%d %d->%d @%dx%d%s' % ('conv_tc' if info.use_tc else 'conv_simt', info.ksize, info.ksize,
+                                                     info.stride, info.Cin, info.Cout, info.OH, info.OW,
+                                                     '+res' if info.has_res else '')
+        else:
+            name = kinds[info.kind]
+        c = classes.setdefault(name, {'ms': 0.0, 'launches': 0, 'macs': 0, 'act_bytes': 0, 'weight_bytes': 0})
+        c['ms'] += float(acc[i])
+        c['launches'] += 1
+        c['macs'] += info.macs * B
+        c['act_bytes'] += info.act_bytes * B
+        c['weight_bytes'] += info.weight_bytes
+    return classes, float(acc.sum())
+
+
+def roofline_block(classes, total_ms, pk):
+    name, c = max(classes.items(), key=lambda kv: kv[1]['ms'])
+    dur = c['ms'] / c['launches'] * 1e-3                      # seconds per launch
+    bytes_per_launch = (c['act_bytes'] + c['weight_bytes']) / c['launches']
+    flops_per_launch = 2.0 * c['macs'] / c['launches']
+    hbm = bytes_per_launch / dur / 1e9
+    tf = flops_per_launch / dur / 1e12
+    f_h, f_t = hbm / pk['hbm_gbs'], tf / pk['bf16_tflops']
+    bound = 'hbm' if bytes_per_launch / (pk['hbm_gbs'] * 1e9) >= flops_per_launch / (pk['bf16_tflops'] * 1e12) else 'tensor'
+    blk = {'kernel': name, 'bound': bound,
+           'achieved': round(hbm if bound == 'hbm' else tf, 2), 'peak': pk['hbm_gbs'] if bound == 'hbm' else pk['bf16_tflops'],
+           'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': round(f_h if bound == 'hbm' else f_t, 4),
+           'peak_source': pk['source'] + (' (burst)' if bound == 'tensor' else ''),
+           'traffic': None, 'other_roof_frac': round(f_t if bound == 'hbm' else f_h, 4),
+           'share_of_hc_time': round(c['ms'] / total_ms, 4), 'launches': c['launches'],
+           'avg_launch_us': round(dur * 1e6, 2), 'algorithmic_bytes_per_launch': int(bytes_per_launch),
+           'flops_per_launch': int(flops_per_launch)}
+    top = sorted(classes.items(), key=lambda kv: -kv[1]['ms'])[:6]
+    blk['top_classes'] = [{'kernel': k, 'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in top]
+    return blk
+
+
+# ----------------------------------------------------------------------------- CPU oracle legs
+def cpu_pipeline_rate(cfgs, batch, iters, threads):
+    """crops/s of the oracle port (reference algorithm on torch-CPU / numpy) for the full path."""
+    from oracle import decode_ref, egonet_ref, hrnet_ref, lifter_ref
+    torch.set_num_threads(threads)
+    hc = hrnet_ref.make_weights(cfgs, 1)
+    lw = lifter_ref.make_weights(cfgs, 11)
+    stats = lifter_ref.make_stats(cfgs, 12)
+    x = egonet_ref.synth_crops(batch, cfgs, 0)
+    recs = egonet_ref.synth_boxes(batch, cfgs, 2)
+
+    def step():
+        out = egonet_ref.run_pipeline(hc, lw, stats, cfgs, x, recs)
+        decode_ref.get_max_preds(out['maps'])
+        decode_ref.soft_arg_max(out['maps'])
+
+    step()  # warm-up
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return batch / float(np.median(times)), times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
+    Python/PyTorch, its algorithm restated on torch-CPU + numpy), all host threads, bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from egonet_b200 import synth
+    cfgs = synth.demo_cfgs()
+    threads = os.cpu_count() or 1
+    batch = args.ref_batch
+    from oracle import decode_ref, egonet_ref, hrnet_ref, lifter_ref
+    torch.set_num_threads(threads)
+    hc = hrnet_ref.make_weights(cfgs, 1)
+    lw = lifter_ref.make_weights(cfgs, 11)
+    stats = lifter_ref.make_stats(cfgs, 12)
+    x = egonet_ref.synth_crops(batch, cfgs, 0)
+    recs = egonet_ref.synth_boxes(batch, cfgs, 2)
+
+    def step():
+        out = egonet_ref.run_pipeline(hc, lw, stats, cfgs, x, recs)
+        decode_ref.get_max_preds(out['maps'])
+        decode_ref.soft_arg_max(out['maps'])
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': round(value, 3), 'unit': 'crops/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(dt / args.steps * 1e3, 2),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]+[2]: full per-crop path (HRNet-W48 heatmap+coords, decode, '
+                                   'affine, lifter, pose), 256x256 crops', 'batch_per_step': batch,
+                       'note': 'bounded sample of the GPU arm\'s workload (same model, same stages)'},
+            'cpu_baseline': {'value': round(value, 3), 'unit': 'crops/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d steps x %d crops, torch-CPU fp32 + numpy' % (args.steps, batch)},
+            'e2e': {'value': round(value, 3), 'unit': 'crops/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=64, help='crops per GPU per step')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--ref-batch', type=int, default=8)
+    ap.add_argument('--cpu-baseline-crops', type=int, default=16)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group('nccl', device_id=dev)
+
+    from egonet_b200 import synth
+    cfgs = synth.demo_cfgs()
+    cfgs['heatmapModel']['b200_precision'] = args.precision
+    ego = build_model(cfgs, dev)
+    B = args.batch
+    K = synth.KITTI_K
+    # rotating set of distinct input batches, total > L2, so no step finds its input cached
+    n_sets = max(2, int(np.ceil(1.5 * L2_BYTES / (B * 3 * 256 * 256 * 4))))
+    recs = synth.boxes(B, cfgs, 2 + rank)
+    centers = torch.as_tensor(np.array([r['center'] for r in recs]), dtype=torch.float64, device=dev)
+    scales = torch.as_tensor(np.array([r['scale'] for r in recs]), dtype=torch.float64, device=dev)
+    host_sets = [synth.crops(B, cfgs, 100 * rank + i).pin_memory() for i in range(n_sets)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    gathered = torch.empty((world * B, 7), device=dev, dtype=torch.float64) if dist else None
+
+    def step(i):
+        pose = one_step(ego, dev_sets[i % n_sets], centers, scales, K)
+        if dist:
+            dist.all_gather_into_tensor(gathered, pose)
+        return pose
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        # ---- e2e: public API from pinned host memory, H2D + D2H inside the timed region
+        out_host = torch.empty((B, 7), dtype=torch.float64).pin_memory()
+
+        def e2e_step(i):
+            x = host_sets[i % n_sets].to(dev, non_blocking=True)
+            pose = ego.forward_crops(x, centers, scales, K=K, alpha_mode='proj')
+            if dist:
+                dist.all_gather_into_tensor(gathered, pose)
+            out_host.copy_(pose, non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- per-kernel-class timing for the roofline block (rank 0)
+        classes, hc_ms = profile_hc(ego, dev_sets[0]) if rank == 0 else ({}, 0.0)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    total_crops = world * B * args.steps
+    value = total_crops / (ms * 1e-3)
+    e2e = total_crops / (ms_e2e * 1e-3)
+    st = ego.HC.stats()
+    line = {
+        'metric': METRIC, 'value': round(value, 1), 'unit': 'crops/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16' if args.precision == 'fp16' else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'configs[1]+[2]: full per-crop path (HRNet-W48 heatmap+coords, argmax+soft-argmax '
+                               'decode, inverse affine, lifter, pose solve), 256x256 crops',
+                   'batch_per_gpu': B, 'global_batch': world * B, 'sharding': 'crops block-partitioned across ranks, '
+                   'NCCL all_gather of [B,7] poses per step' if world > 1 else 'single GPU',
+                   'l2': 'rotating %d distinct input batches (%.0f MB) > 126 MB L2; activation workspace %.0f MB' % (
+                       n_sets, n_sets * B * 3 * 256 * 256 * 4 / 1e6,
+                       ego.HC._workspace.numel() / 1e6 if ego.HC._workspace is not None else 0),
+                   'hc_precision': args.precision, 'tc_conv_launches': st['tc_launches'], 'hc_launches': st['launches']},
+        'e2e': {'value': round(e2e, 1), 'unit': 'crops/s', 'h2d_bytes_per_step': B * 3 * 256 * 256 * 4,
+                'd2h_bytes_per_step': B * 7 * 8, 'ms_per_step': round(ms_e2e / args.steps, 4)},
+        'gpu_launches': launches_per_step(ego) * args.steps,
+        'clocks': clocks,
+    }
+    if classes:
+        line['roofline'] = roofline_block(classes, hc_ms, pk)
+        line['hc_roofline'] = {
+            'tensor_frac': round(value / world * 2 * st['macs_per_crop'] / (pk['bf16_tflops_sustained'] * 1e12), 4),
+            'hbm_frac': round(value / world * (st['act_bytes_per_crop'] + st['weight_bytes'] / B) / (pk['hbm_gbs'] * 1e9), 4),
+            'flops_per_crop': 2 * st['macs_per_crop'], 'algorithmic_bytes_per_crop': st['act_bytes_per_crop'],
+            'weight_bytes': st['weight_bytes'], 'peaks': pk, 'hc_ms_per_batch_profiled': round(hc_ms, 3)}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, times = cpu_pipeline_rate(cfgs, args.cpu_baseline_crops, 3, cores)
+        line['cpu_baseline'] = {'value': round(rate, 3), 'unit': 'crops/s', 'cores': cores, 'kind': 'port',
+                                'sample': '3 timed passes of %d crops (+1 warm-up), oracle port on torch-CPU fp32 '
+                                          '(median %.2f s/pass)' % (args.cpu_baseline_crops, float(np.median(times)))}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

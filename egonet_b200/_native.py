@@ -24,6 +24,12 @@ class EgnError(RuntimeError):
     """A C-ABI entry returned a negative status (message from egn_last_error)."""
 
 
+class OpInfo(ctypes.Structure):
+    _fields_ = [('kind', c_int), ('use_tc', c_int), ('Cin', c_int), ('Cout', c_int), ('H', c_int), ('W', c_int),
+                ('OH', c_int), ('OW', c_int), ('ksize', c_int), ('stride', c_int), ('has_res', c_int),
+                ('macs', c_int64), ('act_bytes', c_int64), ('weight_bytes', c_int64), ('name', ctypes.c_char * 96)]
+
+
 class HRNetCfg(ctypes.Structure):
     _fields_ = [
         ('in_channels', c_int), ('input_w', c_int), ('input_h', c_int),
@@ -70,7 +76,9 @@ SIGNATURES = {
     'egn_lifter_forward': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'egn_pose_solve': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_double, c_double, c_int,
                                c_void_p, c_void_p, c_void_p]),
-    'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
+    'egn_hrnet_op_info': (c_int, [c_void_p, c_int, POINTER(OpInfo)]),
+    'egn_hrnet_profile': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
 

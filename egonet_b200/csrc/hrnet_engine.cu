@@ -547,6 +547,95 @@ static std::vector<float> linspace01(int n) {
 
 }  // namespace egn
 
+namespace egn {
+static char* ws_base(void* workspace) {
+  // 1 KB aligned base inside the caller's buffer
+  uintptr_t p = reinterpret_cast<uintptr_t>(workspace);
+  return reinterpret_cast<char*>((p + 1023) & ~uintptr_t(1023));
+}
+
+// Replays the op list on `st`.  If `events` is non-null it must hold ops.size()+1 events; one is
+// recorded before every op and one after the last (per-op device timing for the roofline report).
+static int run_ops(egn_hrnet* h, const float* x, int batch, float* heatmap_out, float* coords_out,
+                   float* logits_out, void* workspace, cudaStream_t st, cudaEvent_t* events) {
+  char* base = ws_base(workspace);
+  const size_t es = dtype_size(h->dt);
+  auto ptr = [&](int id) -> void* {
+    return id < 0 ? nullptr : base + (size_t)h->tensors[id].offset * (size_t)batch * es;
+  };
+  int op_index = 0;
+  for (const Op& op : h->ops) {
+    if (events) cudaEventRecord(events[op_index], st);
+    ++op_index;
+    switch (op.kind) {
+      case Op::STEM: {
+        const TensorInfo& to = h->tensors[op.out];
+        StemArgs a{};
+        a.x = x;
+        a.out = ptr(op.out);
+        a.w = h->weights[op.wi].d_simt;
+        a.bias = h->weights[op.wi].d_bias;
+        a.B = batch;
+        a.Cin = h->cfg.in_channels;
+        a.H = h->cfg.input_h;
+        a.W = h->cfg.input_w;
+        a.OH = to.H;
+        a.OW = to.W;
+        if (int rc = launch_stem(h->dt, a, st)) return rc;
+        break;
+      }
+      case Op::CONV: {
+        ConvArgs a = conv_shape(h, op, batch);
+        a.in = ptr(op.in);
+        a.out = ptr(op.out);
+        a.res = ptr(op.res);
+        a.bias = h->weights[op.wi].d_bias;
+        a.heatmap = op.write_heatmap ? heatmap_out : nullptr;
+        a.xs = h->d_xs;
+        a.ys = h->d_ys;
+        const int rc = op.use_tc ? launch_conv_tc(h->weights[op.wi].tc, a, st)
+                                 : launch_conv_simt(h->dt, a, h->weights[op.wi].d_simt, st);
+        if (rc) return rc;
+        break;
+      }
+      case Op::FUSE: {
+        const TensorInfo& to = h->tensors[op.out];
+        FuseArgs a{};
+        a.out = ptr(op.out);
+        a.nterms = op.nterms;
+        for (int j = 0; j < op.nterms; ++j) {
+          a.term[j] = ptr(op.term[j]);
+          a.shift[j] = op.shift[j];
+        }
+        a.B = batch;
+        a.H = to.H;
+        a.W = to.W;
+        a.Cp = to.Cp;
+        if (int rc = launch_fuse(h->dt, a, st)) return rc;
+        break;
+      }
+      case Op::TAIL: {
+        if (!coords_out && !logits_out) break;
+        const TensorInfo& ti = h->tensors[op.in];
+        HeadTailArgs a{};
+        a.in = ptr(op.in);
+        a.w = h->weights[op.wi].d_simt;
+        a.bias = h->weights[op.wi].d_bias;
+        a.coords = coords_out;
+        a.logits = logits_out;
+        a.B = batch;
+        a.L = ti.H * ti.W * ti.Cp;
+        a.Cout = h->weights[op.wi].Cout;
+        if (int rc = launch_head_tail(h->dt, a, st)) return rc;
+        break;
+      }
+    }
+  }
+  if (events) cudaEventRecord(events[op_index], st);
+  return EGN_OK;
+}
+}  // namespace egn
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -712,11 +801,6 @@ size_t egn_hrnet_workspace_bytes(const egn_hrnet* h, int batch) {
   return (size_t)h->ws_per_crop * (size_t)batch * egn::dtype_size(h->dt) + 1024;
 }
 
-static char* ws_base(void* workspace) {
-  // 1 KB aligned base inside the caller's buffer
-  uintptr_t p = reinterpret_cast<uintptr_t>(workspace);
-  return reinterpret_cast<char*>((p + 1023) & ~uintptr_t(1023));
-}
 
 int egn_hrnet_forward(egn_hrnet* h, const float* x, int batch, float* heatmap_out, float* coords_out,
                       float* logits_out, void* workspace, size_t workspace_bytes, void* stream) {
@@ -736,78 +820,7 @@ int egn_hrnet_forward(egn_hrnet* h, const float* x, int batch, float* heatmap_ou
   }
   EGN_REQUIRE(h->cfg.head_type == EGN_HEAD_COORDINATES || (!coords_out && !logits_out),
               "coords/logits outputs need the coordinate head");
-  cudaStream_t st = as_stream(stream);
-  char* base = ws_base(workspace);
-  const size_t es = dtype_size(h->dt);
-  auto ptr = [&](int id) -> void* {
-    return id < 0 ? nullptr : base + (size_t)h->tensors[id].offset * (size_t)batch * es;
-  };
-  for (const Op& op : h->ops) {
-    switch (op.kind) {
-      case Op::STEM: {
-        const TensorInfo& to = h->tensors[op.out];
-        StemArgs a{};
-        a.x = x;
-        a.out = ptr(op.out);
-        a.w = h->weights[op.wi].d_simt;
-        a.bias = h->weights[op.wi].d_bias;
-        a.B = batch;
-        a.Cin = h->cfg.in_channels;
-        a.H = h->cfg.input_h;
-        a.W = h->cfg.input_w;
-        a.OH = to.H;
-        a.OW = to.W;
-        if (int rc = launch_stem(h->dt, a, st)) return rc;
-        break;
-      }
-      case Op::CONV: {
-        ConvArgs a = conv_shape(h, op, batch);
-        a.in = ptr(op.in);
-        a.out = ptr(op.out);
-        a.res = ptr(op.res);
-        a.bias = h->weights[op.wi].d_bias;
-        a.heatmap = op.write_heatmap ? heatmap_out : nullptr;
-        a.xs = h->d_xs;
-        a.ys = h->d_ys;
-        const int rc = op.use_tc ? launch_conv_tc(h->weights[op.wi].tc, a, st)
-                                 : launch_conv_simt(h->dt, a, h->weights[op.wi].d_simt, st);
-        if (rc) return rc;
-        break;
-      }
-      case Op::FUSE: {
-        const TensorInfo& to = h->tensors[op.out];
-        FuseArgs a{};
-        a.out = ptr(op.out);
-        a.nterms = op.nterms;
-        for (int j = 0; j < op.nterms; ++j) {
-          a.term[j] = ptr(op.term[j]);
-          a.shift[j] = op.shift[j];
-        }
-        a.B = batch;
-        a.H = to.H;
-        a.W = to.W;
-        a.Cp = to.Cp;
-        if (int rc = launch_fuse(h->dt, a, st)) return rc;
-        break;
-      }
-      case Op::TAIL: {
-        if (!coords_out && !logits_out) break;
-        const TensorInfo& ti = h->tensors[op.in];
-        HeadTailArgs a{};
-        a.in = ptr(op.in);
-        a.w = h->weights[op.wi].d_simt;
-        a.bias = h->weights[op.wi].d_bias;
-        a.coords = coords_out;
-        a.logits = logits_out;
-        a.B = batch;
-        a.L = ti.H * ti.W * ti.Cp;
-        a.Cout = h->weights[op.wi].Cout;
-        if (int rc = launch_head_tail(h->dt, a, st)) return rc;
-        break;
-      }
-    }
-  }
-  return EGN_OK;
+  return egn::run_ops(h, x, batch, heatmap_out, coords_out, logits_out, workspace, as_stream(stream), nullptr);
 }
 
 int egn_hrnet_read_tap(egn_hrnet* h, const char* name, int batch, const void* workspace, float* out,
@@ -819,7 +832,7 @@ int egn_hrnet_read_tap(egn_hrnet* h, const char* name, int batch, const void* wo
   EGN_REQUIRE(it != h->taps.end(), "egn_hrnet_read_tap: unknown tap '%s'", name);
   if (int rc = require_device()) return rc;
   const TensorInfo& t = h->tensors[it->second];
-  char* base = ws_base(const_cast<void*>(workspace));
+  char* base = egn::ws_base(const_cast<void*>(workspace));
   const void* src = base + (size_t)t.offset * (size_t)batch * dtype_size(h->dt);
   if (dims) {
     dims[0] = t.C;
@@ -827,6 +840,71 @@ int egn_hrnet_read_tap(egn_hrnet* h, const char* name, int batch, const void* wo
     dims[2] = t.W;
   }
   return launch_nhwc_to_nchw(h->dt, src, out, batch, t.H, t.W, t.Cp, t.C, as_stream(stream));
+}
+
+int egn_hrnet_profile(egn_hrnet* h, const float* x, int batch, void* workspace, size_t workspace_bytes,
+                      void* stream, float* op_ms) {
+  using namespace egn;
+  EGN_REQUIRE(h && x && op_ms && batch > 0, "egn_hrnet_profile: bad argument");
+  if (!h->finalized) {
+    set_error("egn_hrnet_profile called before egn_hrnet_finalize");
+    return EGN_ERR_STATE;
+  }
+  if (int rc = require_device()) return rc;
+  if (!workspace || workspace_bytes < egn_hrnet_workspace_bytes(h, batch)) {
+    set_error("workspace too small: need %zu bytes for batch %d", egn_hrnet_workspace_bytes(h, batch), batch);
+    return EGN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  std::vector<cudaEvent_t> ev(h->ops.size() + 1);
+  for (auto& e : ev) EGN_CUDA_CHECK(cudaEventCreate(&e));
+  // coords/logits scratch is not needed: the tail is skipped without outputs, so time it with a dummy
+  int rc = run_ops(h, x, batch, nullptr, nullptr, nullptr, workspace, st, ev.data());
+  if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("egn_hrnet_profile: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = EGN_ERR_CUDA;
+  }
+  if (!rc)
+    for (size_t i = 0; i < h->ops.size(); ++i) cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int egn_hrnet_op_info(const egn_hrnet* h, int i, egn_op_info* o) {
+  using namespace egn;
+  EGN_REQUIRE(h && o && i >= 0 && i < (int)h->ops.size(), "egn_hrnet_op_info: bad index");
+  const Op& op = h->ops[i];
+  const int64_t es = (int64_t)dtype_size(h->dt);
+  auto sz = [&](int id) { return id < 0 ? (int64_t)0 : (int64_t)h->tensors[id].H * h->tensors[id].W * h->tensors[id].Cp * es; };
+  *o = egn_op_info{};
+  o->kind = (int)op.kind;
+  o->use_tc = op.use_tc ? 1 : 0;
+  o->stride = op.stride;
+  o->has_res = op.res >= 0;
+  if (op.out >= 0) {
+    o->OH = h->tensors[op.out].H; o->OW = h->tensors[op.out].W; o->Cout = h->tensors[op.out].C;
+  }
+  if (op.in >= 0) {
+    o->H = h->tensors[op.in].H; o->W = h->tensors[op.in].W; o->Cin = h->tensors[op.in].C;
+  }
+  o->act_bytes = sz(op.in) + sz(op.res) + sz(op.out);
+  for (int j = 0; j < op.nterms; ++j) o->act_bytes += sz(op.term[j]);
+  if (op.kind == Op::STEM) {
+    o->Cin = h->cfg.in_channels; o->H = h->cfg.input_h; o->W = h->cfg.input_w; o->ksize = 3; o->stride = 2;
+    o->act_bytes += (int64_t)h->cfg.in_channels * h->cfg.input_h * h->cfg.input_w * 4;
+  }
+  if (op.wi >= 0) {
+    const ConvWeights& w = h->weights[op.wi];
+    const int kh = w.k >= 1000 ? w.k / 1000 : w.k, kw = w.k >= 1000 ? w.k % 1000 : w.k;
+    o->ksize = kh;
+    const int64_t opix = op.kind == Op::TAIL ? 1 : (int64_t)o->OH * o->OW;
+    o->macs = (int64_t)w.Cout * w.Cin * kh * kw * opix;
+    o->weight_bytes = (int64_t)w.Cout_p * w.Cin_p * kh * kw * ((op.kind == Op::CONV && !w.force_fp32 && h->dt == Dtype::F16 && op.use_tc) ? 2 : 4);
+    snprintf(o->name, sizeof(o->name), "%s", w.conv_key.c_str());
+  } else if (op.kind == Op::FUSE) {
+    snprintf(o->name, sizeof(o->name), "%s", h->tensors[op.out].tap.c_str());
+  }
+  return EGN_OK;
 }
 
 int64_t egn_hrnet_macs_per_crop(const egn_hrnet* h) { return h ? h->macs : 0; }

@@ -21,6 +21,9 @@ def pose_solve(kpts_3d, kpts_2d=None, K=None, alpha_mode='trans', want_rotation=
         raise RuntimeError('native pose_solve has no CPU path')
     x = kpts_3d.detach().to(torch.float64).contiguous()
     n = x.shape[0]
+    if n == 0:
+        empty = torch.empty((0, 7), device=x.device, dtype=torch.float64)
+        return (empty, torch.empty((0, 3, 3), device=x.device, dtype=torch.float64)) if want_rotation else empty
     x = x.view(n, -1, 3)
     p = x.shape[1]
     if alpha_mode == 'trans':

@@ -142,6 +142,20 @@ EGN_API int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w
                      int Cin, int Cout, int ksize, int stride, int relu, void* stream);
 
 /* Introspection for bench/roofline accounting. */
+typedef struct {
+  int kind;            /* 0 stem conv, 1 fused conv, 2 cross-resolution fuse, 3 head tail        */
+  int use_tc;          /* 1 if this conv runs on the tcgen05 kernel                               */
+  int Cin, Cout, H, W, OH, OW, ksize, stride, has_res;
+  int64_t macs;        /* per crop                                                                */
+  int64_t act_bytes;   /* algorithmic activation bytes per crop (inputs read once + output)       */
+  int64_t weight_bytes;/* per launch                                                              */
+  char name[96];       /* state_dict key of the conv / tap name of the fuse output                */
+} egn_op_info;
+EGN_API int egn_hrnet_op_info(const egn_hrnet* h, int i, egn_op_info* out);
+/* One forward with a CUDA event between every launch; op_ms[egn_hrnet_num_launches] receives the
+ * device time of each op (synchronises the stream). */
+EGN_API int egn_hrnet_profile(egn_hrnet* h, const float* x, int batch, void* workspace,
+                      size_t workspace_bytes, void* stream, float* op_ms);
 EGN_API int64_t egn_hrnet_macs_per_crop(const egn_hrnet* h);
 EGN_API int egn_hrnet_num_launches(const egn_hrnet* h);        /* kernels per forward          */
 EGN_API int egn_hrnet_num_tc_launches(const egn_hrnet* h);     /* of which tcgen05 convs       */

@@ -13,20 +13,17 @@ import torch
 
 from . import affine_ref, hrnet_ref, lifter_ref, pose_ref
 
-# typical KITTI P2 intrinsics (car_instance.py:933-935 upstream debug constant)
-KITTI_K = np.array([[707.0493, 0.0, 604.0814], [0.0, 707.0493, 180.5066], [0.0, 0.0, 1.0]])
+from egonet_b200.synth import KITTI_K  # noqa: E402,F401
 
 
 def synth_crops(n, cfgs, seed=0):
-    """Seeded N(0,1) crops [n,3,H,W] float32 (ImageNet-normalised images are ~N(0,1))."""
-    W, H = cfgs['heatmapModel']['input_size']
-    rng = np.random.Generator(np.random.PCG64(seed))
-    return torch.from_numpy(rng.standard_normal((n, 3, H, W), dtype=np.float32))
+    from egonet_b200 import synth
+    return synth.crops(n, cfgs, seed)
 
 
 def synth_boxes(n, cfgs, seed=2, enlarge=1.2):
-    """KITTI-shaped detector boxes -> records with center/scale as the reference
-    derives them (tools/inference.py:113-116 then egonet.py:141-142)."""
+    """Same recipe as ``egonet_b200.synth.boxes`` but through the ORACLE's own modify_bbox, so the
+    two implementations of the box geometry are cross-checked by the golden pipeline test."""
     W, H = cfgs['heatmapModel']['input_size']
     target_ar = H / W
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -147,54 +147,14 @@ def state_dict_spec(cfgs, in_channels=None):
 # deterministic synthetic weights (no checkpoints are available offline)
 # ----------------------------------------------------------------------------
 def make_weights(cfgs, seed=1, in_channels=None):
-    """Seeded synthetic ``HC`` state dict (torch fp32 tensors, reference key set).
-
-    numpy ``PCG64`` streams are used instead of ``torch.manual_seed`` so that the
-    same bits are regenerated on any machine / torch version.  Convolution
-    weights are uniform with variance 1/fan_in; every BatchNorm gets randomised
-    affine parameters and running statistics so that BN folding is exercised;
-    the second BN of each residual block is damped so activations stay O(1)
-    through the ~90 sequential layers.
-    """
-    rng = np.random.Generator(np.random.PCG64(seed))
-    spec = state_dict_spec(cfgs, in_channels)
-    sd = OrderedDict()
-    for key, shape in spec.items():
-        leaf = key.rsplit('.', 1)[1]
-        owner = key.rsplit('.', 1)[0]
-        if leaf == 'num_batches_tracked':
-            sd[key] = torch.tensor(0, dtype=torch.long)
-            continue
-        if len(shape) == 4:
-            fan_in = shape[1] * shape[2] * shape[3]
-            b = np.sqrt(3.0 / fan_in)
-            arr = rng.uniform(-b, b, size=shape)
-        elif leaf == 'running_var':
-            arr = rng.uniform(0.5, 1.5, size=shape)
-        elif leaf == 'running_mean':
-            arr = rng.normal(0.0, 0.1, size=shape)
-        elif leaf == 'weight':  # BN gamma
-            damp = owner.endswith('bn2') or owner.endswith('bn3')
-            is_block_tail = damp and ('branches' in owner or 'layer1' in owner or 'head2' in owner)
-            gain = 0.35 if is_block_tail else (0.5 if 'fuse_layers' in owner else 1.0)
-            arr = rng.uniform(0.5, 1.5, size=shape) * gain
-        elif leaf == 'bias':
-            arr = rng.normal(0.0, 0.1, size=shape)
-        else:
-            raise KeyError(key)
-        sd[key] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
-    return sd
+    """Seeded synthetic ``HC`` state dict over this module's own key inventory."""
+    from egonet_b200 import synth
+    return synth.hc_weights(state_dict_spec(cfgs, in_channels), seed)
 
 
 def weights_digest(sd):
-    """Order-dependent fp64 checksum of a state dict (to pin regenerated weights)."""
-    acc = 0.0
-    for i, (k, v) in enumerate(sd.items()):
-        if v.dtype.is_floating_point:
-            a = v.double().flatten()
-            w = torch.arange(1, a.numel() + 1, dtype=torch.float64) % 97 + 1.0
-            acc += float((a * w).sum()) * ((i % 13) + 1)
-    return acc
+    from egonet_b200 import synth
+    return synth.weights_digest(sd)
 
 
 # ----------------------------------------------------------------------------

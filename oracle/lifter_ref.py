@@ -45,39 +45,13 @@ def state_dict_spec(cfgs):
 
 
 def make_weights(cfgs, seed=11):
-    """Seeded synthetic ``L`` state dict (PCG64; nn.Linear-like uniform init)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    sd = OrderedDict()
-    for key, shape in state_dict_spec(cfgs).items():
-        leaf = key.rsplit('.', 1)[1]
-        if leaf == 'num_batches_tracked':
-            sd[key] = torch.tensor(0, dtype=torch.long)
-            continue
-        if len(shape) == 2:
-            b = np.sqrt(3.0 / shape[1])
-            arr = rng.uniform(-b, b, size=shape)
-        elif leaf == 'running_var':
-            arr = rng.uniform(0.5, 1.5, size=shape)
-        elif leaf == 'running_mean':
-            arr = rng.normal(0.0, 0.1, size=shape)
-        elif leaf == 'weight':
-            arr = rng.uniform(0.5, 1.5, size=shape)
-        else:
-            arr = rng.normal(0.0, 0.1, size=shape)
-        sd[key] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
-    return sd
+    from egonet_b200 import synth
+    return synth.lifter_weights(state_dict_spec(cfgs), seed)
 
 
 def make_stats(cfgs, seed=12, image_size=(1242, 375)):
-    """Synthetic ``LS`` statistics dict (SURVEY.md 8d recipe), fp64 [1,n] arrays."""
-    fc = cfgs['FCModel']
-    rng = np.random.Generator(np.random.PCG64(seed))
-    nin, nout = fc['input_size'], fc['output_size']
-    mean_in = np.empty((1, nin))
-    mean_in[0, 0::2] = rng.uniform(0, image_size[0], nin // 2)
-    mean_in[0, 1::2] = rng.uniform(0, image_size[1], nin // 2)
-    return {'mean_in': mean_in, 'std_in': rng.uniform(20, 200, (1, nin)),
-            'mean_out': rng.normal(0, 1, (1, nout)), 'std_out': rng.uniform(0.2, 2, (1, nout))}
+    from egonet_b200 import synth
+    return synth.lifter_stats(cfgs, seed, image_size)
 
 
 def _lin_bn_relu(sd, x, lin, bn):
