@@ -26,6 +26,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -163,7 +164,8 @@ struct TcParams {
   int tiles_w, tiles_h;      // tiles per image along w / h
   int n_tile;                // UMMA N (output channels per CTA)
   int kc;                    // channels per pipeline stage (= swizzle bytes / 2)
-  int kchunks;               // Cin_p / kc
+  int kchunks;               // ceil(Cin_p / kc)
+  int cin_k;                 // kchunks * kc: per-tap K extent of the zero-padded weight matrix
   int stages;
   uint32_t a_bytes, b_bytes; // TMA transaction bytes per stage
   uint32_t tmem_cols;
@@ -243,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_load_5d(smem_a + (size_t)s * a_stage, &map_a, &full_bar[s], wp * p.Cin_p + c0, ow0 + dw, hp, oh0 + dh,
                       b0);
         }
-        tma_load_2d(smem_b + (size_t)s * b_stage, &map_b, &full_bar[s], tap * p.Cin_p + c0, n0);
+        tma_load_2d(smem_b + (size_t)s * b_stage, &map_b, &full_bar[s], tap * p.cin_k + c0, n0);
       }
     }
   } else if (warp == 1) {
@@ -367,7 +369,7 @@ struct TcConvPlan {
   // shape (batch independent)
   int H, W, Cin_p, OH, OW, Cout_p, Cout, ksize, stride, pad;
   int sw;          // swizzle bytes 32 / 64 / 128
-  int kc, kchunks, n_tile, n_tiles, stages;
+  int kc, kchunks, cin_k, n_tile, n_tiles, stages;
   int TW, TH, TB;
   uint32_t tmem_cols;
   size_t smem_bytes;
@@ -411,9 +413,16 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   TcConvPlan* p = new TcConvPlan();
   p->H = a.H; p->W = a.W; p->Cin_p = a.Cin_p; p->OH = a.OH; p->OW = a.OW;
   p->Cout_p = a.Cout_p; p->Cout = a.Cout; p->ksize = a.ksize; p->stride = a.stride; p->pad = a.pad;
-  p->sw = a.Cin_p % 64 == 0 ? 128 : (a.Cin_p % 32 == 0 ? 64 : 32);
+  // Always 128-byte swizzle rows (64 channels per pipeline stage).  When Cin is not a multiple of
+  // 64 the last chunk of a tap is partial: the weight matrix is zero-padded per tap to a multiple
+  // of 64 channels, so whatever the activation box holds in those lanes (TMA zero fill past the
+  // channel extent, or the neighbouring pixel's channels in the stride-2 view) is multiplied by 0.
+  const int force_sw = getenv("EGN_TC_SWIZZLE") ? atoi(getenv("EGN_TC_SWIZZLE")) : 0;
+  p->sw = force_sw ? force_sw : 128;
+  if (force_sw == 0 && a.Cin_p <= 16) p->sw = 32;
+  else if (force_sw == 0 && a.Cin_p <= 32) p->sw = 64;
   p->kc = p->sw / 2;
-  p->kchunks = a.Cin_p / p->kc;
+  p->kchunks = ceil_div(a.Cin_p, p->kc);
   p->n_tiles = a.Cout_p > 256 ? 2 : 1;
   p->n_tile = a.Cout_p / p->n_tiles;
   p->TW = std::min(a.OW, 128);
@@ -429,14 +438,16 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
   p->stages = (int)std::max<size_t>(2, st_count);
   p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
-  // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_p] fp16
+  // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
   const int taps = a.ksize * a.ksize;
-  const size_t K = (size_t)taps * a.Cin_p;
-  std::vector<__half> w((size_t)a.Cout_p * K);
+  const int cin_k = p->kchunks * p->kc;
+  p->cin_k = cin_k;
+  const size_t K = (size_t)taps * cin_k;
+  std::vector<__half> w((size_t)a.Cout_p * K, __float2half_rn(0.f));
   for (int o = 0; o < a.Cout_p; ++o)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < a.Cin_p; ++c)
-        w[(size_t)o * K + (size_t)t * a.Cin_p + c] = __float2half_rn(wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o]);
+        w[(size_t)o * K + (size_t)t * cin_k + c] = __float2half_rn(wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o]);
   p->w_bytes = w.size() * sizeof(__half);
   if (cudaMalloc(&p->d_w, p->w_bytes) != cudaSuccess ||
       cudaMemcpy(p->d_w, w.data(), p->w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -534,7 +545,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
   tp.tiles_w = ceil_div(p->OW, p->TW);
   tp.tiles_h = ceil_div(p->OH, p->TH);
-  tp.n_tile = p->n_tile; tp.kc = p->kc; tp.kchunks = p->kchunks; tp.stages = p->stages;
+  tp.n_tile = p->n_tile; tp.kc = p->kc; tp.kchunks = p->kchunks; tp.cin_k = p->cin_k; tp.stages = p->stages;
   tp.a_bytes = (uint32_t)(p->TW * p->TH * p->TB) * (uint32_t)p->sw;
   tp.b_bytes = (uint32_t)p->n_tile * (uint32_t)p->sw;
   tp.tmem_cols = p->tmem_cols;
@@ -551,3 +562,126 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
 }
 
 }  // namespace egn
+
+// ---------------------------------------------------------------------------
+// Hardware probe: does a K-major swizzled UMMA descriptor whose start address is offset by an
+// arbitrary number of ROWS (not a multiple of the 8-row swizzle atom) address the rows TMA wrote?
+// D[i][n] = sum_k A[off+i][k] * B[n][k] with B = identity, for a few encodings of `base_offset`.
+// Used once to validate the flattened-run conv kernel's operand addressing.
+// ---------------------------------------------------------------------------
+namespace egn {
+
+template <int SW>
+__global__ void __launch_bounds__(128)
+umma_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int row_off,
+                  int bo_mode, float* __restrict__ out /* [128][SW/2] */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int KC = SW / 2;
+  uint8_t* sa = smem;                       // 256 rows x SW bytes
+  uint8_t* sb = smem + 256 * SW;            // KC rows x SW bytes (1024-aligned since 256*SW is)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 8192);
+  uint64_t* bar2 = bar + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 256 * SW + KC * SW);
+    tma_load_2d(sa, &map_a, bar, 0, 0);
+    tma_load_2d(sb, &map_b, bar, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t start = smem_u32(sa) + (uint32_t)row_off * SW;
+    uint64_t adesc = make_smem_desc(start, SW);
+    uint32_t bo = 0;
+    if (bo_mode == 1) bo = (uint32_t)row_off & 7u;          // row phase inside the 8-row atom
+    if (bo_mode == 2) bo = (start >> 7) & 7u;               // literal (addr >> 7) & 7
+    adesc |= (uint64_t)bo << 49;
+    const uint64_t bdesc = make_smem_desc(smem_u32(sb), SW);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(KC >> 3) << 17) | ((128u >> 4) << 24);
+#pragma unroll
+    for (int k = 0; k < SW / 32; ++k) umma_f16(tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+    umma_commit(bar2);
+  }
+  __syncthreads();
+  mbar_wait(bar2, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < KC; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[row * KC + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+template <int SW>
+static int run_probe(int row_off, int bo_mode, const __half* d_a, const __half* d_b, float* d_out, cudaStream_t st) {
+  constexpr int KC = SW / 2;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return EGN_ERR_CUDA;
+  }
+  CUtensorMap ma, mb;
+  const cuuint32_t es[2] = {1, 1};
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)KC, 256};
+    const cuuint64_t gstr[1] = {(cuuint64_t)KC * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, 256};
+    if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(d_a), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(SW), CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("probe: encode A failed");
+      return EGN_ERR_CUDA;
+    }
+  }
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)KC, (cuuint64_t)KC};
+    const cuuint64_t gstr[1] = {(cuuint64_t)KC * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)KC};
+    if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(d_b), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(SW), CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("probe: encode B failed");
+      return EGN_ERR_CUDA;
+    }
+  }
+  const size_t smem = 1024 + 256 * SW + 8192 + 64;
+  EGN_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<SW><<<1, 128, smem, st>>>(ma, mb, row_off, bo_mode, d_out);
+  EGN_LAUNCH_CHECK("umma_probe_kernel");
+  EGN_CUDA_CHECK(cudaStreamSynchronize(st));
+  return EGN_OK;
+}
+
+}  // namespace egn
+
+extern "C" int egn_debug_umma_probe(int swizzle_bytes, int row_off, int bo_mode, const void* a_f16, const void* b_f16,
+                                    float* out, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(a_f16 && b_f16 && out, "egn_debug_umma_probe: null pointer");
+  EGN_REQUIRE(row_off >= 0 && row_off <= 128, "egn_debug_umma_probe: row_off out of range");
+  if (int rc = require_device()) return rc;
+  const __half* a = static_cast<const __half*>(a_f16);
+  const __half* b = static_cast<const __half*>(b_f16);
+  switch (swizzle_bytes) {
+    case 128: return run_probe<128>(row_off, bo_mode, a, b, out, as_stream(stream));
+    case 64: return run_probe<64>(row_off, bo_mode, a, b, out, as_stream(stream));
+    case 32: return run_probe<32>(row_off, bo_mode, a, b, out, as_stream(stream));
+  }
+  set_error("egn_debug_umma_probe: swizzle must be 32, 64 or 128");
+  return EGN_ERR_INVALID;
+}

@@ -141,6 +141,12 @@ EGN_API int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w
                      const float* bias_host, const void* res, void* out, int B, int H, int W,
                      int Cin, int Cout, int ksize, int stride, int relu, void* stream);
 
+/* Hardware probe (debug): one 128 x KC x KC UMMA whose A descriptor starts `row_off` rows into a
+ * TMA-written swizzled tile; bo_mode selects the descriptor base-offset encoding under test.
+ * a: device fp16 [256][KC], b: device fp16 [KC][KC], out: device fp32 [128][KC], KC = swizzle/2. */
+EGN_API int egn_debug_umma_probe(int swizzle_bytes, int row_off, int bo_mode, const void* a_f16,
+                         const void* b_f16, float* out, void* stream);
+
 /* Introspection for bench/roofline accounting. */
 typedef struct {
   int kind;            /* 0 stem conv, 1 fused conv, 2 cross-resolution fuse, 3 head tail        */
