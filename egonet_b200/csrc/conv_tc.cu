@@ -346,6 +346,209 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------
+// v2: "window run" kernel for stride-1 convs (3x3 pad 1 and 1x1)
+//
+// v1 re-fetches the activation tile from L2 once per filter tap (9x the bytes).  Here a CTA loads
+// ONE zero-padded window of the input -- TBW images x (THW+2) rows x (W+2) pixels x Cin, a single
+// TMA box per 64-channel chunk whose out-of-image parts are zero-filled by the TMA unit -- and keeps
+// it in shared memory.  In the flattened window (row pitch Wp = W+2 pixels) the operand of tap
+// (r,s) for output run position m is simply window row m + r*Wp + s, so all nine taps are the SAME
+// shared-memory buffer addressed through UMMA descriptors whose start address is shifted by
+// (r*Wp + s) rows.  (Swizzle is applied on absolute smem address bits, so a row shift that is not
+// a multiple of the 8-row atom is legal with base_offset = 0: verified on hardware by
+// egn_debug_umma_probe, profiles/r01_umma_row_offset_probe.json.)  The two pixels per image row
+// that fall on the window border produce junk accumulator rows which the epilogue skips.
+//
+// Loop order is (tap, chunk) outer / M-tile inner with all T accumulators resident in TMEM, so
+// every weight tile is fetched once per CTA and streamed through a small ring.
+// ---------------------------------------------------------------------------
+constexpr int kMaxChunks = 6;   // Cin_p <= 384
+constexpr int kMaxBStages = 6;
+
+struct RunParams {
+  int B, H, W, Cout_p, Cout, Cin_p;
+  int taps, relu;
+  int halo, Wp, Hw;          // halo = 1 for 3x3, 0 for 1x1; window = TBW x Hw x Wp pixels
+  int THW, TBW, win_per_img;
+  int lead;                  // halo * (Wp + 1): window row of run position 0
+  int m_run, T;              // run length (rows) and number of 128-row M tiles
+  int rows_alloc;            // smem rows per chunk buffer
+  int n_tile, kchunks, cin_k, b_stages;
+  uint32_t a_bytes, b_bytes, tmem_cols;
+  const float* bias;
+  const __half* res;
+  __half* out;
+  float* heatmap;
+  const float* xs;
+  const float* ys;
+  int coord_maps;
+};
+
+__global__ void __launch_bounds__(kTcThreads)
+conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const RunParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_chunk = (uint32_t)p.rows_alloc * 128u;              // multiple of 1024
+  const uint32_t b_stage = ((uint32_t)p.n_tile * 128u + 1023u) & ~1023u;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.kchunks * a_chunk;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_stage);
+  uint64_t* b_full = a_full + kMaxChunks;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* tmem_full_bar = b_empty + kMaxBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int win = blockIdx.x % p.win_per_img;
+  const int bg = blockIdx.x / p.win_per_img;
+  const int h0 = win * p.THW, b0 = bg * p.TBW;
+  const int n0 = blockIdx.y * p.n_tile;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int c = 0; c < p.kchunks; ++c) mbar_init(&a_full[c], 1);
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_iters = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int c = 0; c < p.kchunks; ++c) {
+        mbar_expect_tx(&a_full[c], p.a_bytes);
+        tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, -p.halo, h0 - p.halo, b0);
+      }
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.b_stages;
+        const uint32_t ph = (uint32_t)(it / p.b_stages) & 1u;
+        mbar_wait(&b_empty[s], ph ^ 1u);
+        mbar_expect_tx(&b_full[s], p.b_bytes);
+        const int tap = it / p.kchunks, c = it - tap * p.kchunks;
+        tma_load_2d(smem_b + (size_t)s * b_stage, &map_b, &b_full[s], tap * p.cin_k + c * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.b_stages;
+        const uint32_t ph = (uint32_t)(it / p.b_stages) & 1u;
+        const int tap = it / p.kchunks, c = it - tap * p.kchunks;
+        if (tap == 0) mbar_wait(&a_full[c], 0);
+        mbar_wait(&b_full[s], ph);
+        tc_fence_after();
+        const int r = tap / 3, q = tap - 3 * r;                 // taps == 1 -> r = q = 0
+        const uint32_t row_shift = (uint32_t)(p.halo ? r * p.Wp + q : 0);
+        const uint32_t a_base = smem_u32(smem_a + (size_t)c * a_chunk) + row_shift * 128u;
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)s * b_stage), 128);
+        const int valid = p.Cin_p - c * 64;
+        const int ksteps = valid >= 64 ? 4 : (valid + 15) / 16;   // skip all-zero K slices of a partial chunk
+        for (int t = 0; t < p.T; ++t) {
+          const uint64_t adesc = make_smem_desc(a_base + (uint32_t)t * 128u * 128u, 128);
+          const uint32_t d = tmem_base + (uint32_t)(t * p.n_tile);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        }
+        umma_commit(&b_empty[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int img_rows = p.Hw * p.Wp;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    for (int t = 0; t < p.T; ++t) {
+      const int m = t * 128 + row;
+      const int pos = m + p.lead;
+      const int bi = pos / img_rows;
+      const int rem = pos - bi * img_rows;
+      const int hp = rem / p.Wp, wp = rem - hp * p.Wp;
+      const int b = b0 + bi, oh = h0 + hp - p.halo, ow = wp - p.halo;
+      const bool valid = m < p.m_run && bi < p.TBW && hp >= p.halo && hp < p.Hw - p.halo && wp >= p.halo &&
+                         wp < p.Wp - p.halo && b < p.B && oh < p.H;
+      const size_t pix = ((size_t)b * p.H + oh) * p.W + ow;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.n_tile);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int n = n0 + c0;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bq.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bq.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bq.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bq.w;
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout_p + n);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 rq = __ldg(rp + h);
+              const __half2* r2 = reinterpret_cast<const __half2*>(&rq);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 rf = __half22float2(r2[j]);
+                f[8 * h + 2 * j] += rf.x;
+                f[8 * h + 2 * j + 1] += rf.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.heatmap) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.Cout) p.heatmap[(((size_t)b * p.Cout + n + j) * p.H + oh) * p.W + ow] = f[j];
+          }
+          if (p.coord_maps) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n + j == p.Cout) f[j] = p.xs[ow];
+              if (n + j == p.Cout + 1) f[j] = p.ys[oh];
+            }
+          }
+          uint4 o[2];
+          __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout_p + n);
+          op[0] = o[0];
+          op[1] = o[1];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -373,6 +576,10 @@ struct TcConvPlan {
   int TW, TH, TB;
   uint32_t tmem_cols;
   size_t smem_bytes;
+  // v2 (window run) configuration; use_run == false -> v1 per-tap kernel
+  bool use_run = false;
+  int halo = 0, Wp = 0, Hw = 0, THW = 0, TBW = 1, T = 1, rows_alloc = 0, b_stages = 2;
+  float run_eff = 0.f;
   __half* d_w = nullptr;      // [Cout_p][taps*Cin_p]
   size_t w_bytes = 0;
   CUtensorMap map_b;
@@ -438,6 +645,80 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
   p->stages = (int)std::max<size_t>(2, st_count);
   p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+  // ---- v2 window-run configuration (stride-1 convs) ----
+  {
+    const char* env = getenv("EGN_TC_V2");
+    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks;
+    if (allow) {
+      const int halo = a.ksize == 3 ? 1 : 0;
+      const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
+      const int taps_n = a.ksize * a.ksize;
+      const size_t b_stage_bytes = ((size_t)p->n_tile * 128 + 1023) & ~(size_t)1023;
+      const int n_it = taps_n * p->kchunks;
+      float best = 0.f;
+      const int Tmax = std::min(8, 512 / p->n_tile);
+      for (int T = 1; T <= Tmax; ++T) {
+        for (int multi = 0; multi < 2; ++multi) {
+          int THW, TBW;
+          if (!multi) {
+            THW = std::min(a.H, (128 * T + 2 * halo) / Wp);
+            TBW = 1;
+            if (THW < 1) continue;
+          } else {
+            THW = a.H;
+            const int img = (a.H + 2 * halo) * Wp;
+            TBW = (128 * T + 2 * lead) / img;
+            if (TBW < 2) continue;
+            TBW = std::min(TBW, 64);
+          }
+          const int Hw = THW + 2 * halo;
+          if (Wp > 256 || Hw > 256) continue;
+          const int rows_win = TBW * Hw * Wp;
+          const int m_run = rows_win - 2 * lead;
+          if (m_run > 128 * T) continue;
+          const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
+          const size_t a_bytes = (size_t)p->kchunks * rows_alloc * 128;
+          int bst = std::min(kMaxBStages, std::max(2, n_it));
+          size_t smem = 1024 + a_bytes + bst * b_stage_bytes + 256;
+          while (smem > 200 * 1024 && bst > 2) {
+            --bst;
+            smem = 1024 + a_bytes + bst * b_stage_bytes + 256;
+          }
+          if (smem > 200 * 1024) continue;
+          // cost model (nominal batch 64): CTAs per SM x (MMA rows + window load + fixed overhead);
+          // two co-resident CTAs overlap each other's load / epilogue phases
+          const int windows = multi ? 1 : ceil_div(a.H, THW);
+          const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
+                                   : (double)a.H * a.W / ((double)windows * T * 128);
+          const bool two_per_sm = smem <= 112 * 1024 && pow2_cols(T * p->n_tile) <= 256;
+          const int ctas = windows * ceil_div(64, TBW) * p->n_tiles;
+          const double cta_cost = T + 0.6 * rows_win / 128.0 + 0.7;
+          const double est = ceil_div(ctas, 148) * cta_cost * (two_per_sm ? 0.7 : 1.0);
+          const float score = (float)(1.0 / est);
+          if (score > best) {
+            best = score;
+            p->use_run = true;
+            p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
+            p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
+            p->smem_bytes = smem;
+            p->tmem_cols = pow2_cols(T * p->n_tile);
+          }
+        }
+      }
+      // v1 keeps the small, weight-dominated maps where the run's junk rows cost more than they save
+      const char* minw = getenv("EGN_TC_V2_MIN_W");
+      if (p->use_run && a.W < (minw ? atoi(minw) : 24) && a.ksize == 3) p->use_run = false;
+      if (p->use_run && p->run_eff < 0.6f) p->use_run = false;
+      if (getenv("EGN_TC_VERBOSE"))
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: %s T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB bst=%d tmem=%u\n", a.ksize, a.ksize,
+                a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->use_run ? "v2-run" : "v1-tap", p->T, p->THW, p->TBW, p->run_eff,
+                p->smem_bytes / 1024, p->b_stages, p->tmem_cols);
+      if (!p->use_run) {
+        p->tmem_cols = pow2_cols(p->n_tile);
+        p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+      }
+    }
+  }
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
   const int taps = a.ksize * a.ksize;
   const int cin_k = p->kchunks * p->kc;
@@ -483,7 +764,15 @@ static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   EncodeTiledFn enc = get_encode_fn();
   const cuuint64_t C = p->Cin_p, W = p->W, H = p->H;
   CUresult r;
-  if (p->stride == 1) {
+  if (p->use_run) {
+    const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)p->Wp, (cuuint32_t)p->Hw, (cuuint32_t)p->TBW};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (p->stride == 1) {
     const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
     const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
     const cuuint32_t box[4] = {(cuuint32_t)p->kc, (cuuint32_t)p->TW, (cuuint32_t)p->TH, (cuuint32_t)p->TB};
@@ -538,6 +827,33 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       it = p->a_maps.emplace(key, m).first;
     }
     ma = it->second;
+  }
+  if (p->use_run) {
+    RunParams rp{};
+    rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->Cin_p;
+    rp.taps = p->ksize * p->ksize; rp.relu = a.relu;
+    rp.halo = p->halo; rp.Wp = p->Wp; rp.Hw = p->Hw; rp.THW = p->THW; rp.TBW = p->TBW;
+    rp.win_per_img = ceil_div(p->H, p->THW);
+    rp.lead = p->halo * (p->Wp + 1);
+    rp.m_run = p->TBW * p->Hw * p->Wp - 2 * rp.lead;
+    rp.T = p->T; rp.rows_alloc = p->rows_alloc;
+    rp.n_tile = p->n_tile; rp.kchunks = p->kchunks; rp.cin_k = p->cin_k; rp.b_stages = p->b_stages;
+    rp.a_bytes = (uint32_t)(p->TBW * p->Hw * p->Wp) * 128u;
+    rp.b_bytes = (uint32_t)p->n_tile * 128u;
+    rp.tmem_cols = p->tmem_cols;
+    rp.bias = a.bias;
+    rp.res = static_cast<const __half*>(a.res);
+    rp.out = static_cast<__half*>(a.out);
+    rp.heatmap = a.heatmap; rp.xs = a.xs; rp.ys = a.ys; rp.coord_maps = a.coord_maps;
+    static bool attr_set = false;
+    if (!attr_set) {
+      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)(rp.win_per_img * ceil_div(a.B, p->TBW)), (unsigned)p->n_tiles);
+    conv_run_kernel<<<grid, kTcThreads, p->smem_bytes, st>>>(ma, p->map_b, rp);
+    EGN_LAUNCH_CHECK("conv_run_kernel");
+    return EGN_OK;
   }
   TcParams tp{};
   tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
