@@ -39,6 +39,12 @@ namespace egn {
 // ---------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EGN_TS(i) do { if (p.ts) p.ts[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = gtime(); } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -150,6 +156,149 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t swiz
 }
 
 // ---------------------------------------------------------------------------
+// shared epilogue: TMEM accumulator rows -> bias (+residual) (+ReLU) -> fp16 NHWC
+//
+// One thread owns one accumulator row (= one output pixel).  The residual operand is the only
+// dependent global read of the epilogue; with one 32-byte request per thread in flight it is pure
+// latency (~0.7 us per 16 channels).  Work is therefore cut into groups of 32 channels and the
+// residual of group g+1
+// is requested (8 independent 16-byte loads per thread, double buffered in registers) before group g is
+// converted and stored; the first group is requested before the
+// accumulator barrier is even waited on, so it overlaps the whole main loop.
+// ---------------------------------------------------------------------------
+struct EpiArgs {
+  const float* bias;
+  const __half* res;
+  __half* out;
+  float* heatmap;
+  const float* xs;
+  const float* ys;
+  int coord_maps, relu, Cout, Cout_p, OH, OW;
+  int dbg;
+  unsigned long long* ts;   // this CTA's stamp row or null
+};
+
+struct EpiRow {      // where this thread's accumulator row of M-tile t lands
+  bool valid;
+  int b, oh, ow;
+  size_t pix;
+};
+
+constexpr int kEpiGroup = 2;  // 16-column chunks per group
+
+__device__ __forceinline__ void epi_prefetch(const EpiArgs& e, const EpiRow& r, int n, int nch, uint4 (&buf)[2 * kEpiGroup]) {
+  if (!e.res || !r.valid || (e.dbg & 2)) return;
+  const uint4* rp = reinterpret_cast<const uint4*>(e.res + r.pix * e.Cout_p + n);
+#pragma unroll
+  for (int i = 0; i < 2 * kEpiGroup; ++i)
+    if (i < 2 * nch) buf[i] = __ldg(rp + i);
+}
+
+__device__ __forceinline__ void epi_process(const EpiArgs& e, const EpiRow& r, uint32_t taddr, int n, int nch,
+                                            const uint4 (&buf)[2 * kEpiGroup]) {
+  uint32_t v[kEpiGroup][16];
+#pragma unroll
+  for (int c = 0; c < kEpiGroup; ++c)
+    if (c < nch) tmem_ld16(taddr + 16u * c, v[c]);
+  tmem_ld_wait();
+  if (!r.valid) return;
+#pragma unroll
+  for (int c = 0; c < kEpiGroup; ++c) {
+    if (c >= nch) break;
+    const int nn = n + 16 * c;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bq = reinterpret_cast<const float4*>(e.bias + nn)[j];
+      f[4 * j + 0] = __uint_as_float(v[c][4 * j + 0]) + bq.x;
+      f[4 * j + 1] = __uint_as_float(v[c][4 * j + 1]) + bq.y;
+      f[4 * j + 2] = __uint_as_float(v[c][4 * j + 2]) + bq.z;
+      f[4 * j + 3] = __uint_as_float(v[c][4 * j + 3]) + bq.w;
+    }
+    if (e.res) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const __half2* r2 = reinterpret_cast<const __half2*>(&buf[2 * c + h]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 rf = __half22float2(r2[j]);
+          f[8 * h + 2 * j] += rf.x;
+          f[8 * h + 2 * j + 1] += rf.y;
+        }
+      }
+    }
+    if (e.relu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (e.heatmap) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (nn + j < e.Cout) e.heatmap[(((size_t)r.b * e.Cout + nn + j) * e.OH + r.oh) * e.OW + r.ow] = f[j];
+    }
+    if (e.coord_maps) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (nn + j == e.Cout) f[j] = e.xs[r.ow];
+        if (nn + j == e.Cout + 1) f[j] = e.ys[r.oh];
+      }
+    }
+    uint4 o[2];
+    __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    uint4* op = reinterpret_cast<uint4*>(e.out + r.pix * e.Cout_p + nn);
+    if (!(e.dbg & 1)) {
+      op[0] = o[0];
+      op[1] = o[1];
+    }
+  }
+}
+
+// Runs the grouped, double-buffered epilogue over T accumulator tiles of n_tile columns.
+// row_of(t) maps this thread's TMEM lane of tile t to its output pixel.  Group bookkeeping is
+// incremental (no integer division on the critical path).
+struct EpiCursor {
+  int t, gi;       // tile, group inside the tile
+  EpiRow row;
+};
+
+template <typename RowFn>
+__device__ __forceinline__ void epi_run(const EpiArgs& e, uint32_t tmem_lane_base, int T, int n_tile, int n0,
+                                        uint64_t* tmem_full_bar, RowFn row_of) {
+  const int nch_total = n_tile >> 4;
+  const int groups = (nch_total + kEpiGroup - 1) / kEpiGroup;
+  uint4 bufA[2 * kEpiGroup], bufB[2 * kEpiGroup];
+  auto advance = [&](EpiCursor& c) {          // next group; recompute the row only when the tile changes
+    if (++c.gi == groups) {
+      c.gi = 0;
+      ++c.t;
+      if (c.t < T) c.row = row_of(c.t);
+    }
+  };
+  auto nch_of = [&](const EpiCursor& c) { return min(kEpiGroup, nch_total - c.gi * kEpiGroup); };
+  auto n_of = [&](const EpiCursor& c) { return n0 + 16 * kEpiGroup * c.gi; };
+  auto ta_of = [&](const EpiCursor& c) { return tmem_lane_base + (uint32_t)(c.t * n_tile + 16 * kEpiGroup * c.gi); };
+  EpiCursor ca{0, 0, row_of(0)};
+  epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  if (e.ts && (threadIdx.x & 127) == 64) e.ts[4] = gtime();
+  while (ca.t < T) {
+    EpiCursor cb = ca;
+    advance(cb);
+    const bool has_b = cb.t < T;
+    if (has_b) epi_prefetch(e, cb.row, n_of(cb), nch_of(cb), bufB);
+    epi_process(e, ca.row, ta_of(ca), n_of(ca), nch_of(ca), bufA);
+    if (!has_b) break;
+    ca = cb;
+    advance(ca);
+    if (ca.t < T) epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
+    epi_process(e, cb.row, ta_of(cb), n_of(cb), nch_of(cb), bufB);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
 constexpr int kTcThreads = 192;
@@ -180,7 +329,7 @@ struct TcParams {
 };
 
 template <int SW>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -195,7 +344,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast through a shuffle so the compiler can prove the role branches warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // tile coordinates
   int tile = blockIdx.x;
@@ -220,55 +370,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  const int n_iters = p.taps * p.kchunks;
-
+  // warp-uniform role loops, instructions predicated to lane 0 (see conv_run_kernel)
+  const bool leader = lane == 0;
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
-        const int tap = it / p.kchunks, kcx = it - tap * p.kchunks;
-        const int r = tap / p.ksize, q = tap - r * p.ksize;
-        const int c0 = kcx * p.kc;
-        if (p.stride == 1) {
-          tma_load_4d(smem_a + (size_t)s * a_stage, &map_a, &full_bar[s], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
-        } else {
-          // input row = 2*(oh + dh) + hp, input col = 2*(ow + dw) + wp
-          const int er = r - p.pad, eq = q - p.pad;
-          const int hp = er & 1, dh = (er - hp) / 2;
-          const int wp = eq & 1, dw = (eq - wp) / 2;
-          tma_load_5d(smem_a + (size_t)s * a_stage, &map_a, &full_bar[s], wp * p.Cin_p + c0, ow0 + dw, hp, oh0 + dh,
-                      b0);
+    uint32_t stage = 0, phase = 0;
+    int kcoord = 0;                                  // tap * cin_k + chunk * kc, advanced incrementally
+    for (int r = 0; r < p.ksize; ++r) {
+      for (int q = 0; q < p.ksize; ++q) {
+        // stride 2: input row = 2*(oh + dh) + hp, input col = 2*(ow + dw) + wp
+        const int er = r - p.pad, eq = q - p.pad;
+        const int hp = er & 1, dh = (er - hp) / 2;
+        const int wp = eq & 1, dw = (eq - wp) / 2;
+        for (int kcx = 0; kcx < p.kchunks; ++kcx, kcoord += p.kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const int c0 = kcx * p.kc;
+          if (leader) {
+            mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+            if (p.stride == 1)
+              tma_load_4d(smem_a + stage * a_stage, &map_a, &full_bar[stage], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
+            else
+              tma_load_5d(smem_a + stage * a_stage, &map_a, &full_bar[stage], wp * p.Cin_p + c0, ow0 + dw, hp, oh0 + dh, b0);
+            tma_load_2d(smem_b + stage * b_stage, &map_b, &full_bar[stage], kcoord, n0);
+          }
+          if (++stage == (uint32_t)p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        tma_load_2d(smem_b + (size_t)s * b_stage, &map_b, &full_bar[s], tap * p.cin_k + c0, n0);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (size_t)s * a_stage), SW);
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)s * b_stage), SW);
+    // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = make_smem_desc(0, SW);
+    const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
+    const int n_iters = p.taps * p.kchunks;
+    uint32_t stage = 0, phase = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t adesc = desc_hi | (uint64_t)(((a_addr0 + stage * a_stage) & 0x3FFFFu) >> 4);
+      const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < SW / 32; ++k) {
           // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
           umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);  // frees this stage once the MMAs above have read it
+        umma_commit(&empty_bar[stage]);  // frees this stage once the MMAs above have read it
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      if (++stage == (uint32_t)p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
+    if (leader) umma_commit(tmem_full_bar);    // accumulator complete
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
@@ -276,66 +436,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tb = row / (p.TW * p.TH);
-    const int b = b0 + tb, oh = oh0 + th, ow = ow0 + tw;
-    const bool valid = row < p.TW * p.TH * p.TB && b < p.B && oh < p.OH && ow < p.OW;
-    const size_t pix = ((size_t)b * p.OH + oh) * p.OW + ow;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (valid) {
-        const int n = n0 + c0;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-          f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bq.x;
-          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bq.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bq.z;
-          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bq.w;
-        }
-        if (p.res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout_p + n);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 rq = __ldg(rp + h);
-            const __half2* r2 = reinterpret_cast<const __half2*>(&rq);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 rf = __half22float2(r2[j]);
-              f[8 * h + 2 * j] += rf.x;
-              f[8 * h + 2 * j + 1] += rf.y;
-            }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.heatmap) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < p.Cout) p.heatmap[(((size_t)b * p.Cout + n + j) * p.OH + oh) * p.OW + ow] = f[j];
-        }
-        if (p.coord_maps) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (n + j == p.Cout) f[j] = p.xs[ow];
-            if (n + j == p.Cout + 1) f[j] = p.ys[oh];
-          }
-        }
-        uint4 o[2];
-        __half2* o2 = reinterpret_cast<__half2*>(o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-        uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout_p + n);
-        op[0] = o[0];
-        op[1] = o[1];
-      }
-    }
+    EpiRow er;
+    er.b = b0 + tb;
+    er.oh = oh0 + th;
+    er.ow = ow0 + tw;
+    er.valid = row < p.TW * p.TH * p.TB && er.b < p.B && er.oh < p.OH && er.ow < p.OW;
+    er.pix = ((size_t)er.b * p.OH + er.oh) * p.OW + er.ow;
+    EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr};
+    epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
+            [&](int) { return er; });
   }
   tc_fence_before();
   __syncthreads();
@@ -382,9 +491,13 @@ struct RunParams {
   const float* xs;
   const float* ys;
   int coord_maps;
+  float inv_wp, inv_img;     // 1/Wp, 1/(Hw*Wp)
+  int img_rows;              // Hw * Wp
+  int dbg;   // tuning experiments (EGN_TC_DBG): 1 no stores, 2 no residual, 4 no MMA, 8 no A load, 16 no B loads
+  unsigned long long* ts;  // optional [grid][8] globaltimer stamps (EGN_TC_TS=1)
 };
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
 conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const RunParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -398,12 +511,16 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* b_empty = b_full + kMaxBStages;
   uint64_t* tmem_full_bar = b_empty + kMaxBStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 6);        // [n_tile], 16-byte aligned (offset 176)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) EGN_TS(0);
   const int win = blockIdx.x % p.win_per_img;
   const int bg = blockIdx.x / p.win_per_img;
   const int h0 = win * p.THW, b0 = bg * p.TBW;
   const int n0 = blockIdx.y * p.n_tile;
+  if (threadIdx.x >= 64)
+    for (int i = threadIdx.x - 64; i < p.n_tile; i += kTcThreads - 64) s_bias[i] = __ldg(p.bias + n0 + i);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
@@ -420,131 +537,116 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int n_iters = p.taps * p.kchunks;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (threadIdx.x == 0) EGN_TS(1);
+  const int ntap = p.halo ? 3 : 1;                 // taps per axis
+  const int last_ksteps = (p.Cin_p - (p.kchunks - 1) * 64 + 15) >> 4;   // K16 slices holding real channels
 
+  // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the barriers and
+  // compute identical addresses / descriptors, which therefore live in uniform registers); only the
+  // TMA / tcgen05 instructions themselves are predicated to lane 0.  Keeping the address math out of
+  // a divergent region matters: otherwise every UTCHMMA is wrapped in a waterfall loop.
+  const bool leader = lane == 0;
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int c = 0; c < p.kchunks; ++c) {
+    for (int c = 0; c < p.kchunks && !(p.dbg & 8); ++c) {
+      if (leader) {
         mbar_expect_tx(&a_full[c], p.a_bytes);
         tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, -p.halo, h0 - p.halo, b0);
       }
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % p.b_stages;
-        const uint32_t ph = (uint32_t)(it / p.b_stages) & 1u;
-        mbar_wait(&b_empty[s], ph ^ 1u);
-        mbar_expect_tx(&b_full[s], p.b_bytes);
-        const int tap = it / p.kchunks, c = it - tap * p.kchunks;
-        tma_load_2d(smem_b + (size_t)s * b_stage, &map_b, &b_full[s], tap * p.cin_k + c * 64, n0);
+    }
+    if (!(p.dbg & 16)) {
+      uint32_t stage = 0, phase = 0;
+      int kcoord = 0;                              // tap * cin_k + c * 64, advanced incrementally
+      for (int tap = 0; tap < p.taps; ++tap) {
+        for (int c = 0; c < p.kchunks; ++c, kcoord += 64) {
+          mbar_wait(&b_empty[stage], phase ^ 1u);
+          if (leader) {
+            mbar_expect_tx(&b_full[stage], p.b_bytes);
+            tma_load_2d(smem_b + stage * b_stage, &map_b, &b_full[stage], kcoord, n0);
+          }
+          if (++stage == (uint32_t)p.b_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % p.b_stages;
-        const uint32_t ph = (uint32_t)(it / p.b_stages) & 1u;
-        const int tap = it / p.kchunks, c = it - tap * p.kchunks;
-        if (tap == 0) mbar_wait(&a_full[c], 0);
-        mbar_wait(&b_full[s], ph);
-        tc_fence_after();
-        const int r = tap / 3, q = tap - 3 * r;                 // taps == 1 -> r = q = 0
-        const uint32_t row_shift = (uint32_t)(p.halo ? r * p.Wp + q : 0);
-        const uint32_t a_base = smem_u32(smem_a + (size_t)c * a_chunk) + row_shift * 128u;
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)s * b_stage), 128);
-        const int valid = p.Cin_p - c * 64;
-        const int ksteps = valid >= 64 ? 4 : (valid + 15) / 16;   // skip all-zero K slices of a partial chunk
-        for (int t = 0; t < p.T; ++t) {
-          const uint64_t adesc = make_smem_desc(a_base + (uint32_t)t * 128u * 128u, 128);
-          const uint32_t d = tmem_base + (uint32_t)(t * p.n_tile);
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = make_smem_desc(0, 128);          // everything but the start-address field
+    const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
+    uint32_t stage = 0, phase = 0, accumulate = 0;
+    bool first_tap = true;
+    for (int r = 0; r < ntap; ++r) {
+      for (int q = 0; q < ntap; ++q) {
+        const uint32_t shift = (uint32_t)(r * p.Wp + q) * 128u;   // row shift of this tap inside the window
+        for (int c = 0; c < p.kchunks; ++c) {
+          if (first_tap && !(p.dbg & 8)) {
+            mbar_wait(&a_full[c], 0);
+            if (c == 0 && leader) EGN_TS(2);
+          }
+          if (!(p.dbg & 16)) mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          const uint64_t ad0 = desc_hi | (uint64_t)(((a_addr0 + (uint32_t)c * a_chunk + shift) & 0x3FFFFu) >> 4);
+          const uint64_t bd0 = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
+          const int ksteps = (c == p.kchunks - 1) ? last_ksteps : 4;
+          if (!(p.dbg & 4)) {
+            uint64_t ad = ad0;
+            uint32_t d = tmem_base;
+            for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile) {
+              if (leader) {
+                umma_f16(d, ad, bd0, idesc, accumulate);
+                for (int k = 1; k < ksteps; ++k) umma_f16(d, ad + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, 1u);
+              }
+            }
+          }
+          accumulate = 1u;
+          if (leader) umma_commit(&b_empty[stage]);
+          if (++stage == (uint32_t)p.b_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(&b_empty[s]);
+        first_tap = false;
       }
+    }
+    if (leader) {
       umma_commit(tmem_full_bar);
+      EGN_TS(3);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int img_rows = p.Hw * p.Wp;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    for (int t = 0; t < p.T; ++t) {
-      const int m = t * 128 + row;
-      const int pos = m + p.lead;
-      const int bi = pos / img_rows;
-      const int rem = pos - bi * img_rows;
-      const int hp = rem / p.Wp, wp = rem - hp * p.Wp;
-      const int b = b0 + bi, oh = h0 + hp - p.halo, ow = wp - p.halo;
-      const bool valid = m < p.m_run && bi < p.TBW && hp >= p.halo && hp < p.Hw - p.halo && wp >= p.halo &&
-                         wp < p.Wp - p.halo && b < p.B && oh < p.H;
-      const size_t pix = ((size_t)b * p.H + oh) * p.W + ow;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.n_tile);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          const int n = n0 + c0;
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bq.x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bq.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bq.z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bq.w;
-          }
-          if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout_p + n);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 rq = __ldg(rp + h);
-              const __half2* r2 = reinterpret_cast<const __half2*>(&rq);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 rf = __half22float2(r2[j]);
-                f[8 * h + 2 * j] += rf.x;
-                f[8 * h + 2 * j + 1] += rf.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.heatmap) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n + j < p.Cout) p.heatmap[(((size_t)b * p.Cout + n + j) * p.H + oh) * p.W + ow] = f[j];
-          }
-          if (p.coord_maps) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (n + j == p.Cout) f[j] = p.xs[ow];
-              if (n + j == p.Cout + 1) f[j] = p.ys[oh];
-            }
-          }
-          uint4 o[2];
-          __half2* o2 = reinterpret_cast<__half2*>(o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout_p + n);
-          op[0] = o[0];
-          op[1] = o[1];
-        }
-      }
-    }
+    EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
+              p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr};
+    epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), p.T, p.n_tile, n0, tmem_full_bar, [&](int t) {
+      // run position -> window position -> (image, row, column); float reciprocals are exact here
+      // (positions < 2^16, margins >= 0.5 / pitch)
+      const int pos = t * 128 + row + p.lead;
+      const int bi = p.TBW == 1 ? 0 : (int)(((float)pos + 0.5f) * p.inv_img);
+      const int rem = pos - bi * p.img_rows;
+      const int hp = (int)(((float)rem + 0.5f) * p.inv_wp);
+      const int wp = rem - hp * p.Wp;
+      EpiRow rr;
+      rr.b = b0 + bi;
+      rr.oh = h0 + hp - p.halo;
+      rr.ow = wp - p.halo;
+      rr.valid = pos - p.lead < p.m_run && bi < p.TBW && hp >= p.halo && hp < p.Hw - p.halo && wp >= p.halo &&
+                 wp < p.Wp - p.halo && rr.b < p.B && rr.oh < p.H;
+      rr.pix = ((size_t)rr.b * p.H + rr.oh) * p.W + rr.ow;
+      return rr;
+    });
+    if ((threadIdx.x & 127) == 64) EGN_TS(5);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+    if (lane == 0) EGN_TS(6);
   }
 }
 
@@ -679,10 +781,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
           const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
           const size_t a_bytes = (size_t)p->kchunks * rows_alloc * 128;
           int bst = std::min(kMaxBStages, std::max(2, n_it));
-          size_t smem = 1024 + a_bytes + bst * b_stage_bytes + 256;
+          size_t smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
           while (smem > 200 * 1024 && bst > 2) {
             --bst;
-            smem = 1024 + a_bytes + bst * b_stage_bytes + 256;
+            smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
           }
           if (smem > 200 * 1024) continue;
           // cost model (nominal batch 64): CTAs per SM x (MMA rows + window load + fixed overhead);
@@ -836,6 +938,9 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.win_per_img = ceil_div(p->H, p->THW);
     rp.lead = p->halo * (p->Wp + 1);
     rp.m_run = p->TBW * p->Hw * p->Wp - 2 * rp.lead;
+    rp.img_rows = p->Hw * p->Wp;
+    rp.inv_wp = 1.0f / (float)p->Wp;
+    rp.inv_img = 1.0f / (float)rp.img_rows;
     rp.T = p->T; rp.rows_alloc = p->rows_alloc;
     rp.n_tile = p->n_tile; rp.kchunks = p->kchunks; rp.cin_k = p->cin_k; rp.b_stages = p->b_stages;
     rp.a_bytes = (uint32_t)(p->TBW * p->Hw * p->Wp) * 128u;
@@ -845,6 +950,14 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.res = static_cast<const __half*>(a.res);
     rp.out = static_cast<__half*>(a.out);
     rp.heatmap = a.heatmap; rp.xs = a.xs; rp.ys = a.ys; rp.coord_maps = a.coord_maps;
+    rp.dbg = getenv("EGN_TC_DBG") ? atoi(getenv("EGN_TC_DBG")) : 0;
+    rp.ts = nullptr;
+    static unsigned long long* d_ts = nullptr;
+    const size_t n_cta = (size_t)(ceil_div(p->H, p->THW) * ceil_div(a.B, p->TBW)) * p->n_tiles;
+    if (getenv("EGN_TC_TS")) {
+      if (!d_ts) cudaMalloc(&d_ts, 8192 * 8 * sizeof(unsigned long long));
+      if (n_cta <= 8192) rp.ts = d_ts;
+    }
     static bool attr_set = false;
     if (!attr_set) {
       EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
@@ -853,6 +966,21 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     dim3 grid((unsigned)(rp.win_per_img * ceil_div(a.B, p->TBW)), (unsigned)p->n_tiles);
     conv_run_kernel<<<grid, kTcThreads, p->smem_bytes, st>>>(ma, p->map_b, rp);
     EGN_LAUNCH_CHECK("conv_run_kernel");
+    if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> h(n_cta * 8);
+      cudaMemcpy(h.data(), d_ts, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull, t1 = 0;
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (size_t c = 0; c < n_cta; ++c) {
+        t0 = std::min(t0, h[c * 8]);
+        t1 = std::max(t1, h[c * 8 + 6]);
+        for (int i = 1; i < 7; ++i) acc[i] += (double)(h[c * 8 + i] - h[c * 8]);
+      }
+      fprintf(stderr, "[egn-ts] ctas=%zu span=%.2fus | avg since CTA start (us): init %.2f, A-ready %.2f, mma-issued %.2f, acc-ready %.2f, epi-done %.2f, dealloc %.2f\n",
+              n_cta, (t1 - t0) * 1e-3, acc[1] / n_cta * 1e-3, acc[2] / n_cta * 1e-3, acc[3] / n_cta * 1e-3, acc[4] / n_cta * 1e-3,
+              acc[5] / n_cta * 1e-3, acc[6] / n_cta * 1e-3);
+    }
     return EGN_OK;
   }
   TcParams tp{};

@@ -918,9 +918,10 @@ int64_t egn_hrnet_weight_bytes(const egn_hrnet* h) { return h ? h->weight_bytes 
 // ---------------------------------------------------------------------------
 // single fused conv layer (per-layer parity tests; synchronous convenience call)
 // ---------------------------------------------------------------------------
-extern "C" int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w_oihw_host,
-                                const float* bias_host, const void* res, void* out, int B, int H, int W,
-                                int Cin, int Cout, int ksize, int stride, int relu, void* stream) {
+static int conv2d_fused_impl(int impl, int dtype, const void* in, const float* w_oihw_host,
+                             const float* bias_host, const void* res, void* out, int B, int H, int W,
+                             int Cin, int Cout, int ksize, int stride, int relu, void* stream, int iters,
+                             float* avg_ms) {
   using namespace egn;
   EGN_REQUIRE(in && w_oihw_host && out, "egn_conv2d_fused: null pointer");
   EGN_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "egn_conv2d_fused: bad shape");
@@ -963,6 +964,20 @@ extern "C" int egn_conv2d_fused(int impl, int dtype, const void* in, const float
       TcConvPlan* plan = nullptr;
       rc = tc_conv_plan_create(a, wf.data(), &plan);
       if (!rc) rc = launch_conv_tc(plan, a, st);
+      if (!rc && iters > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && !rc; ++i) rc = launch_conv_tc(plan, a, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (avg_ms) *avg_ms = ms / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+      }
       if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
         set_error("egn_conv2d_fused(tc): %s", cudaGetErrorString(cudaGetLastError()));
         rc = EGN_ERR_CUDA;
@@ -977,6 +992,20 @@ extern "C" int egn_conv2d_fused(int impl, int dtype, const void* in, const float
     } else {
       cudaMemcpy(d_w, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice);
       rc = launch_conv_simt(dtype == 0 ? Dtype::F32 : Dtype::F16, a, d_w, st);
+      if (!rc && iters > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && !rc; ++i) rc = launch_conv_simt(dtype == 0 ? Dtype::F32 : Dtype::F16, a, d_w, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (avg_ms) *avg_ms = ms / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+      }
       if (!rc && cudaStreamSynchronize(st) != cudaSuccess) {
         set_error("egn_conv2d_fused(simt): %s", cudaGetErrorString(cudaGetLastError()));
         rc = EGN_ERR_CUDA;
@@ -986,4 +1015,21 @@ extern "C" int egn_conv2d_fused(int impl, int dtype, const void* in, const float
   }
   cudaFree(d_bias);
   return rc;
+}
+
+extern "C" int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w_oihw_host,
+                                const float* bias_host, const void* res, void* out, int B, int H, int W,
+                                int Cin, int Cout, int ksize, int stride, int relu, void* stream) {
+  return conv2d_fused_impl(impl, dtype, in, w_oihw_host, bias_host, res, out, B, H, W, Cin, Cout, ksize, stride,
+                           relu, stream, 0, nullptr);
+}
+
+extern "C" int egn_conv2d_bench(int impl, int dtype, const void* in, const float* w_oihw_host,
+                                const float* bias_host, const void* res, void* out, int B, int H, int W,
+                                int Cin, int Cout, int ksize, int stride, int relu, void* stream, int iters,
+                                float* avg_ms) {
+  using namespace egn;
+  EGN_REQUIRE(iters > 0 && avg_ms, "egn_conv2d_bench: iters must be positive");
+  return conv2d_fused_impl(impl, dtype, in, w_oihw_host, bias_host, res, out, B, H, W, Cin, Cout, ksize, stride,
+                           relu, stream, iters, avg_ms);
 }

@@ -141,6 +141,13 @@ EGN_API int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w
                      const float* bias_host, const void* res, void* out, int B, int H, int W,
                      int Cin, int Cout, int ksize, int stride, int relu, void* stream);
 
+/* Same layer launched `iters` times back to back (after one warm-up launch) with CUDA events around
+ * the loop; avg_ms receives the mean device time per launch.  Kernel-tuning utility. */
+EGN_API int egn_conv2d_bench(int impl, int dtype, const void* in, const float* w_oihw_host,
+                     const float* bias_host, const void* res, void* out, int B, int H, int W,
+                     int Cin, int Cout, int ksize, int stride, int relu, void* stream, int iters,
+                     float* avg_ms);
+
 /* Hardware probe (debug): one 128 x KC x KC UMMA whose A descriptor starts `row_off` rows into a
  * TMA-written swizzled tile; bo_mode selects the descriptor base-offset encoding under test.
  * a: device fp16 [256][KC], b: device fp16 [KC][KC], out: device fp32 [128][KC], KC = swizzle/2. */

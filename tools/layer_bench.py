@@ -1,0 +1,71 @@
+"""Time single fused conv layers (tcgen05 v1 per-tap / v2 window-run / CUDA-core) at a given batch.
+
+    python tools/layer_bench.py [--batch 64] [--iters 30]      (on the GPU box)
+"""
+import argparse, ctypes, json, os, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+SHAPES = [  # Cin, Cout, H, W, k, stride, residual
+    (48, 48, 64, 64, 3, 1, 1), (96, 96, 32, 32, 3, 1, 1), (192, 192, 16, 16, 3, 1, 1), (384, 384, 8, 8, 3, 1, 1),
+    (64, 64, 64, 64, 3, 1, 0), (256, 64, 64, 64, 1, 1, 0), (64, 256, 64, 64, 1, 1, 1), (64, 64, 128, 128, 3, 2, 0),
+    (96, 48, 32, 32, 1, 1, 0), (384, 48, 8, 8, 1, 1, 0), (48, 96, 64, 64, 3, 2, 0),
+]
+
+
+def run_child(args):
+    import torch
+    from egonet_b200 import _native as N
+    B = args.batch
+    out_rows = []
+    for (Cin, Cout, H, W, k, st, has_res) in SHAPES:
+        g = torch.Generator().manual_seed(1)
+        Cip, Cop = (Cin + 15) // 16 * 16, (Cout + 15) // 16 * 16
+        x = torch.randn((B, H, W, Cip), generator=g).to(torch.float16).cuda()
+        pad = 1 if k == 3 else 0
+        OH, OW = (H + 2 * pad - k) // st + 1, (W + 2 * pad - k) // st + 1
+        res = torch.randn((B, OH, OW, Cop), generator=g).to(torch.float16).cuda() if has_res else None
+        out = torch.empty((B, OH, OW, Cop), dtype=torch.float16, device='cuda')
+        w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5).contiguous()
+        ms = ctypes.c_float(0)
+        N.check(N.lib().egn_conv2d_bench(1, 1, N.ptr(x), N.ptr(w), None, N.ptr(res), N.ptr(out), B, H, W, Cin, Cout,
+                                         k, st, 1, None, args.iters, ctypes.byref(ms)))
+        flops = 2.0 * B * OH * OW * Cout * Cin * k * k
+        byts = 2.0 * (x.numel() + out.numel() + (res.numel() if has_res else 0)) + 2.0 * Cop * Cip * k * k
+        out_rows.append({'shape': '%dx%d s%d %d->%d @%dx%d%s' % (k, k, st, Cin, Cout, OH, OW, '+res' if has_res else ''),
+                         'us': round(ms.value * 1e3, 2), 'tflops': round(flops / ms.value / 1e9, 1),
+                         'gbs': round(byts / ms.value / 1e6, 1)})
+    print('RESULT ' + json.dumps(out_rows))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--iters', type=int, default=30)
+    ap.add_argument('--child', action='store_true')
+    args = ap.parse_args()
+    if args.child:
+        return run_child(args)
+    table = {}
+    for label, env in (('v2_run', {}), ('v1_tap', {'EGN_TC_V2': '0'})):
+        e = dict(os.environ, EGN_TC_VERBOSE='1', **env)
+        r = subprocess.run([sys.executable, __file__, '--child', '--batch', str(args.batch), '--iters', str(args.iters)],
+                           capture_output=True, text=True, env=e)
+        cfg = {}
+        for l in r.stderr.splitlines():
+            if l.startswith('[egn] conv '):
+                key = l[11:].split(':')[0]
+                cfg[key] = l.split(': ', 1)[1]
+        rows = [json.loads(l[7:]) for l in r.stdout.splitlines() if l.startswith('RESULT ')]
+        if not rows:
+            print(label, 'FAILED', r.stdout[-1500:], r.stderr[-3000:])
+            continue
+        for row in rows[0]:
+            table.setdefault(row['shape'], {})[label] = (row, cfg.get(row['shape'].replace('+res', ''), ''))
+    for shape, d in table.items():
+        print(shape)
+        for label, (row, c) in d.items():
+            print('   %-7s %8.2f us  %7.1f TFLOP/s  %7.1f GB/s   %s' % (label, row['us'], row['tflops'], row['gbs'], c))
+
+
+if __name__ == '__main__':
+    main()
