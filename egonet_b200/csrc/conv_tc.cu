@@ -76,6 +76,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -265,7 +268,7 @@ struct EpiCursor {
 
 template <typename RowFn>
 __device__ __forceinline__ void epi_run(const EpiArgs& e, uint32_t tmem_lane_base, int T, int n_tile, int n0,
-                                        uint64_t* tmem_full_bar, RowFn row_of) {
+                                        uint64_t* tmem_full_bar, RowFn row_of, uint32_t parity = 0) {
   const int nch_total = n_tile >> 4;
   const int groups = (nch_total + kEpiGroup - 1) / kEpiGroup;
   uint4 bufA[2 * kEpiGroup], bufB[2 * kEpiGroup];
@@ -281,7 +284,7 @@ __device__ __forceinline__ void epi_run(const EpiArgs& e, uint32_t tmem_lane_bas
   auto ta_of = [&](const EpiCursor& c) { return tmem_lane_base + (uint32_t)(c.t * n_tile + 16 * kEpiGroup * c.gi); };
   EpiCursor ca{0, 0, row_of(0)};
   epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
-  mbar_wait(tmem_full_bar, 0);
+  mbar_wait(tmem_full_bar, parity);
   tc_fence_after();
   if (e.ts && (threadIdx.x & 127) == 64) e.ts[4] = gtime();
   while (ca.t < T) {
@@ -651,6 +654,216 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
+// v3: persistent window-run kernel (one CTA per SM, 12 warps)
+//
+// Same operand addressing as v2, but the CTA stays resident and walks over windows
+// (w = blockIdx.x, += gridDim.x) with every phase of consecutive windows overlapped:
+//   warp 0      A producer: double-buffered input windows (a_full / a_empty)
+//   warp 1      MMA issuer: accumulates window j into TMEM set j&1 (acc_full / acc_empty)
+//   warp 2      B producer: the whole weight matrix once if it fits in smem (w_full), else a ring
+//   warps 4-7   epilogue group 0: drains TMEM set 0 (even windows)
+//   warps 8-11  epilogue group 1: drains TMEM set 1 (odd windows)
+// so while the tensor pipe works on window j, window j+1 is landing in the other smem slot and the
+// accumulators of window j-1 are being converted / stored by the other epilogue group.
+// ---------------------------------------------------------------------------
+constexpr int kPersistThreads = 384;
+
+struct PersistParams {
+  RunParams r;          // geometry / operands as in v2 (r.b_stages = ring depth when streaming)
+  int n_windows;        // win_per_img * ceil(B / TBW)
+  int b_resident;       // 1: all taps*kchunks weight tiles live in smem for the CTA's lifetime
+};
+
+__global__ void __launch_bounds__(kPersistThreads, 1)
+conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const PersistParams pp) {
+  const RunParams& p = pp.r;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_chunk = (uint32_t)p.rows_alloc * 128u;
+  const uint32_t a_slot = a_chunk * (uint32_t)p.kchunks;
+  const uint32_t b_stage = ((uint32_t)p.n_tile * 128u + 1023u) & ~1023u;
+  const int w_tiles = p.taps * p.kchunks;
+  const int b_slots = pp.b_resident ? w_tiles : p.b_stages;
+  uint8_t* smem_a = smem;                                   // 2 slots
+  uint8_t* smem_b = smem + 2 * (size_t)a_slot;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)b_slots * b_stage);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint64_t* b_full = w_full + 1;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // offset (9 + 12) * 8 + 8 = 176: 16-byte aligned
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.n_tile;
+  for (int i = threadIdx.x; i < p.n_tile; i += kPersistThreads) s_bias[i] = __ldg(p.bias + n0 + i);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < kMaxBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const bool leader = lane == 0;
+  const int ntap = p.halo ? 3 : 1;
+  const int last_ksteps = (p.Cin_p - (p.kchunks - 1) * 64 + 15) >> 4;
+  const int acc_cols = p.T * p.n_tile;                       // TMEM columns of one accumulator set
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    int j = 0;
+    for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+      const int slot = j & 1;
+      mbar_wait(&a_empty[slot], (uint32_t)((j >> 1) & 1) ^ 1u);
+      const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
+      if (leader) {
+        mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
+        for (int c = 0; c < p.kchunks; ++c)
+          tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
+                      win * p.THW - p.halo, bg * p.TBW);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer =====================
+    if (pp.b_resident) {
+      if (leader) {
+        mbar_expect_tx(w_full, p.b_bytes * (uint32_t)w_tiles);
+        int kcoord = 0;
+        for (int i = 0; i < w_tiles; ++i, kcoord += 64)
+          tma_load_2d(smem_b + (size_t)i * b_stage, &map_b, w_full, kcoord, n0);
+      }
+    } else {
+      uint32_t stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x) {
+        int kcoord = 0;
+        for (int i = 0; i < w_tiles; ++i, kcoord += 64) {
+          mbar_wait(&b_empty[stage], phase ^ 1u);
+          if (leader) {
+            mbar_expect_tx(&b_full[stage], p.b_bytes);
+            tma_load_2d(smem_b + stage * b_stage, &map_b, &b_full[stage], kcoord, n0);
+          }
+          if (++stage == (uint32_t)p.b_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = make_smem_desc(0, 128);
+    const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
+    if (pp.b_resident) mbar_wait(w_full, 0);
+    uint32_t stage = 0, phase = 0;
+    int j = 0;
+    for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+      const int slot = j & 1;
+      const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
+      mbar_wait(&a_full[slot], ph);                 // window landed
+      tc_fence_after();
+      uint32_t accumulate = 0;
+      int tile = 0;
+      for (int r = 0; r < ntap; ++r) {
+        for (int q = 0; q < ntap; ++q) {
+          const uint32_t shift = (uint32_t)(r * p.Wp + q) * 128u;
+          for (int c = 0; c < p.kchunks; ++c, ++tile) {
+            uint32_t b_addr;
+            if (pp.b_resident) {
+              b_addr = b_addr0 + (uint32_t)tile * b_stage;
+            } else {
+              mbar_wait(&b_full[stage], phase);
+              tc_fence_after();
+              b_addr = b_addr0 + stage * b_stage;
+            }
+            const uint64_t ad0 =
+                desc_hi | (uint64_t)(((a_addr0 + (uint32_t)slot * a_slot + (uint32_t)c * a_chunk + shift) & 0x3FFFFu) >> 4);
+            const uint64_t bd0 = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+            const int ksteps = (c == p.kchunks - 1) ? last_ksteps : 4;
+            uint64_t ad = ad0;
+            uint32_t d = tmem_base + (uint32_t)(slot * acc_cols);
+            for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile) {
+              if (leader) {
+                umma_f16(d, ad, bd0, idesc, accumulate);
+                for (int k = 1; k < ksteps; ++k) umma_f16(d, ad + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, 1u);
+              }
+            }
+            accumulate = 1u;
+            if (!pp.b_resident) {
+              if (leader) umma_commit(&b_empty[stage]);
+              if (++stage == (uint32_t)p.b_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(&a_empty[slot]);      // window slot may be refilled
+        umma_commit(&acc_full[slot]);     // accumulators complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue groups =====================
+    const int grp = (warp - 4) >> 2;                  // 0: even windows, 1: odd windows
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
+              nullptr};
+    int j = 0;
+    for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+      if ((j & 1) != grp) continue;
+      const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
+      const int h0 = win * p.THW, b0 = bg * p.TBW;
+      epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * acc_cols), p.T, p.n_tile, n0,
+              &acc_full[grp], [&](int t) {
+        const int pos = t * 128 + row + p.lead;
+        const int bi = p.TBW == 1 ? 0 : (int)(((float)pos + 0.5f) * p.inv_img);
+        const int rem = pos - bi * p.img_rows;
+        const int hp = (int)(((float)rem + 0.5f) * p.inv_wp);
+        const int wp = rem - hp * p.Wp;
+        EpiRow rr;
+        rr.b = b0 + bi;
+        rr.oh = h0 + hp - p.halo;
+        rr.ow = wp - p.halo;
+        rr.valid = pos - p.lead < p.m_run && bi < p.TBW && hp >= p.halo && hp < p.Hw - p.halo && wp >= p.halo &&
+                   wp < p.Wp - p.halo && rr.b < p.B && rr.oh < p.H;
+        rr.pix = ((size_t)rr.b * p.H + rr.oh) * p.W + rr.ow;
+        return rr;
+      }, ph);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[grp]);       // 128 arrivals release the accumulator set to the MMA warp
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side: tensor maps + plan
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -680,6 +893,8 @@ struct TcConvPlan {
   size_t smem_bytes;
   // v2 (window run) configuration; use_run == false -> v1 per-tap kernel
   bool use_run = false;
+  bool use_persist = false;   // v3: persistent one-CTA-per-SM variant of the window-run kernel
+  int b_resident = 0;
   int halo = 0, Wp = 0, Hw = 0, THW = 0, TBW = 1, T = 1, rows_alloc = 0, b_stages = 2;
   float run_eff = 0.f;
   __half* d_w = nullptr;      // [Cout_p][taps*Cin_p]
@@ -821,6 +1036,75 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
     }
   }
+  // ---- v3 persistent configuration: double-buffered windows + accumulators, weights resident if they fit ----
+  {
+    const char* env = getenv("EGN_TC_V3");
+    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks &&
+                       (a.ksize == 1 ? a.W >= 32 : a.W >= 24);
+    if (allow) {
+      const int halo = a.ksize == 3 ? 1 : 0;
+      const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
+      const size_t b_stage_bytes = ((size_t)p->n_tile * 128 + 1023) & ~(size_t)1023;
+      const int w_tiles = a.ksize * a.ksize * p->kchunks;
+      const size_t smem_cap = 225 * 1024;
+      double best = 1e30;
+      const int Tmax = std::min(8, 256 / p->n_tile);
+      for (int T = 1; T <= Tmax; ++T) {
+        for (int multi = 0; multi < 2; ++multi) {
+          int THW, TBW;
+          if (!multi) {
+            THW = std::min(a.H, (128 * T + 2 * halo) / Wp);
+            TBW = 1;
+            if (THW < 1) continue;
+          } else {
+            THW = a.H;
+            TBW = (128 * T + 2 * lead) / ((a.H + 2 * halo) * Wp);
+            if (TBW < 2) continue;
+            TBW = std::min(TBW, 64);
+          }
+          const int Hw = THW + 2 * halo;
+          if (Wp > 256 || Hw > 256) continue;
+          const int rows_win = TBW * Hw * Wp;
+          if (rows_win - 2 * lead > 128 * T) continue;
+          const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
+          const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
+          int resident = 1, bst = 0;
+          size_t smem = 1024 + a_bytes + (size_t)w_tiles * b_stage_bytes + 1536;
+          if (smem > smem_cap) {
+            resident = 0;
+            bst = std::min(kMaxBStages, w_tiles);
+            smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+            while (smem > smem_cap && bst > 2) {
+              --bst;
+              smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+            }
+            if (smem > smem_cap) continue;
+          }
+          const int windows = multi ? 1 : ceil_div(a.H, THW);
+          const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
+                                   : (double)a.H * a.W / ((double)windows * T * 128);
+          const int n_win = windows * ceil_div(64, TBW);
+          // rounds of the persistent loop x per-window time (MMA rows + fixed cost; streamed weights cost extra)
+          const double est = ceil_div(n_win * p->n_tiles, 148) * (T * (resident ? 1.0 : 1.4) + 0.35);
+          if (est < best) {
+            best = est;
+            p->use_persist = true;
+            p->b_resident = resident;
+            p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
+            p->rows_alloc = rows_alloc; p->b_stages = resident ? 0 : bst; p->run_eff = (float)eff;
+            p->smem_bytes = smem;
+            p->tmem_cols = pow2_cols(2 * T * p->n_tile);
+          }
+        }
+      }
+      if (p->use_persist && p->run_eff < 0.6f) p->use_persist = false;
+      if (p->use_persist) p->use_run = false;
+      if (getenv("EGN_TC_VERBOSE") && p->use_persist)
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB resident=%d bst=%d tmem=%u\n",
+                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->T, p->THW, p->TBW, p->run_eff,
+                p->smem_bytes / 1024, p->b_resident, p->b_stages, p->tmem_cols);
+    }
+  }
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
   const int taps = a.ksize * a.ksize;
   const int cin_k = p->kchunks * p->kc;
@@ -866,7 +1150,7 @@ static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   EncodeTiledFn enc = get_encode_fn();
   const cuuint64_t C = p->Cin_p, W = p->W, H = p->H;
   CUresult r;
-  if (p->use_run) {
+  if (p->use_run || p->use_persist) {
     const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
     const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
     const cuuint32_t box[4] = {64, (cuuint32_t)p->Wp, (cuuint32_t)p->Hw, (cuuint32_t)p->TBW};
@@ -929,6 +1213,47 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       it = p->a_maps.emplace(key, m).first;
     }
     ma = it->second;
+  }
+  if (p->use_persist) {
+    PersistParams pp{};
+    RunParams& rp = pp.r;
+    rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->Cin_p;
+    rp.taps = p->ksize * p->ksize; rp.relu = a.relu;
+    rp.halo = p->halo; rp.Wp = p->Wp; rp.Hw = p->Hw; rp.THW = p->THW; rp.TBW = p->TBW;
+    rp.win_per_img = ceil_div(p->H, p->THW);
+    rp.lead = p->halo * (p->Wp + 1);
+    rp.m_run = p->TBW * p->Hw * p->Wp - 2 * rp.lead;
+    rp.img_rows = p->Hw * p->Wp;
+    rp.inv_wp = 1.0f / (float)p->Wp;
+    rp.inv_img = 1.0f / (float)rp.img_rows;
+    rp.T = p->T; rp.rows_alloc = p->rows_alloc;
+    rp.n_tile = p->n_tile; rp.kchunks = p->kchunks; rp.cin_k = p->cin_k; rp.b_stages = p->b_stages;
+    rp.a_bytes = (uint32_t)(p->TBW * p->Hw * p->Wp) * 128u;
+    rp.b_bytes = (uint32_t)p->n_tile * 128u;
+    rp.tmem_cols = p->tmem_cols;
+    rp.bias = a.bias;
+    rp.res = static_cast<const __half*>(a.res);
+    rp.out = static_cast<__half*>(a.out);
+    rp.heatmap = a.heatmap; rp.xs = a.xs; rp.ys = a.ys; rp.coord_maps = a.coord_maps;
+    rp.dbg = getenv("EGN_TC_DBG") ? atoi(getenv("EGN_TC_DBG")) : 0;
+    rp.ts = nullptr;
+    pp.n_windows = rp.win_per_img * ceil_div(a.B, p->TBW);
+    pp.b_resident = p->b_resident;
+    static bool attr_set = false;
+    if (!attr_set) {
+      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
+    conv_persist_kernel<<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, pp);
+    EGN_LAUNCH_CHECK("conv_persist_kernel");
+    return EGN_OK;
   }
   if (p->use_run) {
     RunParams rp{};
