@@ -48,6 +48,21 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One lane of a converged warp.  The compiler recognises elect.sync and emits the guarded
+// UTCHMMA / UTMALDG directly; predicating on (lane == 0) instead makes it wrap every such
+// instruction in an ELECT + BRA.U.ANY waterfall loop (~10 dependent uniform-datapath instructions,
+// ~150 cycles per MMA on the single issuing warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -376,7 +391,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // warp-uniform role loops, instructions predicated to lane 0 (see conv_run_kernel)
-  const bool leader = lane == 0;
   if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
@@ -390,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kcx = 0; kcx < p.kchunks; ++kcx, kcoord += p.kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const int c0 = kcx * p.kc;
-          if (leader) {
+          if (elect_one()) {
             mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
             if (p.stride == 1)
               tma_load_4d(smem_a + stage * a_stage, &map_a, &full_bar[stage], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
@@ -418,7 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint64_t adesc = desc_hi | (uint64_t)(((a_addr0 + stage * a_stage) & 0x3FFFFu) >> 4);
       const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
-      if (leader) {
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < SW / 32; ++k) {
           // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
@@ -431,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         phase ^= 1u;
       }
     }
-    if (leader) umma_commit(tmem_full_bar);    // accumulator complete
+    if (elect_one()) umma_commit(tmem_full_bar);    // accumulator complete
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
@@ -549,11 +563,10 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   // compute identical addresses / descriptors, which therefore live in uniform registers); only the
   // TMA / tcgen05 instructions themselves are predicated to lane 0.  Keeping the address math out of
   // a divergent region matters: otherwise every UTCHMMA is wrapped in a waterfall loop.
-  const bool leader = lane == 0;
   if (warp == 0) {
     // ===================== TMA producer =====================
     for (int c = 0; c < p.kchunks && !(p.dbg & 8); ++c) {
-      if (leader) {
+      if (elect_one()) {
         mbar_expect_tx(&a_full[c], p.a_bytes);
         tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, -p.halo, h0 - p.halo, b0);
       }
@@ -564,7 +577,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int tap = 0; tap < p.taps; ++tap) {
         for (int c = 0; c < p.kchunks; ++c, kcoord += 64) {
           mbar_wait(&b_empty[stage], phase ^ 1u);
-          if (leader) {
+          if (elect_one()) {
             mbar_expect_tx(&b_full[stage], p.b_bytes);
             tma_load_2d(smem_b + stage * b_stage, &map_b, &b_full[stage], kcoord, n0);
           }
@@ -588,7 +601,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int c = 0; c < p.kchunks; ++c) {
           if (first_tap && !(p.dbg & 8)) {
             mbar_wait(&a_full[c], 0);
-            if (c == 0 && leader) EGN_TS(2);
+            if (c == 0 && lane == 0) EGN_TS(2);
           }
           if (!(p.dbg & 16)) mbar_wait(&b_full[stage], phase);
           tc_fence_after();
@@ -599,14 +612,14 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             uint64_t ad = ad0;
             uint32_t d = tmem_base;
             for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile) {
-              if (leader) {
+              if (elect_one()) {
                 umma_f16(d, ad, bd0, idesc, accumulate);
                 for (int k = 1; k < ksteps; ++k) umma_f16(d, ad + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, 1u);
               }
             }
           }
           accumulate = 1u;
-          if (leader) umma_commit(&b_empty[stage]);
+          if (elect_one()) umma_commit(&b_empty[stage]);
           if (++stage == (uint32_t)p.b_stages) {
             stage = 0;
             phase ^= 1u;
@@ -615,7 +628,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         first_tap = false;
       }
     }
-    if (leader) {
+    if (elect_one()) {
       umma_commit(tmem_full_bar);
       EGN_TS(3);
     }
@@ -721,7 +734,6 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const bool leader = lane == 0;
   const int ntap = p.halo ? 3 : 1;
   const int last_ksteps = (p.Cin_p - (p.kchunks - 1) * 64 + 15) >> 4;
   const int acc_cols = p.T * p.n_tile;                       // TMEM columns of one accumulator set
@@ -733,7 +745,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int slot = j & 1;
       mbar_wait(&a_empty[slot], (uint32_t)((j >> 1) & 1) ^ 1u);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
-      if (leader) {
+      if (elect_one()) {
         mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
         for (int c = 0; c < p.kchunks; ++c)
           tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
@@ -743,7 +755,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 2) {
     // ===================== B producer =====================
     if (pp.b_resident) {
-      if (leader) {
+      if (elect_one()) {
         mbar_expect_tx(w_full, p.b_bytes * (uint32_t)w_tiles);
         int kcoord = 0;
         for (int i = 0; i < w_tiles; ++i, kcoord += 64)
@@ -755,7 +767,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         int kcoord = 0;
         for (int i = 0; i < w_tiles; ++i, kcoord += 64) {
           mbar_wait(&b_empty[stage], phase ^ 1u);
-          if (leader) {
+          if (elect_one()) {
             mbar_expect_tx(&b_full[stage], p.b_bytes);
             tma_load_2d(smem_b + stage * b_stage, &map_b, &b_full[stage], kcoord, n0);
           }
@@ -777,9 +789,12 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
       const int slot = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
       mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
+      if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 1] = gtime();
       mbar_wait(&a_full[slot], ph);                 // window landed
       tc_fence_after();
+      if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
       uint32_t accumulate = 0;
       int tile = 0;
       for (int r = 0; r < ntap; ++r) {
@@ -801,14 +816,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint64_t ad = ad0;
             uint32_t d = tmem_base + (uint32_t)(slot * acc_cols);
             for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile) {
-              if (leader) {
+              if (elect_one()) {
                 umma_f16(d, ad, bd0, idesc, accumulate);
                 for (int k = 1; k < ksteps; ++k) umma_f16(d, ad + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, 1u);
               }
             }
             accumulate = 1u;
             if (!pp.b_resident) {
-              if (leader) umma_commit(&b_empty[stage]);
+              if (elect_one()) umma_commit(&b_empty[stage]);
               if (++stage == (uint32_t)p.b_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -817,9 +832,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       }
-      if (leader) {
+      if (elect_one()) {
         umma_commit(&a_empty[slot]);      // window slot may be refilled
         umma_commit(&acc_full[slot]);     // accumulators complete
+        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 3] = gtime();
       }
     }
   } else if (warp >= 4) {
@@ -835,6 +851,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
       const int h0 = win * p.THW, b0 = bg * p.TBW;
+      e.ts = (p.ts && j < 8) ? p.ts + ((size_t)blockIdx.x * 8 + j) * 8 : nullptr;
       epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * acc_cols), p.T, p.n_tile, n0,
               &acc_full[grp], [&](int t) {
         const int pos = t * 128 + row + p.lead;
@@ -851,6 +868,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         rr.pix = ((size_t)rr.b * p.H + rr.oh) * p.W + rr.ow;
         return rr;
       }, ph);
+      if (e.ts && (threadIdx.x & 127) == 64) e.ts[5] = gtime();
       tc_fence_before();
       mbar_arrive(&acc_empty[grp]);       // 128 arrivals release the accumulator set to the MMA warp
     }
@@ -1237,6 +1255,12 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.heatmap = a.heatmap; rp.xs = a.xs; rp.ys = a.ys; rp.coord_maps = a.coord_maps;
     rp.dbg = getenv("EGN_TC_DBG") ? atoi(getenv("EGN_TC_DBG")) : 0;
     rp.ts = nullptr;
+    static unsigned long long* d_ts3 = nullptr;
+    if (getenv("EGN_TC_TS")) {
+      if (!d_ts3) cudaMalloc(&d_ts3, 256 * 64 * sizeof(unsigned long long));
+      cudaMemsetAsync(d_ts3, 0, 256 * 64 * sizeof(unsigned long long), st);
+      rp.ts = d_ts3;
+    }
     pp.n_windows = rp.win_per_img * ceil_div(a.B, p->TBW);
     pp.b_resident = p->b_resident;
     static bool attr_set = false;
@@ -1253,6 +1277,21 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
     conv_persist_kernel<<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, pp);
     EGN_LAUNCH_CHECK("conv_persist_kernel");
+    if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> h(256 * 64);
+      cudaMemcpy(h.data(), d_ts3, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      // CTA 0 and CTA 77, first windows: times relative to the CTA's first stamp
+      for (int cta : {0, 77}) {
+        const unsigned long long t0 = h[(size_t)cta * 64];
+        for (int j = 0; j < 6; ++j) {
+          const unsigned long long* q = &h[((size_t)cta * 8 + j) * 8];
+          if (!q[0]) continue;
+          fprintf(stderr, "[egn-ts3] cta %d win %d: mma-loop-top %.2f acc-empty-ok %.2f a-full-ok %.2f mma-issued %.2f | epi acc-full-ok %.2f epi-done %.2f (us)\n",
+                  cta, j, (q[0] - t0) * 1e-3, (q[1] - t0) * 1e-3, (q[2] - t0) * 1e-3, (q[3] - t0) * 1e-3, (q[4] - t0) * 1e-3, (q[5] - t0) * 1e-3);
+        }
+      }
+    }
     return EGN_OK;
   }
   if (p->use_run) {
