@@ -608,14 +608,12 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint64_t ad0 = desc_hi | (uint64_t)(((a_addr0 + (uint32_t)c * a_chunk + shift) & 0x3FFFFu) >> 4);
           const uint64_t bd0 = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
           const int ksteps = (c == p.kchunks - 1) ? last_ksteps : 4;
-          if (!(p.dbg & 4)) {
-            uint64_t ad = ad0;
-            uint32_t d = tmem_base;
-            for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile) {
-              if (elect_one()) {
-                umma_f16(d, ad, bd0, idesc, accumulate);
-                for (int k = 1; k < ksteps; ++k) umma_f16(d, ad + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, 1u);
-              }
+          if (!(p.dbg & 4) && elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              uint64_t ad = ad0 + (uint64_t)(2 * k);
+              uint32_t d = tmem_base;
+              for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile)
+                umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)(k > 0));
             }
           }
           accumulate = 1u;
@@ -813,12 +811,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 desc_hi | (uint64_t)(((a_addr0 + (uint32_t)slot * a_slot + (uint32_t)c * a_chunk + shift) & 0x3FFFFu) >> 4);
             const uint64_t bd0 = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
             const int ksteps = (c == p.kchunks - 1) ? last_ksteps : 4;
-            uint64_t ad = ad0;
-            uint32_t d = tmem_base + (uint32_t)(slot * acc_cols);
-            for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile) {
-              if (elect_one()) {
-                umma_f16(d, ad, bd0, idesc, accumulate);
-                for (int k = 1; k < ksteps; ++k) umma_f16(d, ad + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, 1u);
+            // K16 slice outer, M tile inner: consecutive MMAs hit different accumulators, so the
+            // accumulate dependency of one tile never stalls the next instruction
+            if (elect_one()) {
+              for (int k = 0; k < ksteps; ++k) {
+                uint64_t ad = ad0 + (uint64_t)(2 * k);
+                uint32_t d = tmem_base + (uint32_t)(slot * acc_cols);
+                for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile)
+                  umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)(k > 0));
               }
             }
             accumulate = 1u;
@@ -1492,4 +1492,77 @@ extern "C" int egn_debug_umma_probe(int swizzle_bytes, int row_off, int bo_mode,
   }
   set_error("egn_debug_umma_probe: swizzle must be 32, 64 or 128");
   return EGN_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------------------
+// Hardware probe: issue rate of tcgen05.mma (M=128, K=16, kind::f16, SS) as a function of N and of the
+// number of accumulators rotated over.  Operands are whatever is in shared memory (zeros).
+// ---------------------------------------------------------------------------
+namespace egn {
+__global__ void __launch_bounds__(128)
+umma_rate_kernel(int n, int nacc, int iters, int a_rows_shift, long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                 // 1024 rows x 128 B
+  uint8_t* sb = smem + 1024 * 128;    // 256 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 256 * 128);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < (1024 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
+  if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = make_smem_desc(0, 128);
+    const uint64_t ad0 = desc_hi | (uint64_t)(((smem_u32(sa) + (uint32_t)a_rows_shift * 128u) & 0x3FFFFu) >> 4);
+    const uint64_t bd0 = desc_hi | (uint64_t)((smem_u32(sb) & 0x3FFFFu) >> 4);
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        for (int k = 0; k < 4; ++k) {
+          uint64_t ad = ad0 + (uint64_t)(2 * k);
+          uint32_t d = tmem;
+          for (int t = 0; t < nacc; ++t, ad += 1024, d += (uint32_t)n) umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, 1u);
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 32) out_cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace egn
+
+extern "C" int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift, int ctas, double* cycles_per_mma) {
+  using namespace egn;
+  EGN_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512 && iters > 0 && ctas >= 1 && ctas <= 1024,
+              "egn_debug_umma_rate: bad arguments");
+  if (int rc = require_device()) return rc;
+  long long* d = nullptr;
+  EGN_CUDA_CHECK(cudaMalloc(&d, ctas * sizeof(long long)));
+  const size_t smem = 1024 + (1024 + 256) * 128 + 64;
+  EGN_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_kernel<<<ctas, 128, smem>>>(n, nacc, iters, a_rows_shift, d);
+  EGN_LAUNCH_CHECK("umma_rate_kernel");
+  EGN_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<long long> h(ctas);
+  cudaMemcpy(h.data(), d, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  double acc = 0;
+  for (long long v : h) acc += (double)v;
+  *cycles_per_mma = acc / ctas / ((double)iters * 4 * nacc);
+  return EGN_OK;
 }

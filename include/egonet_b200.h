@@ -148,6 +148,10 @@ EGN_API int egn_conv2d_bench(int impl, int dtype, const void* in, const float* w
                      int Cin, int Cout, int ksize, int stride, int relu, void* stream, int iters,
                      float* avg_ms);
 
+/* Hardware probe (debug): SM cycles per tcgen05.mma (M=128, K=16, f16, operands in smem) when `ctas`
+ * CTAs each issue iters*4*nacc MMAs of width n, rotating over nacc accumulators. */
+EGN_API int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift, int ctas, double* cycles_per_mma);
+
 /* Hardware probe (debug): one 128 x KC x KC UMMA whose A descriptor starts `row_off` rows into a
  * TMA-written swizzled tile; bo_mode selects the descriptor base-offset encoding under test.
  * a: device fp16 [256][KC], b: device fp16 [KC][KC], out: device fp32 [128][KC], KC = swizzle/2. */

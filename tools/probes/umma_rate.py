@@ -1,0 +1,16 @@
+"""SM cycles per tcgen05.mma (M=128,K=16,f16,SS) vs N / accumulator rotation / CTA count / A row shift."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from egonet_b200 import _native as N
+torch.zeros(1).cuda()
+L = N.lib()
+def rate(n, nacc, shift=0, ctas=1):
+    v = ctypes.c_double(0)
+    N.check(L.egn_debug_umma_rate(n, nacc, 200, shift, ctas, ctypes.byref(v)))
+    return v.value
+print('N   nacc=1   nacc=2  nacc=max  (1 CTA)   | 148 CTAs nacc=max | shift=67 rows')
+for n in (16, 32, 48, 64, 96, 128, 192, 256):
+    m = max(1, min(8, 512 // n))
+    print('%3d  %7.1f  %7.1f  %7.1f (x%d)      |  %7.1f          |  %7.1f' % (
+        n, rate(n, 1), rate(n, min(2, m)), rate(n, m), m, rate(n, m, 0, 148), rate(n, m, 67)))
