@@ -24,6 +24,14 @@ template <> struct Elem<float> {
   static __device__ __forceinline__ void store4(float* p, const float v[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  static __device__ __forceinline__ void load8(const float* p, float v[8]) {
+    load4(p, v);
+    load4(p + 4, v + 4);
+  }
+  static __device__ __forceinline__ void store8(float* p, const float v[8]) {
+    store4(p, v);
+    store4(p + 4, v + 4);
+  }
   static __device__ __forceinline__ float to_f(float v) { return v; }
   static __device__ __forceinline__ float from_f(float v) { return v; }
 };
@@ -41,6 +49,23 @@ template <> struct Elem<__half> {
     q.x = *reinterpret_cast<const uint32_t*>(&a);
     q.y = *reinterpret_cast<const uint32_t*>(&b);
     *reinterpret_cast<uint2*>(p) = q;
+  }
+  static __device__ __forceinline__ void load8(const __half* p, float v[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store8(__half* p, const float v[8]) {
+    uint4 q;
+    __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
   }
   static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
   static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
@@ -249,45 +274,48 @@ int launch_stem(Dtype dt, const StemArgs& a, cudaStream_t st) {
 // fuse: out = relu(sum_j up(term_j)), 4 channels per thread
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void fuse_kernel(FuseArgs p) {
-  const int cq = p.Cp / 4;
+__global__ void __launch_bounds__(256) fuse_kernel(FuseArgs p) {
+  // 8 channels (16 bytes of fp16) per thread; all terms' loads are issued before the sum so that
+  // several independent requests per thread are in flight
+  const int cq = p.Cp / 8;
   const int64_t total = (int64_t)p.B * p.H * p.W * cq;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % cq) * 4;
+    const int c = (int)(e % cq) * 8;
     int64_t pix = e / cq;
     const int w = (int)(pix % p.W);
     pix /= p.W;
     const int h = (int)(pix % p.H);
     const int b = (int)(pix / p.H);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float v[4][8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (j >= p.nterms) break;
-      const int sh = p.shift[j];
-      const int Hs = p.H >> sh, Ws = p.W >> sh;
-      const T* src = static_cast<const T*>(p.term[j]) +
-                     (((int64_t)b * Hs + (h >> sh)) * Ws + (w >> sh)) * p.Cp + c;
-      float v[4];
-      Elem<T>::load4(src, v);
-      if (j == 0) {
+      if (j < p.nterms) {
+        const int sh = p.shift[j];
+        const int Hs = p.H >> sh, Ws = p.W >> sh;
+        Elem<T>::load8(static_cast<const T*>(p.term[j]) + (((int64_t)b * Hs + (h >> sh)) * Ws + (w >> sh)) * p.Cp + c, v[j]);
+      }
+    }
+    float acc[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = v[q];
-      } else {
+    for (int q = 0; q < 8; ++q) acc[q] = v[0][q];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] += v[q];
+    for (int j = 1; j < 4; ++j) {
+      if (j < p.nterms) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += v[j][q];
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = fmaxf(acc[q], 0.f);
-    Elem<T>::store4(static_cast<T*>(p.out) + (((int64_t)b * p.H + h) * p.W + w) * p.Cp + c, acc);
+    for (int q = 0; q < 8; ++q) acc[q] = fmaxf(acc[q], 0.f);
+    Elem<T>::store8(static_cast<T*>(p.out) + (((int64_t)b * p.H + h) * p.W + w) * p.Cp + c, acc);
   }
 }
 
 int launch_fuse(Dtype dt, const FuseArgs& a, cudaStream_t st) {
-  const int64_t total = (int64_t)a.B * a.H * a.W * (a.Cp / 4);
+  const int64_t total = (int64_t)a.B * a.H * a.W * (a.Cp / 8);
   const int threads = 256;
-  const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 16);
+  const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 8);
   if (dt == Dtype::F32)
     fuse_kernel<float><<<blocks, threads, 0, st>>>(a);
   else

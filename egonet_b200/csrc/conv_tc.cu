@@ -1054,7 +1054,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
     }
   }
-  // ---- v3 persistent configuration: double-buffered windows + accumulators, weights resident if they fit ----
+  // ---- v3 persistent configuration: double-buffered windows + accumulators, weights RESIDENT in smem ----
+  // If the whole [Cout][taps*Cin] matrix does not fit next to two window slots, the output channels are
+  // split over blockIdx.y (each half keeps its own half of the weights resident; the window is loaded by
+  // both).  Streaming the weights per window instead costs more L2->SM bandwidth than it saves.
   {
     const char* env = getenv("EGN_TC_V3");
     const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks &&
@@ -1062,65 +1065,70 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
     if (allow) {
       const int halo = a.ksize == 3 ? 1 : 0;
       const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
-      const size_t b_stage_bytes = ((size_t)p->n_tile * 128 + 1023) & ~(size_t)1023;
       const int w_tiles = a.ksize * a.ksize * p->kchunks;
       const size_t smem_cap = 225 * 1024;
       double best = 1e30;
-      const int Tmax = std::min(8, 256 / p->n_tile);
-      for (int T = 1; T <= Tmax; ++T) {
-        for (int multi = 0; multi < 2; ++multi) {
-          int THW, TBW;
-          if (!multi) {
-            THW = std::min(a.H, (128 * T + 2 * halo) / Wp);
-            TBW = 1;
-            if (THW < 1) continue;
-          } else {
-            THW = a.H;
-            TBW = (128 * T + 2 * lead) / ((a.H + 2 * halo) * Wp);
-            if (TBW < 2) continue;
-            TBW = std::min(TBW, 64);
-          }
-          const int Hw = THW + 2 * halo;
-          if (Wp > 256 || Hw > 256) continue;
-          const int rows_win = TBW * Hw * Wp;
-          if (rows_win - 2 * lead > 128 * T) continue;
-          const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
-          const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
-          int resident = 1, bst = 0;
-          size_t smem = 1024 + a_bytes + (size_t)w_tiles * b_stage_bytes + 1536;
-          if (smem > smem_cap) {
-            resident = 0;
-            bst = std::min(kMaxBStages, w_tiles);
-            smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
-            while (smem > smem_cap && bst > 2) {
-              --bst;
-              smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+      const int base_tiles = p->n_tiles;
+      for (int split = 1; split <= 4; split *= 2) {
+        const int n_tiles = base_tiles * split;
+        if (a.Cout_p % (16 * n_tiles)) continue;
+        const int n_tile = a.Cout_p / n_tiles;
+        if (n_tile > 256 || n_tile < 16) continue;
+        const size_t b_stage_bytes = ((size_t)n_tile * 128 + 1023) & ~(size_t)1023;
+        const int Tmax = std::min(8, 256 / n_tile);
+        for (int T = 1; T <= Tmax; ++T) {
+          for (int multi = 0; multi < 2; ++multi) {
+            int THW, TBW;
+            if (!multi) {
+              THW = std::min(a.H, (128 * T + 2 * halo) / Wp);
+              TBW = 1;
+              if (THW < 1) continue;
+            } else {
+              THW = a.H;
+              TBW = (128 * T + 2 * lead) / ((a.H + 2 * halo) * Wp);
+              if (TBW < 2) continue;
+              TBW = std::min(TBW, 64);
             }
+            const int Hw = THW + 2 * halo;
+            if (Wp > 256 || Hw > 256) continue;
+            const int rows_win = TBW * Hw * Wp;
+            if (rows_win - 2 * lead > 128 * T) continue;
+            const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
+            const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
+            const size_t smem = 1024 + a_bytes + (size_t)w_tiles * b_stage_bytes + 1536;
             if (smem > smem_cap) continue;
-          }
-          const int windows = multi ? 1 : ceil_div(a.H, THW);
-          const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
-                                   : (double)a.H * a.W / ((double)windows * T * 128);
-          const int n_win = windows * ceil_div(64, TBW);
-          // rounds of the persistent loop x per-window time (MMA rows + fixed cost; streamed weights cost extra)
-          const double est = ceil_div(n_win * p->n_tiles, 148) * (T * (resident ? 1.0 : 1.4) + 0.35);
-          if (est < best) {
-            best = est;
-            p->use_persist = true;
-            p->b_resident = resident;
-            p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
-            p->rows_alloc = rows_alloc; p->b_stages = resident ? 0 : bst; p->run_eff = (float)eff;
-            p->smem_bytes = smem;
-            p->tmem_cols = pow2_cols(2 * T * p->n_tile);
+            const int windows = multi ? 1 : ceil_div(a.H, THW);
+            const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
+                                     : (double)a.H * a.W / ((double)windows * T * 128);
+            const int n_win = windows * ceil_div(64, TBW);
+            // rounds of the persistent loop x per-window time; per-MMA cost from the measured issue-rate table
+            // (~45 cycles up to N=64, ~0.5 cycle per extra column beyond)
+            const double mma_cost = 45.0 + std::max(0, n_tile - 64) * 0.5;
+            const double est = ceil_div(n_win * n_tiles, 148) * (T * mma_cost / 45.0 + 0.35);
+            if (est < best) {
+              best = est;
+              p->use_persist = true;
+              p->b_resident = 1;
+              p->n_tiles = n_tiles;
+              p->n_tile = n_tile;
+              p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
+              p->rows_alloc = rows_alloc; p->b_stages = 0; p->run_eff = (float)eff;
+              p->smem_bytes = smem;
+              p->tmem_cols = pow2_cols(2 * T * n_tile);
+            }
           }
         }
       }
-      if (p->use_persist && p->run_eff < 0.6f) p->use_persist = false;
+      if (p->use_persist && p->run_eff < 0.6f) {
+        p->use_persist = false;
+        p->n_tiles = base_tiles;
+        p->n_tile = a.Cout_p / base_tiles;
+      }
       if (p->use_persist) p->use_run = false;
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
-        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB resident=%d bst=%d tmem=%u\n",
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d tmem=%u\n",
                 a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->T, p->THW, p->TBW, p->run_eff,
-                p->smem_bytes / 1024, p->b_resident, p->b_stages, p->tmem_cols);
+                p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->tmem_cols);
     }
   }
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
