@@ -1069,7 +1069,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const size_t smem_cap = 225 * 1024;
       double best = 1e30;
       const int base_tiles = p->n_tiles;
-      for (int split = 1; split <= 4; split *= 2) {
+      // (splitting the output channels further to make larger weight sets resident was measured and
+      //  rejected: 96ch@32x32 with n_tile=48, T=1 runs 2.1x slower than the v2 kernel)
+      for (int split = 1; split <= 1; split *= 2) {
         const int n_tiles = base_tiles * split;
         if (a.Cout_p % (16 * n_tiles)) continue;
         const int n_tile = a.Cout_p / n_tiles;
