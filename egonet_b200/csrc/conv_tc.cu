@@ -1097,8 +1097,20 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             if (rows_win - 2 * lead > 128 * T) continue;
             const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
             const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
-            const size_t smem = 1024 + a_bytes + (size_t)w_tiles * b_stage_bytes + 1536;
-            if (smem > smem_cap) continue;
+            size_t smem = 1024 + a_bytes + (size_t)w_tiles * b_stage_bytes + 1536;
+            int resident = 1, bst = 0;
+            if (smem > smem_cap) {
+              // weights streamed through a ring, once per window: only worth it when a window holds >= 2 M tiles
+              if (T < 2 || getenv("EGN_TC_V3_NOSTREAM")) continue;
+              resident = 0;
+              bst = std::min(kMaxBStages, w_tiles);
+              smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+              while (smem > smem_cap && bst > 3) {
+                --bst;
+                smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+              }
+              if (smem > smem_cap) continue;
+            }
             const int windows = multi ? 1 : ceil_div(a.H, THW);
             const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
                                      : (double)a.H * a.W / ((double)windows * T * 128);
@@ -1106,15 +1118,15 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             // rounds of the persistent loop x per-window time; per-MMA cost from the measured issue-rate table
             // (~45 cycles up to N=64, ~0.5 cycle per extra column beyond)
             const double mma_cost = 45.0 + std::max(0, n_tile - 64) * 0.5;
-            const double est = ceil_div(n_win * n_tiles, 148) * (T * mma_cost / 45.0 + 0.35);
+            const double est = ceil_div(n_win * n_tiles, 148) * (T * mma_cost / 45.0 + 0.35) * (resident ? 1.0 : 1.15);
             if (est < best) {
               best = est;
               p->use_persist = true;
-              p->b_resident = 1;
+              p->b_resident = resident;
               p->n_tiles = n_tiles;
               p->n_tile = n_tile;
               p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
-              p->rows_alloc = rows_alloc; p->b_stages = 0; p->run_eff = (float)eff;
+              p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
               p->smem_bytes = smem;
               p->tmem_cols = pow2_cols(2 * T * n_tile);
             }
@@ -1128,9 +1140,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
       if (p->use_persist) p->use_run = false;
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
-        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d tmem=%u\n",
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u\n",
                 a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->T, p->THW, p->TBW, p->run_eff,
-                p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->tmem_cols);
+                p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->b_resident, p->b_stages, p->tmem_cols);
     }
   }
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
