@@ -153,7 +153,7 @@ def profile_hc(ego, x, passes=3):
     return classes, float(acc.sum())
 
 
-def roofline_block(classes, total_ms, pk):
+def roofline_block(classes, total_ms, pk, batch):
     name, c = max(classes.items(), key=lambda kv: kv[1]['ms'])
     dur = c['ms'] / c['launches'] * 1e-3                      # seconds per launch
     bytes_per_launch = (c['act_bytes'] + c['weight_bytes']) / c['launches']
@@ -170,6 +170,13 @@ def roofline_block(classes, total_ms, pk):
            'share_of_hc_time': round(c['ms'] / total_ms, 4), 'launches': c['launches'],
            'avg_launch_us': round(dur * 1e6, 2), 'algorithmic_bytes_per_launch': int(bytes_per_launch),
            'flops_per_launch': int(flops_per_launch)}
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(name)
+        if tr and tr['batch'] == batch:
+            blk['traffic'] = tr['bytes']
+            blk['traffic_source'] = 'ncu --set full capture of this kernel class at this batch size (profiles/)'
+    except (OSError, ValueError):
+        pass
     top = sorted(classes.items(), key=lambda kv: -kv[1]['ms'])[:6]
     blk['top_classes'] = [{'kernel': k, 'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in top]
     return blk
@@ -411,7 +418,7 @@ def main():
         'clocks': clocks,
     }
     if classes:
-        line['roofline'] = roofline_block(classes, hc_ms, pk)
+        line['roofline'] = roofline_block(classes, hc_ms, pk, B)
         line['hc_roofline'] = {
             'tensor_frac': round(value / world * 2 * st['macs_per_crop'] / (pk['bf16_tflops_sustained'] * 1e12), 4),
             'hbm_frac': round(value / world * (st['act_bytes_per_crop'] + st['weight_bytes'] / B) / (pk['hbm_gbs'] * 1e9), 4),

@@ -215,10 +215,17 @@ __device__ __forceinline__ void epi_prefetch(const EpiArgs& e, const EpiRow& r, 
 __device__ __forceinline__ void epi_process(const EpiArgs& e, const EpiRow& r, uint32_t taddr, int n, int nch,
                                             const uint4 (&buf)[2 * kEpiGroup]) {
   uint32_t v[kEpiGroup][16];
+  if (!(e.dbg & 32)) {
 #pragma unroll
-  for (int c = 0; c < kEpiGroup; ++c)
-    if (c < nch) tmem_ld16(taddr + 16u * c, v[c]);
-  tmem_ld_wait();
+    for (int c = 0; c < kEpiGroup; ++c)
+      if (c < nch) tmem_ld16(taddr + 16u * c, v[c]);
+    tmem_ld_wait();
+  } else {
+#pragma unroll
+    for (int c = 0; c < kEpiGroup; ++c)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[c][j] = 0;
+  }
   if (!r.valid) return;
 #pragma unroll
   for (int c = 0; c < kEpiGroup; ++c) {
