@@ -82,6 +82,7 @@ SIGNATURES = {
     'egn_debug_umma_rate': (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_double)]),
     'egn_debug_umma_probe': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'egn_mse_hm_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
 

@@ -252,6 +252,17 @@ EGN_API int egn_pose_solve(const double* kpts_3d, int N, int P, const double* kp
                    double fx, double cx, int alpha_mode, double* pose_out, double* rot_out,
                    void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Heat-map MSE loss (training config only; loss end of SURVEY.md 8a row a12)   */
+/* replaces JointsMSELoss.forward libs/loss/function.py:28-46 and              */
+/* JointsCompositeLoss.calc_hm_loss libs/loss/function.py:95-111               */
+/* pred/target device fp32 [B,K,H,W]; target_weight device fp32 [B,K] or NULL;  */
+/* loss_out device fp32 scalar; grad_out device fp32 [B,K,H,W] (d loss/d pred)  */
+/* or NULL; workspace8: 8 bytes of device scratch.                              */
+/* ------------------------------------------------------------------------- */
+EGN_API int egn_mse_hm_fwd_bwd(const float* pred, const float* target, const float* target_weight, int B, int K,
+                       int H, int W, float* loss_out, float* grad_out, void* workspace8, void* stream);
+
 /* replaces the loops of EgoNet.get_observation_angle_trans / _proj (egonet.py:203-236):
  * alpha[n] = wrap(ry[n] - atan2(-z[n*stride_z], x[n*stride_x] - x_offset) - pi/2).
  * trans: x = translation[:,0], z = translation[:,2], x_offset = 0.

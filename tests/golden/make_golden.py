@@ -231,6 +231,26 @@ def golden_pipeline(ref):
          centers=np.array([r['center'] for r in recs]), scales=np.array([r['scale'] for r in recs]))
 
 
+def golden_loss(ref):
+    """JointsMSELoss (with / without target weights, incl. autograd gradient) and calc_hm_loss."""
+    import libs.loss.function as F
+    g = rng(21)
+    pred = g.standard_normal((4, 33, 16, 12), dtype=np.float32)
+    gt = np.exp(-g.uniform(0, 6, (4, 33, 16, 12))).astype(np.float32)
+    w = (g.uniform(0, 1, (4, 33, 1)) > 0.3).astype(np.float32)
+    out = {'pred': pred, 'gt': gt, 'w': w}
+    for use_w in (False, True):
+        p = torch.tensor(pred, requires_grad=True)
+        loss = F.JointsMSELoss(use_w)(p, torch.tensor(gt), torch.tensor(w))
+        loss.backward()
+        out['loss_w%d' % use_w] = loss.detach().numpy()
+        out['grad_w%d' % use_w] = p.grad.numpy()
+    comp = F.JointsCompositeLoss.__new__(F.JointsCompositeLoss)
+    comp.comp_dict = {'hm': (torch.nn.MSELoss(reduction='mean'), 1.0)}
+    out['calc_hm_loss'] = comp.calc_hm_loss(torch.tensor(pred), torch.tensor(gt)).numpy()
+    save('loss.npz', **out)
+
+
 def main():
     ref = import_reference()
     torch.set_num_threads(os.cpu_count())
@@ -243,6 +263,7 @@ def main():
     golden_lifter(ref)
     golden_pose(ref)
     golden_pipeline(ref)
+    golden_loss(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,

@@ -334,12 +334,19 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize('variant', ['auto', 'no_v3', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
-def test_conv_layer_tc_and_simt_vs_torch(case):
+def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
     """One fused conv (bias + residual + ReLU) through the tcgen05 and the CUDA-core kernels against
-    torch's fp32 conv2d on the same fp16-rounded operands."""
+    torch's fp32 conv2d on the same fp16-rounded operands.  `variant` restricts which tcgen05 kernel the
+    plan may pick (auto: v3 persistent / v2 window-run / v1 per-tap by shape; no_v3; v1_only), so every
+    kernel is exercised on every shape it supports."""
     import ctypes
     from egonet_b200 import _native as N
+    if variant in ('no_v3', 'v1_only'):
+        monkeypatch.setenv('EGN_TC_V3', '0')
+    if variant == 'v1_only':
+        monkeypatch.setenv('EGN_TC_V2', '0')
     Cin, Cout, H, W, k, stride, B = case
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)
     x = torch.randn((B, Cin, H, W), generator=g).to(DEV)
@@ -370,3 +377,23 @@ def test_conv_layer_tc_and_simt_vs_torch(case):
         outs[impl] = out
     # the two kernels see identical operands: they may differ by fp32 summation order only
     assert (outs[0].float() - outs[1].float()).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+# --------------------------------------------------------------------------- training-config loss (row a12, loss end)
+def test_heatmap_mse_loss_vs_reference_golden(golden):
+    from egonet_b200.libs.loss.function import JointsMSELoss, calc_hm_loss, mse_hm_fwd_bwd
+    g = golden('loss.npz')
+    pred, gt, w = cuda(g['pred']), cuda(g['gt']), cuda(g['w'])
+    for use_w in (0, 1):
+        loss, grad = mse_hm_fwd_bwd(pred, gt, w if use_w else None)
+        assert float(loss) == pytest.approx(float(g['loss_w%d' % use_w]), rel=1e-5)
+        np.testing.assert_allclose(grad.cpu().numpy(), g['grad_w%d' % use_w], rtol=1e-5, atol=1e-9)
+        assert float(JointsMSELoss(bool(use_w))(pred, gt, w)) == pytest.approx(float(g['loss_w%d' % use_w]), rel=1e-5)
+    assert float(calc_hm_loss(pred, gt)) == pytest.approx(float(g['calc_hm_loss']), rel=1e-5)
+    # BASELINE configs[3] shape (batch 128, 33 x 64 x 64): finite-difference property of the fused gradient
+    big = torch.randn((128, 33, 64, 64), device=DEV)
+    tgt = torch.rand((128, 33, 64, 64), device=DEV)
+    loss, grad = mse_hm_fwd_bwd(big, tgt)
+    ref = 0.5 * ((big - tgt) ** 2).double().mean()
+    assert float(loss) == pytest.approx(float(ref), rel=1e-5)
+    assert torch.allclose(grad, (big - tgt) / big.numel(), rtol=1e-5, atol=1e-12)

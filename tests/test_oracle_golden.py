@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import affine_ref, configs, decode_ref, egonet_ref, hrnet_ref, lifter_ref, pose_ref
+from oracle import affine_ref, configs, decode_ref, egonet_ref, hrnet_ref, lifter_ref, loss_ref, pose_ref
 
 HRNET_CASES = [('tiny', configs.tiny_cfgs()), ('tiny_heatmap', configs.tiny_cfgs('heatmap')),
                ('ped', configs.ped_cfgs()), ('demo', configs.demo_cfgs())]
@@ -147,3 +147,12 @@ def test_pipeline_oracle_matches_reference(golden):
     np.testing.assert_allclose(out['translation'], g['translation'], rtol=0, atol=1e-4)
     np.testing.assert_allclose(out['alpha_trans'], g['alpha_trans'], rtol=0, atol=1e-4)
     np.testing.assert_allclose(out['alpha_proj'], g['alpha_proj'], rtol=0, atol=1e-4)
+
+
+def test_loss_oracle_matches_reference(golden):
+    g = golden('loss.npz')
+    for use_w in (0, 1):
+        loss, grad = loss_ref.joints_mse_loss(g['pred'], g['gt'], g['w'] if use_w else None)
+        assert loss == pytest.approx(float(g['loss_w%d' % use_w]), rel=1e-6)
+        np.testing.assert_allclose(grad, g['grad_w%d' % use_w], rtol=1e-5, atol=1e-10)
+    assert float(g['calc_hm_loss']) == pytest.approx(float(g['loss_w0']), rel=1e-7)
