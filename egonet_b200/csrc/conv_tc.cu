@@ -750,7 +750,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int slot = j & 1;
       mbar_wait(&a_empty[slot], (uint32_t)((j >> 1) & 1) ^ 1u);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
-      if (elect_one()) {
+      if (!(p.dbg & 8) && elect_one()) {
         mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
         for (int c = 0; c < p.kchunks; ++c)
           tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
@@ -797,9 +797,12 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
       mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
       if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 1] = gtime();
-      mbar_wait(&a_full[slot], ph);                 // window landed
+      if (!(p.dbg & 8)) mbar_wait(&a_full[slot], ph);                 // window landed
       tc_fence_after();
-      if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
+      if (p.ts && lane == 0 && j < 8) {
+        p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
+        p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 6] = (unsigned long long)clock64();
+      }
       uint32_t accumulate = 0;
       int tile = 0;
       for (int r = 0; r < ntap; ++r) {
@@ -842,7 +845,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (elect_one()) {
         umma_commit(&a_empty[slot]);      // window slot may be refilled
         umma_commit(&acc_full[slot]);     // accumulators complete
-        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 3] = gtime();
+        if (p.ts && j < 8) {
+          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 3] = gtime();
+          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 7] = (unsigned long long)clock64();
+        }
       }
     }
   } else if (warp >= 4) {
@@ -858,6 +864,13 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
       const int h0 = win * p.THW, b0 = bg * p.TBW;
+      if (p.dbg & 64) {
+        mbar_wait(&acc_full[grp], ph);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[grp]);
+        continue;
+      }
       e.ts = (p.ts && j < 8) ? p.ts + ((size_t)blockIdx.x * 8 + j) * 8 : nullptr;
       epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * acc_cols), p.T, p.n_tile, n0,
               &acc_full[grp], [&](int t) {
@@ -1316,8 +1329,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
         for (int j = 0; j < 6; ++j) {
           const unsigned long long* q = &h[((size_t)cta * 8 + j) * 8];
           if (!q[0]) continue;
-          fprintf(stderr, "[egn-ts3] cta %d win %d: mma-loop-top %.2f acc-empty-ok %.2f a-full-ok %.2f mma-issued %.2f | epi acc-full-ok %.2f epi-done %.2f (us)\n",
-                  cta, j, (q[0] - t0) * 1e-3, (q[1] - t0) * 1e-3, (q[2] - t0) * 1e-3, (q[3] - t0) * 1e-3, (q[4] - t0) * 1e-3, (q[5] - t0) * 1e-3);
+          fprintf(stderr, "[egn-ts3] cta %d win %d: mma-loop-top %.2f acc-empty-ok %.2f a-full-ok %.2f mma-issued %.2f | epi acc-full-ok %.2f epi-done %.2f (us) | mma phase %llu SM cycles\n",
+                  cta, j, (q[0] - t0) * 1e-3, (q[1] - t0) * 1e-3, (q[2] - t0) * 1e-3, (q[3] - t0) * 1e-3, (q[4] - t0) * 1e-3, (q[5] - t0) * 1e-3, q[7] - q[6]);
         }
       }
     }
@@ -1536,7 +1549,14 @@ umma_rate_kernel(int n, int nacc, int iters, int a_rows_shift, long long* __rest
   uint8_t* sb = smem + 1024 * 128;    // 256 rows x 128 B
   uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 256 * 128);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
-  for (int i = threadIdx.x; i < (1024 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  // a_rows_shift >= 1000: fill the operands with pseudo-random finite fp16 values instead of zeros
+  const bool random_fill = a_rows_shift >= 1000;
+  if (random_fill) a_rows_shift -= 1000;
+  for (int i = threadIdx.x; i < (1024 + 256) * 128 / 4; i += 128) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    reinterpret_cast<uint32_t*>(smem)[i] = random_fill ? ((h & 0x83FF83FFu) | 0x38003800u) : 0u;
+  }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);

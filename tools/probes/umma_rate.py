@@ -1,4 +1,4 @@
-"""SM cycles per tcgen05.mma (M=128,K=16,f16,SS) vs N / accumulator rotation / CTA count / A row shift."""
+"""SM cycles per tcgen05.mma (M=128,K=16,f16,SS) vs N / accumulator rotation / CTA count / operand data."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
@@ -9,8 +9,9 @@ def rate(n, nacc, shift=0, ctas=1):
     v = ctypes.c_double(0)
     N.check(L.egn_debug_umma_rate(n, nacc, 200, shift, ctas, ctypes.byref(v)))
     return v.value
-print('N   nacc=1   nacc=2  nacc=max  (1 CTA)   | 148 CTAs nacc=max | shift=67 rows')
+print('N   nacc=1  nacc=2  nacc=max | 148 CTAs nacc=max | shift 67 rows | RANDOM data nacc=max 1 CTA / 148 CTAs | random nacc=3')
 for n in (16, 32, 48, 64, 96, 128, 192, 256):
     m = max(1, min(8, 512 // n))
-    print('%3d  %7.1f  %7.1f  %7.1f (x%d)      |  %7.1f          |  %7.1f' % (
-        n, rate(n, 1), rate(n, min(2, m)), rate(n, m), m, rate(n, m, 0, 148), rate(n, m, 67)))
+    print('%3d %7.1f %7.1f %7.1f (x%d) | %7.1f          | %7.1f       | %7.1f / %7.1f                   | %7.1f' % (
+        n, rate(n, 1), rate(n, min(2, m)), rate(n, m), m, rate(n, m, 0, 148), rate(n, m, 67), rate(n, m, 1000), rate(n, m, 1000, 148),
+        rate(n, min(3, m), 1000, 148)))
