@@ -158,6 +158,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld that names the destination registers of the outstanding load as in/out operands, so
+// the compiler cannot hoist arithmetic on them above the wait when the load was issued earlier.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+// Asynchronous L2 prefetch of a contiguous global range (bytes: multiple of 16).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 
 // K-major, swizzled shared-memory matrix descriptor (sm_100 "version 1"):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1)
@@ -290,22 +331,31 @@ struct EpiCursor {
 
 template <typename RowFn>
 __device__ __forceinline__ void epi_run(const EpiArgs& e, uint32_t tmem_lane_base, int T, int n_tile, int n0,
-                                        uint64_t* tmem_full_bar, RowFn row_of, uint32_t parity = 0) {
+                                        uint64_t* tmem_full_bar, RowFn row_of, uint32_t parity = 0, int half = 0,
+                                        int halves = 1) {
+  // With halves == 2 two warps share each TMEM lane quarter and split the (tile, group) items of a
+  // window in a checkerboard ((t + group) & 1), which balances 32/16-column groups across the pair.
   const int nch_total = n_tile >> 4;
   const int groups = (nch_total + kEpiGroup - 1) / kEpiGroup;
   uint4 bufA[2 * kEpiGroup], bufB[2 * kEpiGroup];
-  auto advance = [&](EpiCursor& c) {          // next group; recompute the row only when the tile changes
+  auto step = [&](EpiCursor& c) {             // next group; recompute the row only when the tile changes
     if (++c.gi == groups) {
       c.gi = 0;
       ++c.t;
       if (c.t < T) c.row = row_of(c.t);
     }
   };
+  auto mine = [&](const EpiCursor& c) { return halves == 1 || ((c.t + c.gi) & 1) == half; };
+  auto advance = [&](EpiCursor& c) {
+    step(c);
+    while (c.t < T && !mine(c)) step(c);      // at most two foreign items in a row (tile boundary)
+  };
   auto nch_of = [&](const EpiCursor& c) { return min(kEpiGroup, nch_total - c.gi * kEpiGroup); };
   auto n_of = [&](const EpiCursor& c) { return n0 + 16 * kEpiGroup * c.gi; };
   auto ta_of = [&](const EpiCursor& c) { return tmem_lane_base + (uint32_t)(c.t * n_tile + 16 * kEpiGroup * c.gi); };
   EpiCursor ca{0, 0, row_of(0)};
-  epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
+  while (ca.t < T && !mine(ca)) step(ca);
+  if (ca.t < T) epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
   mbar_wait(tmem_full_bar, parity);
   tc_fence_after();
   if (e.ts && (threadIdx.x & 127) == 64) e.ts[4] = gtime();
@@ -320,6 +370,123 @@ __device__ __forceinline__ void epi_run(const EpiArgs& e, uint32_t tmem_lane_bas
     advance(ca);
     if (ca.t < T) epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
     epi_process(e, cb.row, ta_of(cb), n_of(cb), nch_of(cb), bufB);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// compact epilogue of the persistent kernel (plain layers: bias [+ residual] [+ ReLU] -> fp16 NHWC)
+//
+// The generic epilogue above is ~3000 straight-line instructions per window (two register buffers x two
+// column chunks x the head extras); a warp walking through it once per window runs at ~0.25 IPC.  This
+// one is a single-item loop body without the head code.  An item is 16 accumulator columns of one M
+// tile; kParts (4) warps share a TMEM lane quarter and take items idx = part, part + kParts, ...
+// While item i is converted, the TMEM load of item i+1 and the residual loads of items i+1 and i+2
+// (2 x 32 bytes per thread) are in flight.
+// ---------------------------------------------------------------------------
+struct EpiLite {
+  const __half* res;
+  __half* out;
+  uint32_t bias_s;     // shared-space address of this CTA's bias slice (n_tile floats)
+  int relu, Cout_p, dbg;
+};
+
+struct LiteItem {
+  int t, g;            // M tile, 16-column chunk inside the tile
+  bool valid;
+  size_t pix;
+};
+
+__device__ __forceinline__ void lite_res_load(const EpiLite& e, const LiteItem& it, int n, uint4 (&rb)[2]) {
+  if (!e.res || !it.valid || (e.dbg & 2)) return;
+  const uint4* rp = reinterpret_cast<const uint4*>(e.res + it.pix * e.Cout_p + n);
+  rb[0] = __ldg(rp);
+  rb[1] = __ldg(rp + 1);
+}
+
+__device__ __forceinline__ void lite_store(const EpiLite& e, const LiteItem& it, int n, int nl, const uint32_t (&v)[16],
+                                           const uint4 (&rb)[2]) {
+  if (!it.valid) return;
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 bq = lds_f4(e.bias_s + (uint32_t)(nl + 4 * j) * 4u);
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bq.x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bq.y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bq.z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bq.w;
+  }
+  if (e.res) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const __half2* r2 = reinterpret_cast<const __half2*>(&rb[h]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 rf = __half22float2(r2[j]);
+        f[8 * h + 2 * j] += rf.x;
+        f[8 * h + 2 * j + 1] += rf.y;
+      }
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  uint4 o[2];
+  __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  if (!(e.dbg & 1)) {
+    uint4* op = reinterpret_cast<uint4*>(e.out + it.pix * e.Cout_p + n);
+    op[0] = o[0];
+    op[1] = o[1];
+  }
+}
+
+template <int kParts, typename RowFn>
+__device__ __forceinline__ void epi_window_lite(const EpiLite& e, uint32_t tmem_lane_base, int T, int n_tile, int n0,
+                                                uint64_t* full_bar, uint32_t parity, int half, RowFn row_of,
+                                                unsigned long long* ts) {
+  const int per_tile = n_tile >> 4;
+  auto next = [&](const LiteItem& it) {              // item + kParts; refresh the row when the tile changes
+    LiteItem n = it;
+    n.g += kParts;
+    while (n.g >= per_tile) {
+      n.g -= per_tile;
+      ++n.t;
+    }
+    if (n.t != it.t && n.t < T) {
+      const EpiRow r = row_of(n.t);
+      n.valid = r.valid;
+      n.pix = r.pix;
+    }
+    return n;
+  };
+  auto taddr = [&](const LiteItem& it) { return tmem_lane_base + (uint32_t)(it.t * n_tile + 16 * it.g); };
+
+  LiteItem cur{-1, half - kParts + per_tile, false, 0};   // one step before the first item of tile 0
+  cur = next(cur);
+  LiteItem n1 = next(cur), n2 = next(n1);
+  uint4 r0[2] = {}, r1[2] = {}, r2[2] = {};
+  uint32_t v0[16], v1[16];
+  if (cur.t < T) lite_res_load(e, cur, n0 + 16 * cur.g, r0);
+  if (n1.t < T) lite_res_load(e, n1, n0 + 16 * n1.g, r1);
+  mbar_wait(full_bar, parity);
+  tc_fence_after();
+  if (ts && (threadIdx.x & 127) == 64) ts[4] = gtime();
+  if (cur.t < T) tmem_ld(taddr(cur), v1);
+#pragma unroll 1
+  while (cur.t < T) {
+    if (n2.t < T) lite_res_load(e, n2, n0 + 16 * n2.g, r2);
+    tmem_ld_wait_dep(v1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v0[i] = v1[i];
+    if (n1.t < T) tmem_ld(taddr(n1), v1);
+    lite_store(e, cur, n0 + 16 * cur.g, 16 * cur.g, v0, r0);
+    r0[0] = r1[0]; r0[1] = r1[1];
+    r1[0] = r2[0]; r1[1] = r2[1];
+    cur = n1;
+    n1 = n2;
+    n2 = next(n2);
   }
 }
 
@@ -679,12 +846,13 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 //   warp 0      A producer: double-buffered input windows (a_full / a_empty)
 //   warp 1      MMA issuer: accumulates window j into TMEM set j&1 (acc_full / acc_empty)
 //   warp 2      B producer: the whole weight matrix once if it fits in smem (w_full), else a ring
-//   warps 4-7   epilogue group 0: drains TMEM set 0 (even windows)
-//   warps 8-11  epilogue group 1: drains TMEM set 1 (odd windows)
+//   warps 4-11  epilogue: all eight warps drain the accumulator set of the window just finished
+//               (two warps per TMEM lane quarter, items split in a checkerboard)
 // so while the tensor pipe works on window j, window j+1 is landing in the other smem slot and the
-// accumulators of window j-1 are being converted / stored by the other epilogue group.
+// accumulators of window j-1 are being converted / stored.
 // ---------------------------------------------------------------------------
-constexpr int kPersistThreads = 384;
+constexpr int kPersistThreadsHead = 384;   // 4 role warps + 2 x 4 epilogue warps (generic epilogue, 161 registers)
+constexpr int kPersistThreads = 640;       // 4 role warps + 4 x 4 epilogue warps (compact epilogue)
 
 struct PersistParams {
   RunParams r;          // geometry / operands as in v2 (r.b_stages = ring depth when streaming)
@@ -692,7 +860,8 @@ struct PersistParams {
   int b_resident;       // 1: all taps*kchunks weight tiles live in smem for the CTA's lifetime
 };
 
-__global__ void __launch_bounds__(kPersistThreads, 1)
+template <bool kHead>   // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps)
+__global__ void __launch_bounds__(kHead ? kPersistThreadsHead : kPersistThreads, 1)
 conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const PersistParams pp) {
   const RunParams& p = pp.r;
@@ -714,10 +883,38 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* b_empty = b_full + kMaxBStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // offset (9 + 12) * 8 + 8 = 176: 16-byte aligned
+  uint4* s_issue = reinterpret_cast<uint4*>(s_bias + p.n_tile);   // [n_mma] issue table (n_tile % 16 == 0)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.n_tile;
-  for (int i = threadIdx.x; i < p.n_tile; i += kPersistThreads) s_bias[i] = __ldg(p.bias + n0 + i);
+  constexpr int kParts = kHead ? 2 : 4;              // epilogue warps per TMEM lane quarter
+  for (int i = threadIdx.x; i < p.n_tile; i += (int)blockDim.x) s_bias[i] = __ldg(p.bias + n0 + i);
+  // Issue table: one entry per tcgen05.mma of a window, in issue order (tap, 64-channel chunk, K16
+  // slice, M tile).  The single issuing thread then runs a flat loop of {LDS.128, 3 adds, MMA}; the
+  // nested-loop form spent ~80 SM cycles of scalar work per MMA, twice what the tensor pipe needs
+  // for a 128x48x16 tile (profiles/r01_umma_rate.json).
+  //   x: A descriptor start-address offset from the window slot (>>4)   y: same for the weights
+  //   z: TMEM column offset of the M tile   w: bit0 accumulate, bit1 first / bit2 last MMA of a weight tile
+  {
+    const int ktot = (p.Cin_p + 15) >> 4;                      // K16 slices per tap
+    const int n_mma = p.taps * ktot * p.T;
+    const int ntap_w = p.halo ? 3 : 1;
+    const uint32_t b_stage_t = ((uint32_t)p.n_tile * 128u + 1023u) & ~1023u;
+    for (int i = threadIdx.x; i < n_mma; i += (int)blockDim.x) {
+      const int t = i % p.T, kk = i / p.T;
+      const int tap = kk / ktot, kr = kk - tap * ktot;
+      const int c = kr >> 2, k = kr & 3;
+      const int r = tap / ntap_w, q = tap - r * ntap_w;
+      const int ksteps_c = (c == p.kchunks - 1) ? ktot - 4 * c : 4;
+      uint4 e;
+      e.x = (((uint32_t)c * (uint32_t)p.rows_alloc * 128u + (uint32_t)(r * p.Wp + q) * 128u + (uint32_t)t * 16384u) >> 4) +
+            2u * (uint32_t)k;
+      e.y = (pp.b_resident ? ((uint32_t)(tap * p.kchunks + c) * b_stage_t) >> 4 : 0u) + 2u * (uint32_t)k;
+      e.z = (uint32_t)(t * p.n_tile);
+      e.w = (kk > 0 ? 1u : 0u) | ((k == 0 && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && t == p.T - 1) ? 4u : 0u);
+      s_issue[i] = e;
+    }
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -725,7 +922,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 128 * kParts);
     }
     mbar_init(w_full, 1);
     for (int i = 0; i < kMaxBStages; ++i) {
@@ -739,8 +936,6 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const int ntap = p.halo ? 3 : 1;
-  const int last_ksteps = (p.Cin_p - (p.kchunks - 1) * 64 + 15) >> 4;
   const int acc_cols = p.T * p.n_tile;                       // TMEM columns of one accumulator set
 
   if (warp == 0) {
@@ -755,6 +950,13 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int c = 0; c < p.kchunks; ++c)
           tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
                       win * p.THW - p.halo, bg * p.TBW);
+        if (p.res && !(p.dbg & 128)) {
+          // the residual rows of this window are one contiguous NHWC range: pull them towards L2 now,
+          // ~2 windows before the epilogue reads them
+          const int b0 = bg * p.TBW, h0 = win * p.THW;
+          const int rows = p.TBW > 1 ? min(p.TBW, p.B - b0) * p.H : min(p.THW, p.H - h0);
+          l2_prefetch_bulk(p.res + ((size_t)b0 * p.H + h0) * p.W * p.Cout_p, (uint32_t)(rows * p.W * p.Cout_p * 2));
+        }
       }
     }
   } else if (warp == 2) {
@@ -785,55 +987,47 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t desc_hi = make_smem_desc(0, 128);
-    const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
-    if (pp.b_resident) mbar_wait(w_full, 0);
-    uint32_t stage = 0, phase = 0;
-    int j = 0;
-    for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
-      const int slot = j & 1;
-      const uint32_t ph = (uint32_t)((j >> 1) & 1);
-      if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
-      mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
-      if (p.ts && lane == 0 && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 1] = gtime();
-      if (!(p.dbg & 8)) mbar_wait(&a_full[slot], ph);                 // window landed
-      tc_fence_after();
-      if (p.ts && lane == 0 && j < 8) {
-        p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
-        p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 6] = (unsigned long long)clock64();
-      }
-      uint32_t accumulate = 0;
-      int tile = 0;
-      for (int r = 0; r < ntap; ++r) {
-        for (int q = 0; q < ntap; ++q) {
-          const uint32_t shift = (uint32_t)(r * p.Wp + q) * 128u;
-          for (int c = 0; c < p.kchunks; ++c, ++tile) {
-            uint32_t b_addr;
-            if (pp.b_resident) {
-              b_addr = b_addr0 + (uint32_t)tile * b_stage;
-            } else {
+    // One elected thread runs the whole role (waits, MMAs, commits): no per-burst elect / reconvergence.
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t desc_hi = make_smem_desc(0, 128);
+      const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+      const int n_mma = p.taps * ((p.Cin_p + 15) >> 4) * p.T;
+      if (pp.b_resident) mbar_wait(w_full, 0);
+      uint32_t stage = 0, phase = 0;
+      int j = 0;
+      for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+        const int slot = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
+        mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
+        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 1] = gtime();
+        if (!(p.dbg & 8)) mbar_wait(&a_full[slot], ph);                 // window landed
+        tc_fence_after();
+        if (p.ts && j < 8) {
+          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
+          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 6] = (unsigned long long)clock64();
+        }
+        const uint32_t a_lo = a_lo0 + (((uint32_t)slot * a_slot) >> 4);
+        const uint32_t d0 = tmem_base + (uint32_t)(slot * acc_cols);
+        if (pp.b_resident) {
+#pragma unroll 4
+          for (int i = 0; i < n_mma; ++i) {
+            const uint4 e = s_issue[i];
+            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+          }
+        } else {
+          uint32_t b_lo = b_lo0;
+          for (int i = 0; i < n_mma; ++i) {
+            const uint4 e = s_issue[i];
+            if (e.w & 2u) {
               mbar_wait(&b_full[stage], phase);
               tc_fence_after();
-              b_addr = b_addr0 + stage * b_stage;
+              b_lo = b_lo0 + ((stage * b_stage) >> 4);
             }
-            const uint64_t ad0 =
-                desc_hi | (uint64_t)(((a_addr0 + (uint32_t)slot * a_slot + (uint32_t)c * a_chunk + shift) & 0x3FFFFu) >> 4);
-            const uint64_t bd0 = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
-            const int ksteps = (c == p.kchunks - 1) ? last_ksteps : 4;
-            // K16 slice outer, M tile inner: consecutive MMAs hit different accumulators, so the
-            // accumulate dependency of one tile never stalls the next instruction
-            if (elect_one()) {
-              for (int k = 0; k < ksteps; ++k) {
-                uint64_t ad = ad0 + (uint64_t)(2 * k);
-                uint32_t d = tmem_base + (uint32_t)(slot * acc_cols);
-                for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile)
-                  umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)(k > 0));
-              }
-            }
-            accumulate = 1u;
-            if (!pp.b_resident) {
-              if (elect_one()) umma_commit(&b_empty[stage]);
+            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo + e.y), idesc, e.w & 1u);
+            if (e.w & 4u) {
+              umma_commit(&b_empty[stage]);
               if (++stage == (uint32_t)p.b_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -841,8 +1035,6 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         }
-      }
-      if (elect_one()) {
         umma_commit(&a_empty[slot]);      // window slot may be refilled
         umma_commit(&acc_full[slot]);     // accumulators complete
         if (p.ts && j < 8) {
@@ -852,28 +1044,31 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue groups =====================
-    const int grp = (warp - 4) >> 2;                  // 0: even windows, 1: odd windows
+    // ===================== epilogue (8 warps on every window) =====================
+    // Two warps per TMEM lane quarter split each window's (tile, column group) items between them.
+    // One epilogue of half the length per window lets the MMA warp alternate accumulator sets without
+    // waiting: with one 4-warp group per set the cadence was (t_mma + t_epi) / 2 instead of max(t_mma, t_epi).
+    const int half = (warp - 4) >> 2;                  // which of the kParts warps of this lane quarter
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
               nullptr};
+    const EpiLite el{p.res, p.out, smem_u32(s_bias), p.relu, p.Cout_p, p.dbg};
     int j = 0;
     for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
-      if ((j & 1) != grp) continue;
+      const int slot = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
       const int h0 = win * p.THW, b0 = bg * p.TBW;
       if (p.dbg & 64) {
-        mbar_wait(&acc_full[grp], ph);
+        mbar_wait(&acc_full[slot], ph);
         tc_fence_after();
         tc_fence_before();
-        mbar_arrive(&acc_empty[grp]);
+        mbar_arrive(&acc_empty[slot]);
         continue;
       }
-      e.ts = (p.ts && j < 8) ? p.ts + ((size_t)blockIdx.x * 8 + j) * 8 : nullptr;
-      epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(grp * acc_cols), p.T, p.n_tile, n0,
-              &acc_full[grp], [&](int t) {
+      auto row_of = [&](int t) {
+        // run position -> window position -> (image, row, column); float reciprocals are exact here
         const int pos = t * 128 + row + p.lead;
         const int bi = p.TBW == 1 ? 0 : (int)(((float)pos + 0.5f) * p.inv_img);
         const int rem = pos - bi * p.img_rows;
@@ -887,10 +1082,18 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                    wp < p.Wp - p.halo && rr.b < p.B && rr.oh < p.H;
         rr.pix = ((size_t)rr.b * p.H + rr.oh) * p.W + rr.ow;
         return rr;
-      }, ph);
-      if (e.ts && (threadIdx.x & 127) == 64) e.ts[5] = gtime();
+      };
+      unsigned long long* ts = (p.ts && j < 8 && half == 0) ? p.ts + ((size_t)blockIdx.x * 8 + j) * 8 : nullptr;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * acc_cols);
+      if constexpr (kHead) {
+        e.ts = ts;
+        epi_run(e, tbase, p.T, p.n_tile, n0, &acc_full[slot], row_of, ph, half, 2);
+      } else {
+        epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts);
+      }
+      if (p.ts && j < 8 && lane == 0) atomicMax(p.ts + ((size_t)blockIdx.x * 8 + j) * 8 + 5, gtime());   // last warp done
       tc_fence_before();
-      mbar_arrive(&acc_empty[grp]);       // 128 arrivals release the accumulator set to the MMA warp
+      mbar_arrive(&acc_empty[slot]);      // all epilogue threads release the accumulator set to the MMA warp
     }
   }
   tc_fence_before();
@@ -1089,9 +1292,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const size_t smem_cap = 225 * 1024;
       double best = 1e30;
       const int base_tiles = p->n_tiles;
-      // (splitting the output channels further to make larger weight sets resident was measured and
-      //  rejected: 96ch@32x32 with n_tile=48, T=1 runs 2.1x slower than the v2 kernel)
-      for (int split = 1; split <= 1; split *= 2) {
+      // Splitting the output channels over blockIdx.y (split = 2) lets each half keep its weights resident
+      // when the whole matrix does not fit (96 channels: 2 x 108 KB); both halves then load the window.
+      for (int split = 1; split <= (getenv("EGN_TC_V3_NOSPLIT") ? 1 : 2); split *= 2) {
         const int n_tiles = base_tiles * split;
         if (a.Cout_p % (16 * n_tiles)) continue;
         const int n_tile = a.Cout_p / n_tiles;
@@ -1117,28 +1320,38 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             if (rows_win - 2 * lead > 128 * T) continue;
             const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
             const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
-            size_t smem = 1024 + a_bytes + (size_t)w_tiles * b_stage_bytes + 1536;
+            const size_t fixed = 1024 + 256 + (size_t)n_tile * 4 +
+                                 (size_t)a.ksize * a.ksize * ((a.Cin_p + 15) / 16) * T * 16;   // barriers, bias, issue table
+            size_t smem = a_bytes + (size_t)w_tiles * b_stage_bytes + fixed;
             int resident = 1, bst = 0;
             if (smem > smem_cap) {
               // weights streamed through a ring, once per window: only worth it when a window holds >= 2 M tiles
               if (T < 2 || getenv("EGN_TC_V3_NOSTREAM")) continue;
               resident = 0;
               bst = std::min(kMaxBStages, w_tiles);
-              smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+              smem = a_bytes + bst * b_stage_bytes + fixed;
               while (smem > smem_cap && bst > 3) {
                 --bst;
-                smem = 1024 + a_bytes + bst * b_stage_bytes + 1536;
+                smem = a_bytes + bst * b_stage_bytes + fixed;
               }
               if (smem > smem_cap) continue;
             }
             const int windows = multi ? 1 : ceil_div(a.H, THW);
             const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
                                      : (double)a.H * a.W / ((double)windows * T * 128);
-            const int n_win = windows * ceil_div(64, TBW);
-            // rounds of the persistent loop x per-window time; per-MMA cost from the measured issue-rate table
-            // (~45 cycles up to N=64, ~0.5 cycle per extra column beyond)
-            const double mma_cost = 45.0 + std::max(0, n_tile - 64) * 0.5;
-            const double est = ceil_div(n_win * n_tiles, 148) * (T * mma_cost / 45.0 + 0.35) * (resident ? 1.0 : 1.15);
+            // cost model in SM cycles at the nominal batch 256 (measured constants, profiles/r01_*):
+            //   tcgen05.mma 128 x N x 16: 40 cycles up to N=32, 44 @48, 48 @64, 56 @96, 64 @128, 118 @192, 150 @256
+            //   compact epilogue: ~250 cycles per 16-column item and lane quarter (4 warps per quarter)
+            //   streamed weights: ~2400 cycles per ring tile (measured on 48- and 96-channel layers; the ring does
+            //   not hide the L2 latency behind the window loads queued on the same TMA unit) -> last resort
+            const int n_win = windows * ceil_div(256, TBW);
+            const double mma_cyc = n_tile <= 32 ? 40.0 : n_tile <= 64 ? 40.0 + (n_tile - 32) * 0.25
+                                 : n_tile <= 128 ? 48.0 + (n_tile - 64) * 0.25 : 64.0 + (n_tile - 128) * 0.68;
+            const double t_mma = (double)a.ksize * a.ksize * ((a.Cin_p + 15) / 16) * T * mma_cyc;
+            const double t_epi = (double)T * (n_tile / 16) * 250.0;
+            const double t_w = resident ? 0.0 : (double)w_tiles * 2400.0;
+            const double t_a = (double)p->kchunks * rows_win * 128 / 48.0;      // window load, ~48 B/cycle/SM
+            const double est = ceil_div(n_win * n_tiles, 148) * (std::max(std::max(t_mma, t_epi), std::max(t_w, t_a)) + 300.0);
             if (est < best) {
               best = est;
               p->use_persist = true;
@@ -1307,7 +1520,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     pp.b_resident = p->b_resident;
     static bool attr_set = false;
     if (!attr_set) {
-      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
     static int num_sms = 0;
@@ -1317,7 +1531,10 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
-    conv_persist_kernel<<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, pp);
+    if (a.heatmap || a.coord_maps || getenv("EGN_TC_EPI_GENERIC"))
+      conv_persist_kernel<true><<<grid, kPersistThreadsHead, p->smem_bytes, st>>>(ma, p->map_b, pp);
+    else
+      conv_persist_kernel<false><<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, pp);
     EGN_LAUNCH_CHECK("conv_persist_kernel");
     if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
       cudaStreamSynchronize(st);
