@@ -122,6 +122,31 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       "r"(c3), "r"(c4)
       : "memory");
 }
+// smem -> global tensor store (bulk async group); OOB parts of the box are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA store) after the following barrier
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// packed fp32 pair add (FADD2)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b), z;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(x), "l"(y));
+  return *reinterpret_cast<float2*>(&z);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
@@ -487,6 +512,111 @@ __device__ __forceinline__ void epi_window_lite(const EpiLite& e, uint32_t tmem_
     cur = n1;
     n1 = n2;
     n2 = next(n2);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// staged epilogue of the persistent kernel
+//
+// Direct 16-byte-per-lane global accesses at a row pitch of Cout_p * 2 bytes touch one L1 line per lane
+// (~6x the wavefronts of a coalesced access) and those wavefronts compete with the tensor core's operand
+// reads for the same shared-memory / L1 data path: with the stores enabled the MMA phase of a
+// 48-channel window stretches from 3750 to 6000 SM cycles (profiles/r01_v3b_epilogue_ablation.log).
+// Here the residual window arrives by TMA in a staging buffer laid out [block][pixel][cb channels], every
+// thread converts its 16-column items IN PLACE (read residual, write output at the same address) and
+// the buffer leaves by one TMA tensor store per block, which also clips rows beyond the image / batch.
+// ---------------------------------------------------------------------------
+struct EpiStage {
+  uint32_t base;       // shared-space address of this window's staging buffer
+  uint32_t bias_s;
+  uint32_t blk_bytes;  // bytes of one channel block (rows_stage * cb * 2, 1024-aligned)
+  int cb;              // channels per block: 64 (128-byte rows, SWIZZLE_128B) or 48 (96-byte rows, no swizzle)
+  int has_res, relu, dbg;
+};
+
+struct StageRow {
+  bool valid;          // run position is an output pixel of this window
+  uint32_t srow;       // its row in the staging buffer
+};
+
+template <int kParts, typename RowFn>
+__device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tmem_lane_base, int T, int n_tile,
+                                                  int part, RowFn row_of) {
+  const int per_tile = n_tile >> 4;
+  const uint32_t pitch = (uint32_t)e.cb * 2u;
+  int t = -1, g = part - kParts + per_tile, t_row = -1;
+  StageRow r{false, 0};
+  auto step = [&]() {
+    g += kParts;
+    while (g >= per_tile) {
+      g -= per_tile;
+      ++t;
+    }
+  };
+  step();
+  // one item: accumulators (already loaded) + bias [+ residual from the staging buffer] -> fp16 in place
+  auto item = [&](const uint32_t (&v)[16], const StageRow& sr, int cg) {
+    if (!sr.valid || (e.dbg & 256)) return;
+    const int col = 16 * cg;
+    const int blk = e.cb == 64 ? (col >> 6) : col / 48;
+    const uint32_t ch = (uint32_t)(col - blk * e.cb) >> 3;                    // first 16-byte chunk (even)
+    const uint32_t rowb = e.base + (uint32_t)blk * e.blk_bytes + sr.srow * pitch;
+    const uint32_t sw = e.cb == 64 ? (sr.srow & 7u) : 0u;
+    const uint32_t a0 = rowb + ((ch ^ sw) << 4), a1 = rowb + (((ch + 1u) ^ sw) << 4);
+    float2 f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bq = lds_f4(e.bias_s + (uint32_t)(col + 4 * j) * 4u);
+      f[2 * j] = add2(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(bq.x, bq.y));
+      f[2 * j + 1] =
+          add2(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(bq.z, bq.w));
+    }
+    if (e.has_res) {
+      uint4 q[2];
+      q[0] = lds_u4(a0);
+      q[1] = lds_u4(a1);
+      const __half2* r2 = reinterpret_cast<const __half2*>(q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = add2(f[j], __half22float2(r2[j]));
+    }
+    uint4 o[2];
+    __half2* o2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o2[j] = __float22half2_rn(f[j]);
+    if (e.relu) {
+      const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o2[j] = __hmax2(o2[j], z);     // relu(round(x)) == round(relu(x))
+    }
+    sts_u4(a0, o[0]);
+    sts_u4(a1, o[1]);
+  };
+  auto row_for = [&](int tt) {
+    if (tt != t_row) {
+      r = row_of(tt);
+      t_row = tt;
+    }
+  };
+  // software pipeline over this warp's items with two register buffers: the TMEM load of the next item
+  // is in flight while the current one is converted
+  uint32_t vA[16], vB[16];
+  if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vA);
+#pragma unroll 1
+  while (t < T) {
+    int ct = t, cg = g;
+    step();
+    tmem_ld_wait_dep(vA);
+    if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vB);
+    row_for(ct);
+    item(vA, r, cg);
+    if (t >= T) break;
+    ct = t;
+    cg = g;
+    step();
+    tmem_ld_wait_dep(vB);
+    if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vA);
+    row_for(ct);
+    item(vB, r, cg);
   }
 }
 
@@ -858,11 +988,17 @@ struct PersistParams {
   RunParams r;          // geometry / operands as in v2 (r.b_stages = ring depth when streaming)
   int n_windows;        // win_per_img * ceil(B / TBW)
   int b_resident;       // 1: all taps*kchunks weight tiles live in smem for the CTA's lifetime
+  // staged epilogue (0 = direct global accesses)
+  int n_stage;          // staging buffers: 0, 1 or 2
+  int cb, nblk;         // channels per staging block (64 / 48), blocks per n_tile
+  int rows_stage;       // TBW * THW * W pixels per window
+  uint32_t blk_bytes;   // bytes of one block, 1024-aligned
 };
 
 template <bool kHead>   // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps)
 __global__ void __launch_bounds__(kHead ? kPersistThreadsHead : kPersistThreads, 1)
 conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
                     const PersistParams pp) {
   const RunParams& p = pp.r;
   extern __shared__ uint8_t smem_raw[];
@@ -874,15 +1010,19 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int b_slots = pp.b_resident ? w_tiles : p.b_stages;
   uint8_t* smem_a = smem;                                   // 2 slots
   uint8_t* smem_b = smem + 2 * (size_t)a_slot;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)b_slots * b_stage);
+  uint8_t* smem_stage = smem_b + (size_t)b_slots * b_stage;                  // n_stage x nblk x blk_bytes (1024-aligned)
+  const uint32_t stage_bytes = (uint32_t)pp.nblk * pp.blk_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + (size_t)pp.n_stage * stage_bytes);
   uint64_t* a_empty = a_full + 2;
   uint64_t* acc_full = a_empty + 2;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
   uint64_t* b_full = w_full + 1;
   uint64_t* b_empty = b_full + kMaxBStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // offset (9 + 12) * 8 + 8 = 176: 16-byte aligned
+  uint64_t* stage_full = b_empty + kMaxBStages;     // [2] residual landed / buffer free for the epilogue
+  uint64_t* staged = stage_full + 2;                // [2] epilogue finished writing the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // offset (9 + 12 + 4) * 8 + 8 = 208: 16-byte aligned
   uint4* s_issue = reinterpret_cast<uint4*>(s_bias + p.n_tile);   // [n_mma] issue table (n_tile % 16 == 0)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -918,11 +1058,17 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (pp.n_stage) {
+      tma_prefetch_desc(&map_res);
+      tma_prefetch_desc(&map_out);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128 * kParts);
+      mbar_init(&acc_empty[i], 4 * kParts);        // one arrival per epilogue warp
+      mbar_init(&stage_full[i], 1);
+      mbar_init(&staged[i], 4 * kParts);
     }
     mbar_init(w_full, 1);
     for (int i = 0; i < kMaxBStages; ++i) {
@@ -950,7 +1096,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int c = 0; c < p.kchunks; ++c)
           tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
                       win * p.THW - p.halo, bg * p.TBW);
-        if (p.res && !(p.dbg & 128)) {
+        if (p.res && !pp.n_stage && !(p.dbg & 128)) {
           // the residual rows of this window are one contiguous NHWC range: pull them towards L2 now,
           // ~2 windows before the epilogue reads them
           const int b0 = bg * p.TBW, h0 = win * p.THW;
@@ -1043,6 +1189,48 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
     }
+  } else if (warp == 3) {
+    // ===================== staging DMA (residual in, output out) =====================
+    if (pp.n_stage && elect_one()) {
+      const int S = pp.n_stage;
+      const bool has_res = p.res != nullptr && !(p.dbg & 2);
+      const int my_windows = ((int)pp.n_windows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      auto coords = [&](int jj, int& h0, int& b0) {
+        const int w = blockIdx.x + jj * gridDim.x;
+        const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
+        h0 = win * p.THW;
+        b0 = bg * p.TBW;
+      };
+      auto fill = [&](int jj) {                 // buffer jj % S is free: fetch window jj's residual (or just release it)
+        const int sb = jj % S;
+        if (has_res) {
+          int h0, b0;
+          coords(jj, h0, b0);
+          mbar_expect_tx(&stage_full[sb], (uint32_t)pp.nblk * (uint32_t)(pp.rows_stage * pp.cb * 2));
+          for (int k = 0; k < pp.nblk; ++k)
+            tma_load_4d(smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, &map_res, &stage_full[sb],
+                        n0 + k * pp.cb, 0, h0, b0);
+        } else {
+          mbar_arrive(&stage_full[sb]);
+        }
+      };
+      for (int jj = 0; jj < S && jj < my_windows; ++jj) fill(jj);
+      for (int jj = 0; jj < my_windows; ++jj) {
+        const int sb = jj % S;
+        mbar_wait(&staged[sb], (uint32_t)((jj / S) & 1));
+        if (!(p.dbg & 1)) {
+          int h0, b0;
+          coords(jj, h0, b0);
+          for (int k = 0; k < pp.nblk; ++k)
+            tma_store_4d(&map_out, smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, n0 + k * pp.cb, 0, h0,
+                         b0);
+          bulk_commit();
+          bulk_wait_read0();                      // smem of this buffer has been read: it may be refilled
+        }
+        if (jj + S < my_windows) fill(jj + S);
+      }
+      bulk_wait0();                               // all output writes complete before the CTA exits
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps on every window) =====================
     // Two warps per TMEM lane quarter split each window's (tile, column group) items between them.
@@ -1064,7 +1252,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(&acc_full[slot], ph);
         tc_fence_after();
         tc_fence_before();
-        mbar_arrive(&acc_empty[slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
         continue;
       }
       auto row_of = [&](int t) {
@@ -1089,11 +1278,37 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         e.ts = ts;
         epi_run(e, tbase, p.T, p.n_tile, n0, &acc_full[slot], row_of, ph, half, 2);
       } else {
-        epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts);
+        if (pp.n_stage) {
+          const int sb = j % pp.n_stage;
+          const EpiStage es{smem_u32(smem_stage) + (uint32_t)sb * stage_bytes, smem_u32(s_bias), pp.blk_bytes, pp.cb,
+                            p.res != nullptr && !(p.dbg & 2), p.relu, p.dbg};
+          mbar_wait(&stage_full[sb], (uint32_t)((j / pp.n_stage) & 1));
+          mbar_wait(&acc_full[slot], ph);
+          tc_fence_after();
+          if (ts && (threadIdx.x & 127) == 64) ts[4] = gtime();
+          epi_window_staged<kParts>(es, tbase, p.T, p.n_tile, half, [&](int t) {
+            const int pos = t * 128 + row + p.lead;
+            const int bi = p.TBW == 1 ? 0 : (int)(((float)pos + 0.5f) * p.inv_img);
+            const int rem = pos - bi * p.img_rows;
+            const int hp = (int)(((float)rem + 0.5f) * p.inv_wp);
+            const int wp = rem - hp * p.Wp;
+            StageRow sr;
+            sr.valid = pos - p.lead < p.m_run && bi < p.TBW && hp >= p.halo && hp < p.Hw - p.halo && wp >= p.halo &&
+                       wp < p.Wp - p.halo;
+            sr.srow = (uint32_t)(((bi * p.THW) + (hp - p.halo)) * p.W + (wp - p.halo));
+            return sr;
+          });
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&staged[sb]);
+        } else {
+          epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts);
+        }
       }
       if (p.ts && j < 8 && lane == 0) atomicMax(p.ts + ((size_t)blockIdx.x * 8 + j) * 8 + 5, gtime());   // last warp done
       tc_fence_before();
-      mbar_arrive(&acc_empty[slot]);      // all epilogue threads release the accumulator set to the MMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);      // one arrival per warp releases the accumulator set
     }
   }
   tc_fence_before();
@@ -1136,12 +1351,15 @@ struct TcConvPlan {
   bool use_run = false;
   bool use_persist = false;   // v3: persistent one-CTA-per-SM variant of the window-run kernel
   int b_resident = 0;
+  int n_stage = 0, cb = 0, nblk = 0, rows_stage = 0;   // staged (TMA) epilogue of the persistent kernel
+  uint32_t blk_bytes = 0;
   int halo = 0, Wp = 0, Hw = 0, THW = 0, TBW = 1, T = 1, rows_alloc = 0, b_stages = 2;
   float run_eff = 0.f;
   __half* d_w = nullptr;      // [Cout_p][taps*Cin_p]
   size_t w_bytes = 0;
   CUtensorMap map_b;
   std::map<std::pair<const void*, int>, CUtensorMap> a_maps;  // (input pointer, batch) -> map
+  std::map<std::pair<const void*, int>, CUtensorMap> io_maps; // (residual / output pointer, batch) -> staging map
   std::mutex mu;
 };
 
@@ -1291,6 +1509,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const int w_tiles = a.ksize * a.ksize * p->kchunks;
       const size_t smem_cap = 225 * 1024;
       double best = 1e30;
+      const int force_T = getenv("EGN_TC_V3_T") ? atoi(getenv("EGN_TC_V3_T")) : 0;
+      const int max_stage = getenv("EGN_TC_STAGE") ? atoi(getenv("EGN_TC_STAGE")) : 2;
       const int base_tiles = p->n_tiles;
       // Splitting the output channels over blockIdx.y (split = 2) lets each half keep its weights resident
       // when the whole matrix does not fit (96 channels: 2 x 108 KB); both halves then load the window.
@@ -1339,29 +1559,45 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const int windows = multi ? 1 : ceil_div(a.H, THW);
             const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
                                      : (double)a.H * a.W / ((double)windows * T * 128);
+            if (force_T && T != force_T) continue;
+            // staging buffers of the TMA epilogue: [block][TBW*THW*W pixels][cb channels]
+            const int cb = n_tile % 64 == 0 ? 64 : (n_tile % 48 == 0 ? 48 : 0);
+            const int rows_stage = TBW * THW * a.W;
+            const size_t blk_bytes = cb ? (((size_t)rows_stage * cb * 2 + 1023) & ~(size_t)1023) : 0;
+            const int nblk = cb ? n_tile / cb : 0;
             // cost model in SM cycles at the nominal batch 256 (measured constants, profiles/r01_*):
-            //   tcgen05.mma 128 x N x 16: 40 cycles up to N=32, 44 @48, 48 @64, 56 @96, 64 @128, 118 @192, 150 @256
-            //   compact epilogue: ~250 cycles per 16-column item and lane quarter (4 warps per quarter)
+            //   tcgen05.mma 128 x N x 16: 40 cycles up to N=32, 44 @48, 48 @64, 56 @96, 64 @128, 118 @192, 150 @256;
+            //     x1.5 while a direct (uncoalesced) epilogue competes for the smem / L1 data path
+            //   epilogue: ~250 (direct) / ~100 (staged) cycles per 16-column item and lane quarter
+            //   a single staging buffer exposes store drain + residual load (~4000 cycles measured) once per window
             //   streamed weights: ~2400 cycles per ring tile (measured on 48- and 96-channel layers; the ring does
             //   not hide the L2 latency behind the window loads queued on the same TMA unit) -> last resort
             const int n_win = windows * ceil_div(256, TBW);
             const double mma_cyc = n_tile <= 32 ? 40.0 : n_tile <= 64 ? 40.0 + (n_tile - 32) * 0.25
                                  : n_tile <= 128 ? 48.0 + (n_tile - 64) * 0.25 : 64.0 + (n_tile - 128) * 0.68;
             const double t_mma = (double)a.ksize * a.ksize * ((a.Cin_p + 15) / 16) * T * mma_cyc;
-            const double t_epi = (double)T * (n_tile / 16) * 250.0;
             const double t_w = resident ? 0.0 : (double)w_tiles * 2400.0;
             const double t_a = (double)p->kchunks * rows_win * 128 / 48.0;      // window load, ~48 B/cycle/SM
-            const double est = ceil_div(n_win * n_tiles, 148) * (std::max(std::max(t_mma, t_epi), std::max(t_w, t_a)) + 300.0);
-            if (est < best) {
-              best = est;
-              p->use_persist = true;
-              p->b_resident = resident;
-              p->n_tiles = n_tiles;
-              p->n_tile = n_tile;
-              p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
-              p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
-              p->smem_bytes = smem;
-              p->tmem_cols = pow2_cols(2 * T * n_tile);
+            for (int S = max_stage; S >= 0; --S) {
+              if (S && !cb) continue;
+              const size_t smem_s = smem + (size_t)S * nblk * blk_bytes;
+              if (smem_s > smem_cap) continue;
+              const double t_epi = (double)T * (n_tile / 16) * (S ? 100.0 : 250.0);
+              const double t_win = std::max(std::max(S ? t_mma : 1.5 * t_mma, t_epi), std::max(t_w, t_a)) +
+                                   (S == 1 ? 4000.0 : 0.0) + 300.0;
+              const double est = ceil_div(n_win * n_tiles, 148) * t_win;
+              if (est < best) {
+                best = est;
+                p->use_persist = true;
+                p->b_resident = resident;
+                p->n_tiles = n_tiles;
+                p->n_tile = n_tile;
+                p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
+                p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
+                p->smem_bytes = smem_s;
+                p->tmem_cols = pow2_cols(2 * T * n_tile);
+                p->n_stage = S; p->cb = cb; p->nblk = nblk; p->rows_stage = rows_stage; p->blk_bytes = (uint32_t)blk_bytes;
+              }
             }
           }
         }
@@ -1373,9 +1609,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
       if (p->use_persist) p->use_run = false;
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
-        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u\n",
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
                 a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->T, p->THW, p->TBW, p->run_eff,
-                p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->b_resident, p->b_stages, p->tmem_cols);
+                p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->b_resident, p->b_stages, p->tmem_cols, p->n_stage, p->nblk,
+                p->blk_bytes, p->cb);
     }
   }
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
@@ -1418,6 +1655,25 @@ void tc_conv_plan_destroy(TcConvPlan* p) {
 }
 
 size_t tc_conv_plan_weight_bytes(const TcConvPlan* p) { return p ? p->w_bytes : 0; }
+
+// [B][OH][OW][Cout_p] tensor seen through the staging box of the persistent kernel's TMA epilogue
+static int make_io_map(TcConvPlan* p, const void* ptr, int B, CUtensorMap* m) {
+  EncodeTiledFn enc = get_encode_fn();
+  const cuuint64_t C = p->Cout_p, W = p->OW, H = p->OH;
+  const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)p->cb, (cuuint32_t)p->OW, (cuuint32_t)p->THW, (cuuint32_t)p->TBW};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, p->cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(staging %dx%dx%d, B=%d, box %dx%dx%dx%d) failed with %d", p->OH, p->OW, p->Cout_p, B,
+              p->cb, p->OW, p->THW, p->TBW, (int)r);
+    return EGN_ERR_CUDA;
+  }
+  return EGN_OK;
+}
 
 static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   EncodeTiledFn enc = get_encode_fn();
@@ -1518,6 +1774,26 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     }
     pp.n_windows = rp.win_per_img * ceil_div(a.B, p->TBW);
     pp.b_resident = p->b_resident;
+    const bool head = a.heatmap || a.coord_maps || getenv("EGN_TC_EPI_GENERIC");
+    CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
+    if (p->n_stage && !head) {
+      pp.n_stage = p->n_stage; pp.cb = p->cb; pp.nblk = p->nblk; pp.rows_stage = p->rows_stage; pp.blk_bytes = p->blk_bytes;
+      std::lock_guard<std::mutex> lock(p->mu);
+      for (int which = 0; which < 2; ++which) {
+        const void* ptr = which ? a.out : a.res;
+        if (!ptr) continue;
+        auto key = std::make_pair(ptr, a.B);
+        auto it = p->io_maps.find(key);
+        if (it == p->io_maps.end()) {
+          if (p->io_maps.size() > 64) p->io_maps.clear();
+          CUtensorMap m;
+          if (int rc = make_io_map(p, ptr, a.B, &m)) return rc;
+          it = p->io_maps.emplace(key, m).first;
+        }
+        (which ? m_out : m_res) = it->second;
+      }
+      if (!a.res) m_res = m_out;
+    }
     static bool attr_set = false;
     if (!attr_set) {
       EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1531,10 +1807,10 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
-    if (a.heatmap || a.coord_maps || getenv("EGN_TC_EPI_GENERIC"))
-      conv_persist_kernel<true><<<grid, kPersistThreadsHead, p->smem_bytes, st>>>(ma, p->map_b, pp);
+    if (head)
+      conv_persist_kernel<true><<<grid, kPersistThreadsHead, p->smem_bytes, st>>>(ma, p->map_b, m_res, m_out, pp);
     else
-      conv_persist_kernel<false><<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, pp);
+      conv_persist_kernel<false><<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, m_res, m_out, pp);
     EGN_LAUNCH_CHECK("conv_persist_kernel");
     if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
       cudaStreamSynchronize(st);

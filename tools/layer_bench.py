@@ -17,7 +17,7 @@ def run_child(args):
     from egonet_b200 import _native as N
     B = args.batch
     out_rows = []
-    for (Cin, Cout, H, W, k, st, has_res) in SHAPES:
+    for (Cin, Cout, H, W, k, st, has_res) in SHAPES[:args.shapes]:
         g = torch.Generator().manual_seed(1)
         Cip, Cop = (Cin + 15) // 16 * 16, (Cout + 15) // 16 * 16
         x = torch.randn((B, H, W, Cip), generator=g).to(torch.float16).cuda()
@@ -42,6 +42,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--iters', type=int, default=30)
     ap.add_argument('--child', action='store_true')
+    ap.add_argument('--shapes', type=int, default=len(SHAPES), help='only the first N shapes')
     args = ap.parse_args()
     if args.child:
         return run_child(args)
