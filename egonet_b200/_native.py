@@ -30,6 +30,11 @@ class OpInfo(ctypes.Structure):
                 ('macs', c_int64), ('act_bytes', c_int64), ('weight_bytes', c_int64), ('name', ctypes.c_char * 96)]
 
 
+class Image(ctypes.Structure):
+    """egn_image: one decoded 8-bit RGB image resident in device memory."""
+    _fields_ = [('data', c_void_p), ('height', c_int32), ('width', c_int32), ('pitch', c_int32), ('channels', c_int32)]
+
+
 class HRNetCfg(ctypes.Structure):
     _fields_ = [
         ('in_channels', c_int), ('input_w', c_int), ('input_h', c_int),
@@ -83,6 +88,8 @@ SIGNATURES = {
     'egn_debug_umma_probe': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     'egn_mse_hm_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_crop_instances': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
 

@@ -139,6 +139,69 @@ def local_to_screen(coords, centers, scales, resolution, rots=None):
     return out
 
 
+def normalize_params(pth_trans):
+    """(mean, std) of the ``Compose([ToTensor(), Normalize(mean, std)])`` the dataset hands to the
+    model [car_instance.py:522-531]; (0, 1) per channel when the pipeline has no Normalize.
+    Anything else has no device implementation and raises (there is no host fallback)."""
+    mean, std = [0., 0., 0.], [1., 1., 1.]
+    steps = getattr(pth_trans, 'transforms', None)
+    if steps is None:
+        raise NotImplementedError('pth_trans must be a Compose of ToTensor / Normalize (got %r)' % (pth_trans,))
+    saw_tensor = False
+    for t in steps:
+        name = type(t).__name__
+        if name == 'ToTensor':
+            saw_tensor = True
+        elif name == 'Normalize':
+            mean, std = [float(v) for v in t.mean], [float(v) for v in t.std]
+        else:
+            raise NotImplementedError('transform %s has no device implementation' % name)
+    if not saw_tensor:
+        raise NotImplementedError('pth_trans without ToTensor has no device implementation')
+    return mean, std
+
+
+def crop_instances_device(images, image_of_crop, centers, scales, resolution, mean=None, std=None,
+                          return_u8=False):
+    """Every crop of a batch in one launch: the device form of ``EgoNet.crop_single_instance``
+    [egonet.py:68-95] = ``get_affine_transform`` [img_proc.py:26-64] + ``cv2.warpAffine(INTER_LINEAR)``
+    [egonet.py:85-89] + ``ToTensor``/``Normalize`` [car_instance.py:522-531].
+
+    images: list of CUDA uint8 [H,W,3] RGB tensors (rows may be strided); image_of_crop: [N] ints;
+    centers/scales: [N,2] fp64 (``modify_bbox`` output); resolution = (width, height).
+    Returns CUDA fp32 [N,3,height,width] (and the uint8 [N,height,width,3] warp result with ``return_u8``)."""
+    import ctypes
+    if not images or not all(torch.is_tensor(i) and i.is_cuda for i in images):
+        raise RuntimeError('native crop front-end needs CUDA uint8 images (there is no CPU path)')
+    dev = images[0].device
+    width, height = int(resolution[0]), int(resolution[1])
+    table = (N.Image * len(images))()
+    for k, im in enumerate(images):
+        if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or im.stride(2) != 1 or im.stride(1) != 3:
+            raise ValueError('image %d must be uint8 [H,W,3] with packed pixels' % k)
+        table[k] = N.Image(im.data_ptr(), im.shape[0], im.shape[1], im.stride(0), 3)
+    table_dev = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+    ce = torch.as_tensor(np.asarray(centers, dtype=np.float64) if not torch.is_tensor(centers) else centers,
+                         dtype=torch.float64).to(dev).contiguous().view(-1, 2)
+    sc = torch.as_tensor(np.asarray(scales, dtype=np.float64) if not torch.is_tensor(scales) else scales,
+                         dtype=torch.float64).to(dev).contiguous().view(-1, 2)
+    n = ce.shape[0]
+    idx_host = np.asarray(image_of_crop, dtype=np.int32).reshape(-1)
+    if len(idx_host) != n or sc.shape[0] != n:
+        raise ValueError('centers / scales / image_of_crop disagree on the number of crops')
+    if n and (idx_host.min() < 0 or idx_host.max() >= len(images)):
+        raise ValueError('image_of_crop out of range')
+    idx = torch.as_tensor(idx_host).to(dev)
+    out = torch.empty((n, 3, height, width), device=dev, dtype=torch.float32)
+    u8 = torch.empty((n, height, width, 3), device=dev, dtype=torch.uint8) if return_u8 else None
+    m3 = (ctypes.c_float * 3)(*(mean if mean is not None else [0., 0., 0.]))
+    s3 = (ctypes.c_float * 3)(*(std if std is not None else [1., 1., 1.]))
+    with torch.cuda.device(dev):
+        N.check(N.lib().egn_crop_instances(N.ptr(table_dev), len(images), N.ptr(idx), N.ptr(ce), N.ptr(sc), n,
+                                           width, height, m3, s3, N.ptr(out), N.ptr(u8), N.current_stream()))
+    return (out, u8) if return_u8 else out
+
+
 def to_npy(tensor):
     """[img_proc.py:722-728]"""
     return tensor if isinstance(tensor, np.ndarray) else tensor.data.cpu().numpy()

@@ -13,8 +13,9 @@ loops of the reference are replaced by batched device calls:
   forward_crops      the whole path for already-cropped tensors with a single
                      D2H copy of the [N,7] pose records (what bench.py times)
 
-Image reading / cv2 warping (``crop_instances``) stays on the host as upstream
-(SURVEY.md section 8f ranks a device crop front-end as the next row).
+  crop_instances     decoded uint8 images are uploaded once; one launch produces every
+                     normalised crop (cv2.warpAffine's fixed-point bilinear + ToTensor +
+                     Normalize, bit-identical).  Image decoding (cv2.imread) stays host code.
 """
 import math
 from os.path import join as pjoin
@@ -68,21 +69,25 @@ class EgoNet(nn.Module):
     def _device(self):
         return torch.device('cuda', torch.cuda.current_device())
 
-    # ------------------------------------------------------------------ crops (host, as upstream)
+    # ------------------------------------------------------------------ crops (device front-end)
     def crop_single_instance(self, img, bbox, resolution, pth_trans=None, xy_dict=None):
-        """[egonet.py:68-95]"""
-        import cv2
+        """[egonet.py:68-95] one box of one decoded image through the device crop kernel.
+        Returns what upstream returns: the uint8 [h,w,3] warp result (numpy) without ``pth_trans``,
+        else the normalised fp32 [3,h,w] tensor (left on the device)."""
+        if xy_dict is not None and xy_dict['flag']:
+            raise NotImplementedError('add_xy input channels need generate_xy_map (out of the hot path)')
         bbox = lip.to_npy(bbox)
         width, height = resolution
         ret = lip.modify_bbox(bbox, height / width)
-        trans = lip.get_affine_transform(ret['c'], ret['s'], 0., (height, width))
-        instance = cv2.warpAffine(img, trans, (int(width), int(height)), flags=cv2.INTER_LINEAR)
-        if xy_dict is not None and xy_dict['flag']:
-            raise NotImplementedError('add_xy input channels need generate_xy_map (out of the hot path)')
-        return instance if pth_trans is None else pth_trans(instance)
+        image = img if torch.is_tensor(img) else torch.from_numpy(np.ascontiguousarray(img))
+        image = image.to(self._device())
+        mean, std = (None, None) if pth_trans is None else lip.normalize_params(pth_trans)
+        out, u8 = lip.crop_instances_device([image], [0], ret['c'][None], ret['s'][None], resolution,
+                                            mean, std, return_u8=True)
+        return u8[0].cpu().numpy() if pth_trans is None else out[0]
 
     def load_cv2(self, path, rgb=True):
-        """[egonet.py:97-103]"""
+        """[egonet.py:97-103] image decoding stays host code (cv2.imread), as upstream."""
         import cv2
         data = cv2.imread(path, 1 | 128)
         if data is None:
@@ -90,24 +95,41 @@ class EgoNet(nn.Module):
         return cv2.cvtColor(data, cv2.COLOR_BGR2RGB) if rgb else data
 
     def crop_instances(self, annot_dict, resolution, pth_trans=None, rgb=True, xy_dict=None):
-        """[egonet.py:105-155]"""
-        crops, records = [], []
+        """[egonet.py:105-155] every box of every image of the batch: each decoded image is uploaded
+        once (uint8) and ONE launch writes all normalised crops, instead of a cv2.warpAffine +
+        ToTensor + Normalize per box on the host.  ``annot_dict['images']`` (decoded uint8 RGB arrays
+        or CUDA tensors, one per path) skips the file read.  Returns (CUDA fp32 [N,3,h,w], records)."""
+        if xy_dict is not None and xy_dict['flag']:
+            raise NotImplementedError('add_xy input channels need generate_xy_map (out of the hot path)')
+        mean, std = lip.normalize_params(pth_trans)
+        dev = self._device()
+        images, image_of_crop, centers, scales, records = [], [], [], [], []
         target_ar = resolution[1] / resolution[0]
         for img_idx, path in enumerate(annot_dict['path']):
-            image = self.load_cv2(path, rgb)
             boxes = annot_dict['boxes'][img_idx]
             n = len(boxes)
+            if n == 0:
+                continue
+            image = annot_dict['images'][img_idx] if 'images' in annot_dict else self.load_cv2(path, rgb)
+            if not torch.is_tensor(image):
+                image = torch.from_numpy(np.ascontiguousarray(image))
+            images.append(image.to(dev, non_blocking=True))
             labels = annot_dict['labels'][img_idx] if 'labels' in annot_dict else -np.ones(n, dtype=np.int64)
             scores = annot_dict['scores'][img_idx] if 'scores' in annot_dict else -np.ones(n)
             for k, bbox in enumerate(boxes):
-                crop = self.crop_single_instance(image, bbox, resolution, pth_trans=pth_trans, xy_dict=xy_dict)
                 bbox = lip.to_npy(bbox)
                 ret = lip.modify_bbox(bbox, target_ar)
-                crops.append(torch.unsqueeze(crop, dim=0))
+                image_of_crop.append(len(images) - 1)
+                centers.append(ret['c'])
+                scales.append(ret['s'])
                 records.append({'path': path, 'center': ret['c'], 'scale': ret['s'], 'bbox': bbox,
                                 'bbox_resize': ret['bbox'], 'rotation': 0., 'label': labels[k],
                                 'score': scores[k]})
-        return torch.cat(crops, dim=0), records
+        if not records:
+            return torch.empty((0, 3, int(resolution[1]), int(resolution[0])), device=dev), records
+        crops = lip.crop_instances_device(images, image_of_crop, np.array(centers), np.array(scales),
+                                          resolution, mean, std)
+        return crops, records
 
     # ------------------------------------------------------------------ HC + affine
     def new_img_dict(self):

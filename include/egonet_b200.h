@@ -253,6 +253,34 @@ EGN_API int egn_pose_solve(const double* kpts_3d, int N, int P, const double* kp
                    void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Crop front-end: decoded image(s) in HBM -> network input */
+/* replaces, per box, EgoNet.crop_single_instance egonet.py:68-95 as called    */
+/* by crop_instances egonet.py:105-155:                                        */
+/*   get_affine_transform(c, s, 0, (h, w)) img_proc.py:26-64,                  */
+/*   cv2.warpAffine(img, trans, (w, h), flags=INTER_LINEAR) egonet.py:85-89    */
+/*     (OpenCV's 8-bit fixed-point bilinear path, BORDER_CONSTANT 0),          */
+/*   transforms.ToTensor + Normalize(mean, std) car_instance.py:522-531.       */
+/* center/scale come from modify_bbox (img_proc.py:453-459), as for            */
+/* egn_local_to_screen; only scale[:,0] is used (img_proc.py:41-42).           */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  const uint8_t* data; /* DEVICE pointer, interleaved 8-bit RGB rows (cv2 HWC layout) */
+  int32_t height, width;
+  int32_t pitch;       /* bytes between rows (>= 3*width)                             */
+  int32_t channels;    /* must be 3                                                   */
+} egn_image;
+
+/* images_dev: DEVICE array of n_images descriptors; image_of_crop_dev: device int32 [N]
+ * (index into images_dev) or NULL (every crop comes from image 0).
+ * center_dev/scale_dev: device fp64 [N,2].  mean3_host/std3_host: HOST float[3] or NULL (0 / 1).
+ * out_nchw: device fp32 [N,3,res_h,res_w] = Normalize(ToTensor(warpAffine(...))).
+ * out_u8 : device uint8 [N,res_h,res_w,3], the warpAffine result itself, or NULL. */
+EGN_API int egn_crop_instances(const egn_image* images_dev, int n_images, const int32_t* image_of_crop_dev,
+                       const double* center_dev, const double* scale_dev, int N, int res_w, int res_h,
+                       const float* mean3_host, const float* std3_host, float* out_nchw,
+                       uint8_t* out_u8, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Heat-map MSE loss (training config only; loss end of SURVEY.md 8a row a12)   */
 /* replaces JointsMSELoss.forward libs/loss/function.py:28-46 and              */
 /* JointsCompositeLoss.calc_hm_loss libs/loss/function.py:95-111               */

@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 
 from _refimport import import_reference  # noqa: E402
-from oracle import configs, egonet_ref, hrnet_ref, lifter_ref  # noqa: E402
+from oracle import configs, crop_ref, egonet_ref, hrnet_ref, lifter_ref  # noqa: E402
 
 
 def rng(seed):
@@ -250,6 +250,48 @@ def golden_loss(ref):
     out['calc_hm_loss'] = comp.calc_hm_loss(torch.tensor(pred), torch.tensor(gt)).numpy()
     save('loss.npz', **out)
 
+# mean / std of cfgs['dataset']['pth_transform'] (configs/KITTI_inference:demo.yml:49-53)
+CROP_MEAN = [0.485, 0.456, 0.406]
+CROP_STD = [0.229, 0.224, 0.225]
+# x1, y1, x2, y2 on a 375 x 1242 image: ordinary boxes, up-/down-sampling extremes, boxes cut by each
+# border, one entirely outside (all-zero crop), one with integer-aligned geometry
+CROP_BOXES = np.array([
+    [600.3, 150.2, 760.9, 260.7], [35.5, 170.0, 130.25, 240.5], [1100.0, 120.0, 1240.0, 330.0],
+    [400.0, 175.0, 424.0, 193.0], [100.0, 10.0, 1100.0, 370.0], [-60.0, 200.0, 90.0, 300.0],
+    [500.0, -40.0, 700.0, 80.0], [1180.0, 300.0, 1300.0, 420.0], [1400.0, 100.0, 1500.0, 200.0],
+    [512.0, 128.0, 768.0, 256.0], [611.7, 180.3, 640.2, 201.9], [300.123, 90.456, 555.789, 310.012]])
+
+
+def golden_crop(ref):
+    """crop_single_instance of the reference (cv2.warpAffine + torchvision ToTensor/Normalize) on a seeded
+    synthetic KITTI-sized image; the image itself is regenerated from its seed by the tests."""
+    import hashlib
+    from torchvision import transforms
+    ego_cls = ref['egonet'].EgoNet
+    pth_trans = transforms.Compose([transforms.ToTensor(),
+                                    transforms.Normalize(mean=CROP_MEAN, std=CROP_STD)])   # car_instance.py:522-531
+    img = crop_ref.synth_image(375, 1242, 21)
+    arrays = {'image_seed': 21, 'image_shape': np.array(img.shape), 'mean': np.array(CROP_MEAN), 'std': np.array(CROP_STD),
+              'image_sha1': np.frombuffer(hashlib.sha1(img.tobytes()).digest(), np.uint8), 'boxes': CROP_BOXES}
+    # full uint8 crops are stored for a few boxes only (they do not compress); every box has its SHA-1
+    for tag, res, full in (('sq', (256, 256), (0, 3, 5, 9)), ('ped', (192, 256), (0, 7))):   # res = (width, height)
+        u8, sha, sub, sums, cs, ss = [], [], [], [], [], []
+        for i, b in enumerate(CROP_BOXES):
+            raw = ego_cls.crop_single_instance(None, img, b, res, pth_trans=None, xy_dict=None)
+            ten = ego_cls.crop_single_instance(None, img, b, res, pth_trans=pth_trans, xy_dict=None)
+            assert raw.dtype == np.uint8 and raw.shape == (res[1], res[0], 3) and ten.dtype == torch.float32
+            ret = ref['img_proc'].modify_bbox(b, res[1] / res[0])
+            if i in full:
+                u8.append(raw)
+            sha.append(np.frombuffer(hashlib.sha1(np.ascontiguousarray(raw).tobytes()).digest(), np.uint8))
+            sub.append(ten.numpy()[:, ::4, ::4])
+            sums.append(ten.double().sum().item())
+            cs.append(ret['c']); ss.append(ret['s'])
+        arrays.update({tag + '_u8': np.array(u8), tag + '_u8_index': np.array(full), tag + '_u8_sha1': np.array(sha),
+                       tag + '_norm_sub': np.array(sub), tag + '_norm_sum': np.array(sums),
+                       tag + '_centers': np.array(cs), tag + '_scales': np.array(ss)})
+    save('crop.npz', **arrays)
+
 
 def main():
     ref = import_reference()
@@ -264,6 +306,7 @@ def main():
     golden_pose(ref)
     golden_pipeline(ref)
     golden_loss(ref)
+    golden_crop(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,
