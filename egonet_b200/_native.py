@@ -90,6 +90,8 @@ SIGNATURES = {
     'egn_mse_hm_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_crop_instances': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                    POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_void_p]),
+    'egn_pnp_refine': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
 

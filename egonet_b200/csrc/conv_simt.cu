@@ -198,73 +198,100 @@ int launch_conv_simt(Dtype dt, const ConvArgs& a, const float* w_packed, cudaStr
 // ---------------------------------------------------------------------------
 // stem conv1: fp32 NCHW input, 3x3 s2 p1, Cin in {3,5} -> 64 channels NHWC
 // ---------------------------------------------------------------------------
-constexpr int ST = 16;              // 16x16 output pixels per CTA
-constexpr int SP = 2 * ST + 1;      // input patch edge
+// One CTA = an 8 x 32 tile of output pixels; a warp owns one output row of the tile.  Lane (qc, cg):
+// four pixels ox = qc + 8i (i = 0..3) x sixteen channels {16q + 4cg + j}: 64 accumulators per thread,
+// so each weight float4 read from shared memory feeds 16 FMAs and each input value 16 (LDS : FFMA = 1 : 8;
+// the previous one-pixel-per-thread mapping sat at 1 : 3 and was LDS-issue bound).  Patch reads of a warp
+// are stride-2 floats (conflict free, broadcast over cg); weight reads are 64 contiguous bytes
+// (broadcast over qc).  Every output accumulates its taps in the order c, r, s starting from 0 --
+// the same order as the reference-parity fp32 path always had, so results are unchanged bit for bit.
+constexpr int STH = 8, STW = 32;                  // output tile (rows x cols)
+constexpr int SPH = 2 * STH + 1, SPW = 2 * STW + 1;   // input patch 17 x 65
+constexpr int SPP = SPW + 1;                      // patch row pitch (floats)
+constexpr int STEM_THREADS = 256;
 constexpr int STEM_MAX_CIN = 5;
 
 template <typename T>
-__global__ void __launch_bounds__(ST * ST)
+__global__ void __launch_bounds__(STEM_THREADS, 2)
 stem_kernel(StemArgs p) {
-  extern __shared__ float sm[];
-  float* patch = sm;                                  // [Cin][SP][SP]
-  float* w = sm + p.Cin * SP * SP;                    // [9*Cin][64]
+  extern __shared__ __align__(16) float sm[];
+  float* w = sm;                                      // [9*Cin][64]
   float* bias = w + 9 * p.Cin * 64;                   // [64]
+  float* patch = bias + 64;                           // [Cin][SPH][SPP]
   const int t = threadIdx.x;
-  const int tiles_x = (p.OW + ST - 1) / ST;
+  const int tiles_x = (p.OW + STW - 1) / STW;
   const int b = blockIdx.y;
-  const int oy0 = (blockIdx.x / tiles_x) * ST, ox0 = (blockIdx.x % tiles_x) * ST;
+  const int oy0 = (blockIdx.x / tiles_x) * STH, ox0 = (blockIdx.x % tiles_x) * STW;
   const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-  for (int e = t; e < p.Cin * SP * SP; e += ST * ST) {
-    const int c = e / (SP * SP), r = (e / SP) % SP, q = e % SP;
+  for (int e = t; e < p.Cin * SPH * SPW; e += STEM_THREADS) {
+    const int c = e / (SPH * SPW), r = (e / SPW) % SPH, q = e % SPW;
     const int iy = iy0 + r, ix = ix0 + q;
     float v = 0.f;
     if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
       v = __ldg(p.x + (((int64_t)b * p.Cin + c) * p.H + iy) * p.W + ix);
-    patch[e] = v;
+    patch[(c * SPH + r) * SPP + q] = v;
   }
-  for (int e = t; e < 9 * p.Cin * 64; e += ST * ST) w[e] = __ldg(p.w + e);
+  for (int e = t; e < 9 * p.Cin * 16; e += STEM_THREADS)
+    reinterpret_cast<float4*>(w)[e] = __ldg(reinterpret_cast<const float4*>(p.w) + e);
   if (t < 64) bias[t] = __ldg(p.bias + t);
   __syncthreads();
-  const int ty = t / ST, tx = t % ST;
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy >= p.OH || ox >= p.OW) return;
-  T* out = static_cast<T*>(p.out) + (((int64_t)b * p.OH + oy) * p.OW + ox) * 64;
-#pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    float acc[16];
+  const int cg = t & 3, qc = (t >> 2) & 7, ty = t >> 5;
+  float acc[4][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    for (int c = 0; c < p.Cin; ++c) {
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+  for (int c = 0; c < p.Cin; ++c) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const float xv = patch[(c * SP + 2 * ty + r) * SP + 2 * tx + s];
-          const float* wr = w + ((r * 3 + s) * p.Cin + c) * 64 + pass * 16;
+    for (int r = 0; r < 3; ++r) {
+      const float* prow = patch + (c * SPH + 2 * ty + r) * SPP + 2 * qc;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+      for (int s = 0; s < 3; ++s) {
+        float xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = prow[16 * i + s];
+        const float* wr = w + ((r * 3 + s) * p.Cin + c) * 64 + cg * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = *reinterpret_cast<const float4*>(wr + q * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][q * 4 + 0] = fmaf(xv[i], wv.x, acc[i][q * 4 + 0]);
+            acc[i][q * 4 + 1] = fmaf(xv[i], wv.y, acc[i][q * 4 + 1]);
+            acc[i][q * 4 + 2] = fmaf(xv[i], wv.z, acc[i][q * 4 + 2]);
+            acc[i][q * 4 + 3] = fmaf(xv[i], wv.w, acc[i][q * 4 + 3]);
+          }
         }
+      }
     }
+  }
+  const int oy = oy0 + ty;
+  if (oy >= p.OH) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ox = ox0 + qc + 8 * i;
+    if (ox >= p.OW) continue;
+    T* out = static_cast<T*>(p.out) + (((int64_t)b * p.OH + oy) * p.OW + ox) * 64 + cg * 4;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = fmaxf(acc[q * 4 + j] + bias[pass * 16 + q * 4 + j], 0.f);
-      Elem<T>::store4(out + pass * 16 + q * 4, v);
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(acc[i][q * 4 + j] + bias[q * 16 + cg * 4 + j], 0.f);
+      Elem<T>::store4(out + q * 16, v);
     }
   }
 }
 
 int launch_stem(Dtype dt, const StemArgs& a, cudaStream_t st) {
   EGN_REQUIRE(a.Cin >= 1 && a.Cin <= STEM_MAX_CIN, "stem: unsupported input channel count %d", a.Cin);
-  const size_t smem = ((size_t)a.Cin * SP * SP + 9 * a.Cin * 64 + 64) * sizeof(float);
-  dim3 grid(ceil_div(a.OW, ST) * ceil_div(a.OH, ST), a.B);
+  const size_t smem = ((size_t)a.Cin * SPH * SPP + 9 * a.Cin * 64 + 64) * sizeof(float);
+  dim3 grid(ceil_div(a.OW, STW) * ceil_div(a.OH, STH), a.B);
   if (dt == Dtype::F32) {
     EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_kernel<float><<<grid, ST * ST, smem, st>>>(a);
+    stem_kernel<float><<<grid, STEM_THREADS, smem, st>>>(a);
   } else {
     EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_kernel<__half><<<grid, ST * ST, smem, st>>>(a);
+    stem_kernel<__half><<<grid, STEM_THREADS, smem, st>>>(a);
   }
   EGN_LAUNCH_CHECK("stem_kernel");
   return EGN_OK;

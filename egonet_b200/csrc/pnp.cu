@@ -1,0 +1,45 @@
+// Batched reprojection refinement: one thread per instance runs the whole of
+// cv2.solvePnP(SOLVEPNP_ITERATIVE) + Rodrigues + transform (pnp_math.h) in fp64.
+// upstream: pnp_refine libs/common/transformation.py:143-157 (one cv2 call per instance on the host;
+// callers: tools/inference_legacy.py:518-547, libs/trainer/trainer.py:355-381).
+// Latency-bound (a 12x12 and a few 6x6 Jacobi eigen-decompositions per instance, ~0.3 MFLOP);
+// it keeps the refined boxes on the device next to the pose records.
+#include "common.h"
+#include "pnp_math.h"
+
+namespace egn {
+
+__global__ void __launch_bounds__(64) pnp_refine_kernel(const double* __restrict__ kpts_3d,
+                                                        const double* __restrict__ kpts_2d, int N, int P,
+                                                        PnpCamera cam, int max_iter, double eps,
+                                                        double* __restrict__ refined, double* __restrict__ pose6,
+                                                        double* __restrict__ info, int32_t* __restrict__ status) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int st = pnp_refine_one(kpts_3d + (size_t)n * P * 3, kpts_2d + (size_t)n * P * 2, P, cam, max_iter, eps,
+                                refined + (size_t)n * P * 3, pose6 ? pose6 + (size_t)n * 6 : nullptr,
+                                info ? info + (size_t)n * 2 : nullptr);
+  if (status) status[n] = st;
+}
+
+}  // namespace egn
+
+extern "C" int egn_pnp_refine(const double* kpts_3d, const double* kpts_2d, int N, int P, double fx, double fy,
+                              double cx, double cy, int max_iter, double* refined, double* pose6, double* info,
+                              int32_t* status, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(N >= 0, "egn_pnp_refine: negative N");
+  EGN_REQUIRE(P >= 6 && P <= kPnpMaxPoints, "egn_pnp_refine: P must be in [6, %d] (got %d; the DLT needs 6 points)",
+              kPnpMaxPoints, P);
+  EGN_REQUIRE(fx != 0.0 && fy != 0.0, "egn_pnp_refine: zero focal length");
+  EGN_REQUIRE(max_iter >= 0, "egn_pnp_refine: negative max_iter");
+  EGN_REQUIRE(N == 0 || (kpts_3d && kpts_2d && refined), "egn_pnp_refine: null pointer");
+  if (int rc = require_device()) return rc;
+  if (N == 0) return EGN_OK;
+  PnpCamera cam{fx, fy, cx, cy};
+  const int threads = 64;
+  pnp_refine_kernel<<<ceil_div(N, threads), threads, 0, as_stream(stream)>>>(
+      kpts_3d, kpts_2d, N, P, cam, max_iter > 0 ? max_iter : 20, 1.1920928955078125e-07, refined, pose6, info, status);
+  EGN_LAUNCH_CHECK("pnp_refine_kernel");
+  return EGN_OK;
+}

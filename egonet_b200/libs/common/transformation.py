@@ -4,7 +4,8 @@
 The reference solves one instance at a time on the host (``compute_rigid_transform``
 [transformation.py:99-134] inside ``EgoNet.get_6d_rep`` [egonet.py:279-295], then
 scipy Euler angles and the observation angle [egonet.py:203-236]).  ``pose_solve``
-does all of it for N instances in one fp64 kernel launch.
+does all of it for N instances in one fp64 kernel launch.  ``pnp_refine`` is the
+batched form of the optional reprojection refinement [transformation.py:143-157].
 """
 import numpy as np
 import torch
@@ -56,3 +57,41 @@ def compute_rigid_transform(X, Y, W=None, verbose=False):
     raise NotImplementedError('use pose_solve(kpts_3d, want_rotation=True): the native kernel derives the '
                               'template from the prediction (egonet.py:238-263) and does not accept an '
                               'arbitrary X')
+
+
+def pnp_refine_batch(predictions, observations, intrinsics, max_iter=0, return_info=False):
+    """N instances of ``pnp_refine`` [transformation.py:143-157] in one launch.
+    predictions [N,P,3], observations [N,P,2] (tensors or arrays), intrinsics 3x3.
+    Returns CUDA fp64 [N,P,3] (= ``(Rodrigues(R) @ X.T + T).T`` per instance); with ``return_info``
+    also pose [N,6] (rvec | tvec), info [N,2] (LM iterations, residual norm in px), status [N]."""
+    dev = predictions.device if torch.is_tensor(predictions) and predictions.is_cuda else \
+        torch.device('cuda', torch.cuda.current_device())
+    x = torch.as_tensor(predictions, dtype=torch.float64).to(dev).contiguous()
+    u = torch.as_tensor(observations, dtype=torch.float64).to(dev).contiguous()
+    n, p = x.shape[0], x.shape[1]
+    if x.dim() != 3 or x.shape[2] != 3 or tuple(u.shape) != (n, p, 2):
+        raise ValueError('predictions must be [N,P,3] and observations [N,P,2]')
+    Kn = np.asarray(intrinsics, dtype=np.float64)
+    out = torch.empty_like(x)
+    pose = torch.empty((n, 6), device=dev, dtype=torch.float64)
+    info = torch.empty((n, 2), device=dev, dtype=torch.float64)
+    status = torch.empty((n,), device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        N.check(N.lib().egn_pnp_refine(N.ptr(x), N.ptr(u), n, p, float(Kn[0, 0]), float(Kn[1, 1]), float(Kn[0, 2]),
+                                       float(Kn[1, 2]), int(max_iter), N.ptr(out), N.ptr(pose), N.ptr(info),
+                                       N.ptr(status), N.current_stream()))
+    return (out, pose, info, status) if return_info else out
+
+
+def pnp_refine(prediction, observation, intrinsics, dist_coeffs):
+    """[transformation.py:143-157] single-instance signature of the reference: prediction [P,3],
+    observation [P,2] -> refined [3,P] (numpy fp64).  Lens distortion is not supported by the kernel."""
+    if dist_coeffs is not None and np.any(np.asarray(dist_coeffs, dtype=np.float64) != 0):
+        raise NotImplementedError('native pnp_refine supports zero lens distortion only')
+    pred = np.asarray(prediction, dtype=np.float64)
+    out, _, _, status = pnp_refine_batch(pred[None], np.asarray(observation, dtype=np.float64)[None], intrinsics,
+                                         return_info=True)
+    if int(status[0]) != 0:
+        print('PnP failed.')          # as upstream: keep the prediction
+        return pred
+    return out[0].cpu().numpy().T

@@ -281,6 +281,25 @@ EGN_API int egn_crop_instances(const egn_image* images_dev, int n_images, const 
                        uint8_t* out_u8, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Reprojection refinement                                */
+/* replaces pnp_refine libs/common/transformation.py:143-157:                  */
+/*   cv2.solvePnP(prediction, observation, K, dist, SOLVEPNP_ITERATIVE)        */
+/*   (DLT start + Levenberg-Marquardt, OpenCV calib3d) then                    */
+/*   Rodrigues(R) @ prediction.T + T, for N instances in one launch.           */
+/* kpts_3d device fp64 [N,P,3] (camera frame), kpts_2d device fp64 [N,P,2]     */
+/* (pixels), 6 <= P <= 64; zero lens distortion; max_iter 0 = OpenCV's 20.     */
+/* refined device fp64 [N,P,3]; pose6 [N,6] = rvec | tvec or NULL; info [N,2]  */
+/* = accepted LM iterations, final residual norm (px) or NULL; status int32    */
+/* [N] (egn_pnp_status) or NULL.  Instances that are planar / degenerate are   */
+/* returned unrefined (upstream keeps the prediction when solvePnP fails).     */
+/* ------------------------------------------------------------------------- */
+typedef enum { EGN_PNP_STATUS_OK = 0, EGN_PNP_STATUS_PLANAR = 1, EGN_PNP_STATUS_DEGENERATE = 2 } egn_pnp_status;
+
+EGN_API int egn_pnp_refine(const double* kpts_3d, const double* kpts_2d, int N, int P, double fx, double fy,
+                   double cx, double cy, int max_iter, double* refined, double* pose6, double* info,
+                   int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Heat-map MSE loss (training config only; loss end of SURVEY.md 8a row a12)   */
 /* replaces JointsMSELoss.forward libs/loss/function.py:28-46 and              */
 /* JointsCompositeLoss.calc_hm_loss libs/loss/function.py:95-111               */

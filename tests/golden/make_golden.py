@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 
 from _refimport import import_reference  # noqa: E402
-from oracle import configs, crop_ref, egonet_ref, hrnet_ref, lifter_ref  # noqa: E402
+from oracle import configs, crop_ref, egonet_ref, hrnet_ref, lifter_ref, pnp_ref  # noqa: E402
 
 
 def rng(seed):
@@ -292,6 +292,28 @@ def golden_crop(ref):
                        tag + '_centers': np.array(cs), tag + '_scales': np.array(ss)})
     save('crop.npz', **arrays)
 
+def golden_pnp(ref):
+    """pnp_refine of the reference (cv2.solvePnP ITERATIVE + Rodrigues) on seeded cuboids; inputs are
+    regenerated from the seeds by ``oracle.pnp_ref.synth_cases``.  ``converged`` marks the instances where
+    cv2 stopped on its relative-step criterion (fewer than 20 LM iterations in the restatement) -- on the
+    others the 20-step cap cuts a still-moving, chaotic iteration and only loose agreement is meaningful."""
+    import cv2
+    fn = ref['transformation'].pnp_refine
+    K = egonet_ref.KITTI_K
+    arrays = {'K': K}
+    for tag, kw in (('p9', dict(n=48, seed=31, points=9)), ('p33', dict(n=16, seed=32, points=33)),
+                    ('p9_noisy', dict(n=32, seed=33, points=9, noise_3d=0.25, noise_px=1.5))):
+        preds, obs = pnp_ref.synth_cases(**kw)
+        refined, rts, conv = [], [], []
+        for X, uv in zip(preds, obs):
+            refined.append(fn(X, uv, K, np.zeros((4, 1))).T)
+            ok, rv, tv = cv2.solvePnP(X, uv, K, np.zeros((4, 1)), flags=cv2.SOLVEPNP_ITERATIVE)
+            rts.append(np.concatenate([rv.ravel(), tv.ravel()]))
+            conv.append(pnp_ref.solve_pnp_iterative(X, uv, K)[2] < 20)
+        arrays.update({tag + '_seed': kw['seed'], tag + '_refined': np.array(refined), tag + '_rt': np.array(rts),
+                       tag + '_converged': np.array(conv), tag + '_digest': np.array([preds.sum(), obs.sum()])})
+    save('pnp.npz', **arrays)
+
 
 def main():
     ref = import_reference()
@@ -307,6 +329,7 @@ def main():
     golden_pipeline(ref)
     golden_loss(ref)
     golden_crop(ref)
+    golden_pnp(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,
