@@ -182,6 +182,45 @@ def roofline_block(classes, total_ms, pk, batch):
     return blk
 
 
+def side_stages(ego, recs, B, K, dev, pk_hbm):
+    """Device time of the crop front-end (B crops cut from one KITTI-sized uint8 image) and of the
+    optional reprojection refinement (B instances of 33 points), each timed alone with CUDA events."""
+    from egonet_b200.libs.common import img_proc, transformation
+    g = torch.Generator().manual_seed(5)
+    image = torch.randint(0, 256, (375, 1242, 3), generator=g, dtype=torch.uint8).to(dev)
+    centers = np.array([r['center'] for r in recs])
+    scales = np.array([r['scale'] for r in recs])
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    ms_crop = timed(lambda: img_proc.crop_instances_device([image], [0] * B, centers, scales, ego.resolution, mean, std))
+    out_bytes = B * 3 * ego.resolution[0] * ego.resolution[1] * 4
+    k3 = torch.randn((B, 33, 3), generator=g, dtype=torch.float64) * 0.8 + torch.tensor([0., 1., 25.], dtype=torch.float64)
+    Kt = torch.as_tensor(np.asarray(K, dtype=np.float64))
+    uv = k3 @ Kt.T
+    uv = uv[..., :2] / uv[..., 2:3]
+    k3d, uvd = (k3 + 0.02 * torch.randn(k3.shape, generator=g, dtype=torch.float64)).to(dev), uv.to(dev)
+    ms_pnp = timed(lambda: transformation.pnp_refine_batch(k3d, uvd, K))
+    return {'crop_frontend': {'ms_per_batch': round(ms_crop, 4), 'crops_per_s': round(B / ms_crop * 1e3, 1),
+                              'write_gbs': round(out_bytes / ms_crop / 1e6, 1),
+                              'hbm_frac': round(out_bytes / ms_crop / 1e6 / pk_hbm, 4),
+                              'note': 'uint8 image in HBM -> fp32 NCHW crops incl. host-side table upload; '
+                                      'algorithmic bytes = the fp32 crops written'},
+            'pnp_refine': {'ms_per_batch': round(ms_pnp, 4), 'instances_per_s': round(B / ms_pnp * 1e3, 1),
+                           'points': 33, 'note': 'optional stage (disabled in the reference\'s maintained path)'}}
+
+
 # ----------------------------------------------------------------------------- CPU oracle legs
 def cpu_pipeline_rate(cfgs, batch, iters, threads):
     """crops/s of the oracle port (reference algorithm on torch-CPU / numpy) for the full path."""
@@ -384,6 +423,13 @@ def main():
             b64 = 64 * 10 / (q0.elapsed_time(q1) * 1e-3)
         # ---- per-kernel-class timing for the roofline block (rank 0)
         classes, hc_ms = profile_hc(ego, dev_sets[0]) if rank == 0 else ({}, 0.0)
+        # ---- stages either side of the path, timed alone for reference
+        extras = None
+        if rank == 0:
+            try:
+                extras = side_stages(ego, recs, B, K, dev, pk_hbm=peaks()['hbm_gbs'])
+            except Exception as e:  # reported next to the headline numbers, never instead of them
+                extras = {'error': '%s: %s' % (type(e).__name__, e)}
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if dist:
@@ -417,6 +463,8 @@ def main():
         'gpu_launches': launches_per_step(ego) * args.steps,
         'clocks': clocks,
     }
+    if extras:
+        line['config']['side_stages'] = extras
     if classes:
         line['roofline'] = roofline_block(classes, hc_ms, pk, B)
         line['hc_roofline'] = {

@@ -1,6 +1,7 @@
 // Error reporting + device gate shared by every entry point.
 #include "common.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace egn {
@@ -15,6 +16,11 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("EGN_PDL") && atoi(getenv("EGN_PDL")) == 0);
+  return on;
+}
 
 static int probe_device(std::string* why) {
   int n = 0;

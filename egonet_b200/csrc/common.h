@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 #include "egonet_b200.h"
 
@@ -47,6 +48,43 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
       return EGN_ERR_INVALID;                                                             \
     }                                                                                     \
   } while (0)
+
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the HC forward is launched with the
+// programmatic-stream-serialisation attribute: its CTAs may be scheduled while the previous kernel
+// of the stream is still draining, run their independent prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, weight loads) and then block in pdl_wait() until the previous grid has
+// completed and flushed its writes.  Rules kept by every such kernel:
+//   * pdl_wait() is executed by every thread that reads or writes activation memory, before it does;
+//   * at least the threads that produce the kernel's output wait, so "this grid completed" always
+//     implies "its predecessor completed" (dependencies reach back more than one launch);
+//   * pdl_trigger() right at the top: dependents only become schedulable once every CTA of this grid
+//     has started, so they never compete with its own unscheduled CTAs.
+// EGN_PDL=0 launches everything fully serialised (the instructions are then no-ops).
+// ---------------------------------------------------------------------------
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

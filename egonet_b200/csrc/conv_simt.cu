@@ -82,6 +82,8 @@ conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
   __shared__ __align__(16) float As[CBK][CBM + 4];
   __shared__ __align__(16) float Bs[CBK][CBN];
   const int t = threadIdx.x;
+  if (t == 0) pdl_trigger();
+  pdl_wait();
   const int64_t M = (int64_t)p.B * p.OH * p.OW;
   const int64_t m0 = (int64_t)blockIdx.x * CBM;
   const int n0 = blockIdx.y * CBN;
@@ -188,9 +190,9 @@ int launch_conv_simt(Dtype dt, const ConvArgs& a, const float* w_packed, cudaStr
   const int64_t M = (int64_t)a.B * a.OH * a.OW;
   dim3 grid((unsigned)ceil_div64(M, CBM), (unsigned)ceil_div(a.Cout_p, CBN));
   if (dt == Dtype::F32)
-    conv_simt_kernel<float><<<grid, CTHREADS, 0, st>>>(a, w_packed);
+    EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<float>, grid, dim3(CTHREADS), 0, st, a, w_packed));
   else
-    conv_simt_kernel<__half><<<grid, CTHREADS, 0, st>>>(a, w_packed);
+    EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<__half>, grid, dim3(CTHREADS), 0, st, a, w_packed));
   EGN_LAUNCH_CHECK("conv_simt_kernel");
   return EGN_OK;
 }
@@ -223,6 +225,11 @@ stem_kernel(StemArgs p) {
   const int b = blockIdx.y;
   const int oy0 = (blockIdx.x / tiles_x) * STH, ox0 = (blockIdx.x % tiles_x) * STW;
   const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+  if (t == 0) pdl_trigger();
+  for (int e = t; e < 9 * p.Cin * 16; e += STEM_THREADS)
+    reinterpret_cast<float4*>(w)[e] = __ldg(reinterpret_cast<const float4*>(p.w) + e);
+  if (t < 64) bias[t] = __ldg(p.bias + t);
+  pdl_wait();   // weights staged above do not depend on the previous kernel; the input and the output buffer do
   for (int e = t; e < p.Cin * SPH * SPW; e += STEM_THREADS) {
     const int c = e / (SPH * SPW), r = (e / SPW) % SPH, q = e % SPW;
     const int iy = iy0 + r, ix = ix0 + q;
@@ -231,9 +238,6 @@ stem_kernel(StemArgs p) {
       v = __ldg(p.x + (((int64_t)b * p.Cin + c) * p.H + iy) * p.W + ix);
     patch[(c * SPH + r) * SPP + q] = v;
   }
-  for (int e = t; e < 9 * p.Cin * 16; e += STEM_THREADS)
-    reinterpret_cast<float4*>(w)[e] = __ldg(reinterpret_cast<const float4*>(p.w) + e);
-  if (t < 64) bias[t] = __ldg(p.bias + t);
   __syncthreads();
   const int cg = t & 3, qc = (t >> 2) & 7, ty = t >> 5;
   float acc[4][16];
@@ -288,10 +292,10 @@ int launch_stem(Dtype dt, const StemArgs& a, cudaStream_t st) {
   dim3 grid(ceil_div(a.OW, STW) * ceil_div(a.OH, STH), a.B);
   if (dt == Dtype::F32) {
     EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_kernel<float><<<grid, STEM_THREADS, smem, st>>>(a);
+    EGN_CUDA_CHECK(launch_pdl(stem_kernel<float>, grid, dim3(STEM_THREADS), smem, st, a));
   } else {
     EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_kernel<__half><<<grid, STEM_THREADS, smem, st>>>(a);
+    EGN_CUDA_CHECK(launch_pdl(stem_kernel<__half>, grid, dim3(STEM_THREADS), smem, st, a));
   }
   EGN_LAUNCH_CHECK("stem_kernel");
   return EGN_OK;
@@ -304,6 +308,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs p) {
   // 8 channels (16 bytes of fp16) per thread; all terms' loads are issued before the sum so that
   // several independent requests per thread are in flight
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   const int cq = p.Cp / 8;
   const int64_t total = (int64_t)p.B * p.H * p.W * cq;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -344,9 +350,9 @@ int launch_fuse(Dtype dt, const FuseArgs& a, cudaStream_t st) {
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 8);
   if (dt == Dtype::F32)
-    fuse_kernel<float><<<blocks, threads, 0, st>>>(a);
+    EGN_CUDA_CHECK(launch_pdl(fuse_kernel<float>, dim3(blocks), dim3(threads), 0, st, a));
   else
-    fuse_kernel<__half><<<blocks, threads, 0, st>>>(a);
+    EGN_CUDA_CHECK(launch_pdl(fuse_kernel<__half>, dim3(blocks), dim3(threads), 0, st, a));
   EGN_LAUNCH_CHECK("fuse_kernel");
   return EGN_OK;
 }
@@ -356,6 +362,8 @@ int launch_fuse(Dtype dt, const FuseArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) head_tail_kernel(HeadTailArgs p) {
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   extern __shared__ float xin[];
   const T* in = static_cast<const T*>(p.in) + (int64_t)blockIdx.x * p.L;
   for (int e = threadIdx.x; e < p.L; e += blockDim.x) xin[e] = Elem<T>::to_f(in[e]);
@@ -380,10 +388,10 @@ int launch_head_tail(Dtype dt, const HeadTailArgs& a, cudaStream_t st) {
   EGN_REQUIRE(smem <= 200 * 1024, "head tail: map too large (%d elements)", a.L);
   if (dt == Dtype::F32) {
     EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_tail_kernel<float><<<a.B, 256, smem, st>>>(a);
+    EGN_CUDA_CHECK(launch_pdl(head_tail_kernel<float>, dim3(a.B), dim3(256), smem, st, a));
   } else {
     EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_tail_kernel<__half><<<a.B, 256, smem, st>>>(a);
+    EGN_CUDA_CHECK(launch_pdl(head_tail_kernel<__half>, dim3(a.B), dim3(256), smem, st, a));
   }
   EGN_LAUNCH_CHECK("head_tail_kernel");
   return EGN_OK;

@@ -679,6 +679,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int n0 = blockIdx.y * p.n_tile;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < p.stages; ++s) {
@@ -693,6 +694,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // everything above is independent of the previous kernel (common.h, PDL rules)
 
   // warp-uniform role loops, instructions predicated to lane 0 (see conv_run_kernel)
   if (warp == 0) {
@@ -844,6 +846,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int i = threadIdx.x - 64; i < p.n_tile; i += kTcThreads - 64) s_bias[i] = __ldg(p.bias + n0 + i);
 
   if (threadIdx.x == 0) {
+    pdl_trigger();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int c = 0; c < p.kchunks; ++c) mbar_init(&a_full[c], 1);
@@ -859,6 +862,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // everything above is independent of the previous kernel (common.h, PDL rules)
   if (threadIdx.x == 0) EGN_TS(1);
   const int ntap = p.halo ? 3 : 1;                 // taps per axis
   const int last_ksteps = (p.Cin_p - (p.kchunks - 1) * 64 + 15) >> 4;   // K16 slices holding real channels
@@ -1056,6 +1060,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   }
   if (threadIdx.x == 0) {
+    pdl_trigger();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (pp.n_stage) {
@@ -1084,8 +1089,12 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int acc_cols = p.T * p.n_tile;                       // TMEM columns of one accumulator set
 
+  // PDL: the weight producer (warp 2) and the MMA issuer (warp 1) never touch activation memory and start
+  // at once -- the resident weights stream in while the previous kernel drains; the roles that read or
+  // write activations (A producer, staging DMA, epilogue) first wait for the previous grid to complete.
   if (warp == 0) {
     // ===================== A producer =====================
+    pdl_wait();
     int j = 0;
     for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
       const int slot = j & 1;
@@ -1191,6 +1200,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 3) {
     // ===================== staging DMA (residual in, output out) =====================
+    pdl_wait();
     if (pp.n_stage && elect_one()) {
       const int S = pp.n_stage;
       const bool has_res = p.res != nullptr && !(p.dbg & 2);
@@ -1236,6 +1246,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // Two warps per TMEM lane quarter split each window's (tile, column group) items between them.
     // One epilogue of half the length per window lets the MMA warp alternate accumulator sets without
     // waiting: with one 4-warp group per set the cadence was (t_mma + t_epi) / 2 instead of max(t_mma, t_epi).
+    pdl_wait();
     const int half = (warp - 4) >> 2;                  // which of the kParts warps of this lane quarter
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -1720,7 +1731,7 @@ static int launch_sw(TcConvPlan* p, const CUtensorMap& ma, const TcParams& tp, d
     EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<SW><<<grid, kTcThreads, p->smem_bytes, st>>>(ma, p->map_b, tp);
+  EGN_CUDA_CHECK(launch_pdl(conv_tc_kernel<SW>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, tp));
   EGN_LAUNCH_CHECK("conv_tc_kernel");
   return EGN_OK;
 }
@@ -1808,9 +1819,9 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     }
     dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
     if (head)
-      conv_persist_kernel<true><<<grid, kPersistThreadsHead, p->smem_bytes, st>>>(ma, p->map_b, m_res, m_out, pp);
+      EGN_CUDA_CHECK(launch_pdl(conv_persist_kernel<true>, grid, dim3(kPersistThreadsHead), p->smem_bytes, st, ma, p->map_b, m_res, m_out, pp));
     else
-      conv_persist_kernel<false><<<grid, kPersistThreads, p->smem_bytes, st>>>(ma, p->map_b, m_res, m_out, pp);
+      EGN_CUDA_CHECK(launch_pdl(conv_persist_kernel<false>, grid, dim3(kPersistThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, pp));
     EGN_LAUNCH_CHECK("conv_persist_kernel");
     if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
       cudaStreamSynchronize(st);
@@ -1863,7 +1874,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       attr_set = true;
     }
     dim3 grid((unsigned)(rp.win_per_img * ceil_div(a.B, p->TBW)), (unsigned)p->n_tiles);
-    conv_run_kernel<<<grid, kTcThreads, p->smem_bytes, st>>>(ma, p->map_b, rp);
+    EGN_CUDA_CHECK(launch_pdl(conv_run_kernel, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, rp));
     EGN_LAUNCH_CHECK("conv_run_kernel");
     if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
       cudaStreamSynchronize(st);
