@@ -1777,10 +1777,10 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.heatmap = a.heatmap; rp.xs = a.xs; rp.ys = a.ys; rp.coord_maps = a.coord_maps;
     rp.dbg = getenv("EGN_TC_DBG") ? atoi(getenv("EGN_TC_DBG")) : 0;
     // L2 bulk prefetch of the residual rows by the A producer (direct, non-staged epilogue only):
-    // EGN_TC_RES_PREFETCH = 1 always (default), 0 never, 2 only when the output channels are not split over
-    // blockIdx.y (a split layer prefetches the all-channel rows once per half: 2x the residual DRAM traffic,
-    // profiles/r01d_ncu_conv_persist_96ch.md)
-    static const int res_prefetch = getenv("EGN_TC_RES_PREFETCH") ? atoi(getenv("EGN_TC_RES_PREFETCH")) : 1;
+    // EGN_TC_RES_PREFETCH = 2 (default) only when the output channels are not split over blockIdx.y, 1 always,
+    // 0 never.  A split layer would prefetch the all-channel rows once per half -- 2x the residual DRAM traffic
+    // (profiles/r01d_ncu_conv_persist_96ch.md) for no measurable gain (10.91k vs 10.92k crops/s, 5 A/B runs).
+    static const int res_prefetch = getenv("EGN_TC_RES_PREFETCH") ? atoi(getenv("EGN_TC_RES_PREFETCH")) : 2;
     if (res_prefetch == 0 || (res_prefetch == 2 && p->n_tiles > 1)) rp.dbg |= 128;
     rp.ts = nullptr;
     static unsigned long long* d_ts3 = nullptr;
