@@ -157,6 +157,66 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// ---- CTA pair (cta_group::2) variants: two CTAs of a cluster drive one M = 256 MMA; each provides its own
+// 128 rows of A and half of the N rows of B, at identical shared-memory offsets ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(const void* local, uint32_t rank) {
+  uint32_t d;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(smem_u32(local)), "r"(rank));
+  return d;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads issued by either CTA of a pair; the transaction bytes are signalled on the barrier at `bar_cluster`
+// (a shared::cluster address, normally the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// M = 256 MMA over the CTA pair, issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem], kind::f16, issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -467,11 +527,26 @@ __device__ __forceinline__ void lite_store(const EpiLite& e, const LiteItem& it,
   }
 }
 
+// K-split accumulators: the K loop of a tile is dealt round-robin over `ksplit` TMEM accumulators (consecutive
+// tcgen05.mma then never wait for each other's result: 62 -> 44 cycles per 128x48x16 MMA between 1 and 8
+// accumulators, profiles/r01k_umma_rate.log); the epilogue adds the partial sums.  v holds accumulator 0 of the
+// 16 columns at `taddr`; the others sit `acc_stride` columns apart.
+__device__ __forceinline__ void add_split_accumulators(uint32_t (&v)[16], uint32_t taddr, int ksplit, uint32_t acc_stride) {
+  for (int a = 1; a < ksplit; ++a) {
+    uint32_t x[16];
+    tmem_ld(taddr + (uint32_t)a * acc_stride, x);
+    tmem_ld_wait_dep(x);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(x[i]));
+  }
+}
+
 template <int kParts, typename RowFn>
 __device__ __forceinline__ void epi_window_lite(const EpiLite& e, uint32_t tmem_lane_base, int T, int n_tile, int n0,
                                                 uint64_t* full_bar, uint32_t parity, int half, RowFn row_of,
-                                                unsigned long long* ts) {
+                                                unsigned long long* ts, int ksplit = 1) {
   const int per_tile = n_tile >> 4;
+  const uint32_t acc_stride = (uint32_t)(T * n_tile);
   auto next = [&](const LiteItem& it) {              // item + kParts; refresh the row when the tile changes
     LiteItem n = it;
     n.g += kParts;
@@ -506,6 +581,7 @@ __device__ __forceinline__ void epi_window_lite(const EpiLite& e, uint32_t tmem_
 #pragma unroll
     for (int i = 0; i < 16; ++i) v0[i] = v1[i];
     if (n1.t < T) tmem_ld(taddr(n1), v1);
+    if (ksplit > 1) add_split_accumulators(v0, taddr(cur), ksplit, acc_stride);
     lite_store(e, cur, n0 + 16 * cur.g, 16 * cur.g, v0, r0);
     r0[0] = r1[0]; r0[1] = r1[1];
     r1[0] = r2[0]; r1[1] = r2[1];
@@ -541,8 +617,9 @@ struct StageRow {
 
 template <int kParts, typename RowFn>
 __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tmem_lane_base, int T, int n_tile,
-                                                  int part, RowFn row_of) {
+                                                  int part, RowFn row_of, int ksplit = 1) {
   const int per_tile = n_tile >> 4;
+  const uint32_t acc_stride = (uint32_t)(T * n_tile);
   const uint32_t pitch = (uint32_t)e.cb * 2u;
   int t = -1, g = part - kParts + per_tile, t_row = -1;
   StageRow r{false, 0};
@@ -607,6 +684,7 @@ __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tm
     step();
     tmem_ld_wait_dep(vA);
     if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vB);
+    if (ksplit > 1) add_split_accumulators(vA, tmem_lane_base + (uint32_t)(ct * n_tile + 16 * cg), ksplit, acc_stride);
     row_for(ct);
     item(vA, r, cg);
     if (t >= T) break;
@@ -615,6 +693,7 @@ __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tm
     step();
     tmem_ld_wait_dep(vB);
     if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vA);
+    if (ksplit > 1) add_split_accumulators(vB, tmem_lane_base + (uint32_t)(ct * n_tile + 16 * cg), ksplit, acc_stride);
     row_for(ct);
     item(vB, r, cg);
   }
@@ -992,6 +1071,11 @@ struct PersistParams {
   RunParams r;          // geometry / operands as in v2 (r.b_stages = ring depth when streaming)
   int n_windows;        // win_per_img * ceil(B / TBW)
   int b_resident;       // 1: all taps*kchunks weight tiles live in smem for the CTA's lifetime
+  int b_rows;           // weight rows per CTA tile: n_tile, or n_tile / 2 in CTA-pair mode (each CTA holds half of N)
+  int ksplit;           // accumulators per M tile (K loop dealt round-robin; summed by the epilogue), >= 1
+  int pack_tail;        // 1: 3x3 conv whose last 64-channel chunk holds 32 real channels -- the weight matrix keeps
+                        //    those tail chunks of taps (2i, 2i+1) side by side in ONE 64-wide tile (resident mode)
+  int w_tiles;          // weight tiles resident per CTA: taps * kchunks, or taps * (kchunks-1) + ceil(taps/2) packed
   // staged epilogue (0 = direct global accesses)
   int n_stage;          // staging buffers: 0, 1 or 2
   int cb, nblk;         // channels per staging block (64 / 48), blocks per n_tile
@@ -999,7 +1083,14 @@ struct PersistParams {
   uint32_t blk_bytes;   // bytes of one block, 1024-aligned
 };
 
-template <bool kHead>   // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps)
+// kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps).
+// kPair: the CTAs of a 2-CTA cluster work as a pair (tcgen05 cta_group::2).  Each CTA loads its own window (its
+//   128 x T rows of the M = 256 x T tile) and keeps HALF of the output channels' weights resident; the leader's
+//   MMA thread issues one N = n_tile MMA for both, so a layer whose weights only fit when split over N runs one
+//   pass of N = 96 MMAs instead of two passes of N = 48 (same operand bytes per MMA, twice the work).
+//   Barrier protocol: a_full / w_full / acc_empty live in the LEADER (the peer's TMA transactions and epilogue
+//   arrivals are sent there); a_empty / acc_full are signalled in both CTAs by multicast tcgen05.commit.
+template <bool kHead, bool kPair = false>
 __global__ void __launch_bounds__(kHead ? kPersistThreadsHead : kPersistThreads, 1)
 conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
@@ -1009,9 +1100,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_chunk = (uint32_t)p.rows_alloc * 128u;
   const uint32_t a_slot = a_chunk * (uint32_t)p.kchunks;
-  const uint32_t b_stage = ((uint32_t)p.n_tile * 128u + 1023u) & ~1023u;
-  const int w_tiles = p.taps * p.kchunks;
+  const uint32_t b_stage = ((uint32_t)pp.b_rows * 128u + 1023u) & ~1023u;
+  const int w_tiles = pp.w_tiles;
   const int b_slots = pp.b_resident ? w_tiles : p.b_stages;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;          // 0 = leader of the pair
+  // window of iteration j: w0 + j * gridDim.x + w_off (pair: consecutive windows 2q, 2q+1 per iteration; the odd
+  // one may lie past the end -- its loads are zero-filled by TMA and its rows are invalid in the epilogue)
+  const int w_off = kPair ? (int)crank : 0;
+  const int w0 = (int)blockIdx.x - w_off;
   uint8_t* smem_a = smem;                                   // 2 slots
   uint8_t* smem_b = smem + 2 * (size_t)a_slot;
   uint8_t* smem_stage = smem_b + (size_t)b_slots * b_stage;                  // n_stage x nblk x blk_bytes (1024-aligned)
@@ -1043,7 +1139,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int ktot = (p.Cin_p + 15) >> 4;                      // K16 slices per tap
     const int n_mma = p.taps * ktot * p.T;
     const int ntap_w = p.halo ? 3 : 1;
-    const uint32_t b_stage_t = ((uint32_t)p.n_tile * 128u + 1023u) & ~1023u;
+    const uint32_t b_stage_t = ((uint32_t)pp.b_rows * 128u + 1023u) & ~1023u;
     for (int i = threadIdx.x; i < n_mma; i += (int)blockDim.x) {
       const int t = i % p.T, kk = i / p.T;
       const int tap = kk / ktot, kr = kk - tap * ktot;
@@ -1053,9 +1149,20 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint4 e;
       e.x = (((uint32_t)c * (uint32_t)p.rows_alloc * 128u + (uint32_t)(r * p.Wp + q) * 128u + (uint32_t)t * 16384u) >> 4) +
             2u * (uint32_t)k;
-      e.y = (pp.b_resident ? ((uint32_t)(tap * p.kchunks + c) * b_stage_t) >> 4 : 0u) + 2u * (uint32_t)k;
-      e.z = (uint32_t)(t * p.n_tile);
-      e.w = (kk > 0 ? 1u : 0u) | ((k == 0 && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && t == p.T - 1) ? 4u : 0u);
+      // weight tile and K16 slot inside it: (tap, chunk) tiles in order, or -- packed -- the full chunks first and
+      // then one tile per pair of taps holding both 32-channel tails (slots 0-1: even tap, 2-3: odd tap)
+      uint32_t wt = (uint32_t)(tap * p.kchunks + c), ks = (uint32_t)k;
+      if (pp.pack_tail) {
+        if (c < p.kchunks - 1) {
+          wt = (uint32_t)(tap * (p.kchunks - 1) + c);
+        } else {
+          wt = (uint32_t)(p.taps * (p.kchunks - 1) + (tap >> 1));
+          ks = (uint32_t)((tap & 1) * 2 + k);
+        }
+      }
+      e.y = (pp.b_resident ? (wt * b_stage_t) >> 4 : 0u) + 2u * ks;
+      e.z = (uint32_t)(((kk % pp.ksplit) * p.T + t) * p.n_tile);
+      e.w = (kk >= pp.ksplit ? 1u : 0u) | ((k == 0 && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && t == p.T - 1) ? 4u : 0u);
       s_issue[i] = e;
     }
   }
@@ -1071,7 +1178,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4 * kParts);        // one arrival per epilogue warp
+      mbar_init(&acc_empty[i], (kPair ? 2 : 1) * 4 * kParts);        // one arrival per epilogue warp (of both CTAs)
       mbar_init(&stage_full[i], 1);
       mbar_init(&staged[i], 4 * kParts);
     }
@@ -1082,12 +1189,17 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if constexpr (kPair) {
+    cluster_sync_all();                            // both CTAs' barriers initialised before any remote signal
+    if (warp == 1) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+  } else {
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const int acc_cols = p.T * p.n_tile;                       // TMEM columns of one accumulator set
+  const int acc_cols = pp.ksplit * p.T * p.n_tile;           // TMEM columns of one accumulator set
 
   // PDL: the weight producer (warp 2) and the MMA issuer (warp 1) never touch activation memory and start
   // at once -- the resident weights stream in while the previous kernel drains; the roles that read or
@@ -1096,16 +1208,26 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== A producer =====================
     pdl_wait();
     int j = 0;
-    for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+    for (int wb = w0; wb < pp.n_windows; wb += gridDim.x, ++j) {
+      const int w = wb + w_off;
       const int slot = j & 1;
       mbar_wait(&a_empty[slot], (uint32_t)((j >> 1) & 1) ^ 1u);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
       if (!(p.dbg & 8) && elect_one()) {
-        mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
-        for (int c = 0; c < p.kchunks; ++c)
-          tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
-                      win * p.THW - p.halo, bg * p.TBW);
-        if (p.res && !pp.n_stage && !(p.dbg & 128)) {
+        if constexpr (kPair) {
+          // both windows of the iteration are accounted for on the leader's barrier
+          if (crank == 0) mbar_expect_tx(&a_full[slot], 2u * p.a_bytes * (uint32_t)p.kchunks);
+          const uint32_t bar = mapa_rank(&a_full[slot], 0);
+          for (int c = 0; c < p.kchunks; ++c)
+            tma_load_4d_pair(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, bar, c * 64, -p.halo,
+                             win * p.THW - p.halo, bg * p.TBW);
+        } else {
+          mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
+          for (int c = 0; c < p.kchunks; ++c)
+            tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
+                        win * p.THW - p.halo, bg * p.TBW);
+        }
+        if (p.res && !pp.n_stage && !(p.dbg & 128) && w < pp.n_windows) {
           // the residual rows of this window are one contiguous NHWC range: pull them towards L2 now,
           // ~2 windows before the epilogue reads them
           const int b0 = bg * p.TBW, h0 = win * p.THW;
@@ -1118,10 +1240,18 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== B producer =====================
     if (pp.b_resident) {
       if (elect_one()) {
-        mbar_expect_tx(w_full, p.b_bytes * (uint32_t)w_tiles);
         int kcoord = 0;
-        for (int i = 0; i < w_tiles; ++i, kcoord += 64)
-          tma_load_2d(smem_b + (size_t)i * b_stage, &map_b, w_full, kcoord, n0);
+        if constexpr (kPair) {
+          // this CTA's half of the output channels; both halves are accounted for on the leader's barrier
+          if (crank == 0) mbar_expect_tx(w_full, 2u * p.b_bytes * (uint32_t)w_tiles);
+          const uint32_t bar = mapa_rank(w_full, 0);
+          for (int i = 0; i < w_tiles; ++i, kcoord += 64)
+            tma_load_2d_pair(smem_b + (size_t)i * b_stage, &map_b, bar, kcoord, n0 + (int)crank * pp.b_rows);
+        } else {
+          mbar_expect_tx(w_full, p.b_bytes * (uint32_t)w_tiles);
+          for (int i = 0; i < w_tiles; ++i, kcoord += 64)
+            tma_load_2d(smem_b + (size_t)i * b_stage, &map_b, w_full, kcoord, n0);
+        }
       }
     } else {
       uint32_t stage = 0, phase = 0;
@@ -1143,15 +1273,15 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // One elected thread runs the whole role (waits, MMAs, commits): no per-burst elect / reconvergence.
-    if (elect_one()) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    if ((!kPair || crank == 0) && elect_one()) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
       const uint64_t desc_hi = make_smem_desc(0, 128);
       const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
       const int n_mma = p.taps * ((p.Cin_p + 15) >> 4) * p.T;
       if (pp.b_resident) mbar_wait(w_full, 0);
       uint32_t stage = 0, phase = 0;
       int j = 0;
-      for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+      for (int w = w0; w < pp.n_windows; w += gridDim.x, ++j) {
         const int slot = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
         if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
@@ -1165,6 +1295,16 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         const uint32_t a_lo = a_lo0 + (((uint32_t)slot * a_slot) >> 4);
         const uint32_t d0 = tmem_base + (uint32_t)(slot * acc_cols);
+        if constexpr (kPair) {
+#pragma unroll 4
+          for (int i = 0; i < n_mma; ++i) {
+            const uint4 e = s_issue[i];
+            umma_f16_pair(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+          }
+          umma_commit_pair(&a_empty[slot]);     // both CTAs' window slots may be refilled
+          umma_commit_pair(&acc_full[slot]);    // both CTAs' accumulator halves complete
+          continue;
+        }
         if (pp.b_resident) {
 #pragma unroll 4
           for (int i = 0; i < n_mma; ++i) {
@@ -1204,9 +1344,9 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (pp.n_stage && elect_one()) {
       const int S = pp.n_stage;
       const bool has_res = p.res != nullptr && !(p.dbg & 2);
-      const int my_windows = ((int)pp.n_windows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int my_windows = ((int)pp.n_windows - w0 + (int)gridDim.x - 1) / (int)gridDim.x;   // iterations of this CTA (pair)
       auto coords = [&](int jj, int& h0, int& b0) {
-        const int w = blockIdx.x + jj * gridDim.x;
+        const int w = w0 + jj * (int)gridDim.x + w_off;    // past-the-end window of a pair: loads zero-filled, stores clipped
         const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
         h0 = win * p.THW;
         b0 = bg * p.TBW;
@@ -1253,8 +1393,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
               nullptr};
     const EpiLite el{p.res, p.out, smem_u32(s_bias), p.relu, p.Cout_p, p.dbg};
+    const uint32_t acc_empty_leader[2] = {kPair ? mapa_rank(&acc_empty[0], 0) : 0u, kPair ? mapa_rank(&acc_empty[1], 0) : 0u};
     int j = 0;
-    for (int w = blockIdx.x; w < pp.n_windows; w += gridDim.x, ++j) {
+    for (int wb = w0; wb < pp.n_windows; wb += gridDim.x, ++j) {
+      const int w = wb + w_off;
       const int slot = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
@@ -1308,25 +1450,30 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                        wp < p.Wp - p.halo;
             sr.srow = (uint32_t)(((bi * p.THW) + (hp - p.halo)) * p.W + (wp - p.halo));
             return sr;
-          });
+          }, pp.ksplit);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&staged[sb]);
         } else {
-          epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts);
+          epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts, pp.ksplit);
         }
       }
       if (p.ts && j < 8 && lane == 0) atomicMax(p.ts + ((size_t)blockIdx.x * 8 + j) * 8 + 5, gtime());   // last warp done
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[slot]);      // one arrival per warp releases the accumulator set
+      if (lane == 0) {                                   // one arrival per warp releases the accumulator set
+        if constexpr (kPair) mbar_arrive_cluster(acc_empty_leader[slot]);
+        else mbar_arrive(&acc_empty[slot]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();              // the peer's smem / barriers stay valid until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -1361,6 +1508,10 @@ struct TcConvPlan {
   // v2 (window run) configuration; use_run == false -> v1 per-tap kernel
   bool use_run = false;
   bool use_persist = false;   // v3: persistent one-CTA-per-SM variant of the window-run kernel
+  bool use_pair = false;      // v3 with CTA pairs (cta_group::2) instead of an N split over blockIdx.y
+  size_t pair_smem = 0;       // dynamic smem per CTA in pair mode
+  bool pack_tail = false;     // weight matrix stored with the 32-channel tail chunks of two taps per tile (see PersistParams)
+  int w_tiles = 0;            // resident weight tiles per CTA
   int b_resident = 0;
   int n_stage = 0, cb = 0, nblk = 0, rows_stage = 0;   // staged (TMA) epilogue of the persistent kernel
   uint32_t blk_bytes = 0;
@@ -1553,7 +1704,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
             const size_t fixed = 1024 + 256 + (size_t)n_tile * 4 +
                                  (size_t)a.ksize * a.ksize * ((a.Cin_p + 15) / 16) * T * 16;   // barriers, bias, issue table
-            size_t smem = a_bytes + (size_t)w_tiles * b_stage_bytes + fixed;
+            // resident weights: the 32-channel tail chunks of a 3x3 conv are packed two taps per tile
+            const bool can_pack = a.ksize == 3 && p->kchunks >= 2 && a.Cin_p % 64 == 32 && !getenv("EGN_TC_NOPACK");
+            const int w_tiles_res = can_pack ? a.ksize * a.ksize * (p->kchunks - 1) + (a.ksize * a.ksize + 1) / 2 : w_tiles;
+            size_t smem = a_bytes + (size_t)w_tiles_res * b_stage_bytes + fixed;
             int resident = 1, bst = 0;
             if (smem > smem_cap) {
               // weights streamed through a ring, once per window: only worth it when a window holds >= 2 M tiles
@@ -1608,6 +1762,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->smem_bytes = smem_s;
                 p->tmem_cols = pow2_cols(2 * T * n_tile);
                 p->n_stage = S; p->cb = cb; p->nblk = nblk; p->rows_stage = rows_stage; p->blk_bytes = (uint32_t)blk_bytes;
+                p->pack_tail = resident && can_pack;
+                p->w_tiles = resident ? w_tiles_res : w_tiles;
               }
             }
           }
@@ -1615,10 +1771,23 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
       if (p->use_persist && p->run_eff < 0.6f) {
         p->use_persist = false;
+        p->pack_tail = false;
         p->n_tiles = base_tiles;
         p->n_tile = a.Cout_p / base_tiles;
       }
       if (p->use_persist) p->use_run = false;
+      // An N split chosen only to make the weights fit (two passes of N/2-wide MMAs over the same windows) runs
+      // as ONE pass of CTA pairs instead: same smem per CTA, N-wide cta_group::2 MMAs (EGN_TC_PAIR=0 disables).
+      {
+        const char* pe = getenv("EGN_TC_PAIR");
+        // per CTA the pair keeps the split's weights and windows but stages / biases the full N
+        const size_t pair_smem = p->smem_bytes + (size_t)p->n_stage * p->nblk * p->blk_bytes + 4 * (size_t)p->n_tile;
+        p->use_pair = p->use_persist && !(pe && atoi(pe) == 0) && base_tiles == 1 && p->n_tiles == 2 && p->b_resident &&
+                      (2 * p->n_tile) % 16 == 0 && 2 * p->T * 2 * p->n_tile <= 512 && pair_smem <= 227 * 1024;
+        if (p->use_pair) p->pair_smem = pair_smem;
+        if (p->use_pair) p->tmem_cols = pow2_cols(2 * p->T * 2 * p->n_tile);
+      }
+      if (getenv("EGN_TC_VERBOSE") && p->use_persist && p->use_pair) fprintf(stderr, "[egn] (next line) CTA-pair mode\n");
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
         fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
                 a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->T, p->THW, p->TBW, p->run_eff,
@@ -1630,12 +1799,18 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   const int taps = a.ksize * a.ksize;
   const int cin_k = p->kchunks * p->kc;
   p->cin_k = cin_k;
-  const size_t K = (size_t)taps * cin_k;
+  const bool pack = p->use_persist && p->pack_tail;
+  const int full_k = (p->kchunks - 1) * 64;              // channels of a tap that live in full 64-wide chunks
+  const size_t K = pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * cin_k;
   std::vector<__half> w((size_t)a.Cout_p * K, __float2half_rn(0.f));
   for (int o = 0; o < a.Cout_p; ++o)
     for (int t = 0; t < taps; ++t)
-      for (int c = 0; c < a.Cin_p; ++c)
-        w[(size_t)o * K + (size_t)t * cin_k + c] = __float2half_rn(wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o]);
+      for (int c = 0; c < a.Cin_p; ++c) {
+        size_t k = (size_t)t * cin_k + c;
+        if (pack) k = c < full_k ? (size_t)t * full_k + c
+                                 : (size_t)taps * full_k + (size_t)(t >> 1) * 64 + (size_t)(t & 1) * 32 + (c - full_k);
+        w[(size_t)o * K + k] = __float2half_rn(wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o]);
+      }
   p->w_bytes = w.size() * sizeof(__half);
   if (cudaMalloc(&p->d_w, p->w_bytes) != cudaSuccess ||
       cudaMemcpy(p->d_w, w.data(), p->w_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1791,10 +1966,31 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     }
     pp.n_windows = rp.win_per_img * ceil_div(a.B, p->TBW);
     pp.b_resident = p->b_resident;
+    pp.b_rows = p->n_tile;
+    pp.pack_tail = p->pack_tail ? 1 : 0;
+    pp.w_tiles = p->w_tiles;
     const bool head = a.heatmap || a.coord_maps || getenv("EGN_TC_EPI_GENERIC");
+    const bool pair = p->use_pair && !head && pp.n_windows >= 2;
+    if (pair) rp.n_tile = 2 * p->n_tile;         // MMA / epilogue width; b_rows (and b_bytes) stay per-CTA
+    // K-split accumulators (EGN_TC_KSPLIT=k, off by default): where a window is a single M tile the MMAs form one
+    // dependent chain (62 SM cycles per MMA for every N <= 128, profiles/r01k_umma_rate.log, r01m_timeline_96ch.log);
+    // dealing the K loop over k accumulators was measured on the 96-channel layers and did NOT pay: 85.9 -> 87.1 (k=2)
+    // -> 88.3 us (k=4) with the N split, 82.1 -> 83.7 us (k=2) with CTA pairs.  Kept as a tested switch.
+    {
+      const int ks_env = getenv("EGN_TC_KSPLIT") ? atoi(getenv("EGN_TC_KSPLIT")) : 0;
+      const int ksteps = rp.taps * ((p->Cin_p + 15) / 16);
+      int ks = 1;
+      if (!head && ks_env > 1) {
+        ks = ks_env;
+        while (ks > 1 && (2 * ks * p->T * rp.n_tile > 512 || ks > ksteps)) --ks;
+      }
+      pp.ksplit = ks;
+      rp.tmem_cols = pow2_cols(2 * ks * p->T * rp.n_tile);
+    }
     CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
     if (p->n_stage && !head) {
-      pp.n_stage = p->n_stage; pp.cb = p->cb; pp.nblk = p->nblk; pp.rows_stage = p->rows_stage; pp.blk_bytes = p->blk_bytes;
+      pp.n_stage = p->n_stage; pp.cb = p->cb; pp.nblk = pair ? 2 * p->nblk : p->nblk; pp.rows_stage = p->rows_stage;
+      pp.blk_bytes = p->blk_bytes;
       std::lock_guard<std::mutex> lock(p->mu);
       for (int which = 0; which < 2; ++which) {
         const void* ptr = which ? a.out : a.res;
@@ -1815,6 +2011,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     if (!attr_set) {
       EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
     static int num_sms = 0;
@@ -1824,7 +2021,12 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
-    if (head)
+    if (pair) {
+      // one cluster of two CTAs per SM pair; the extra bias floats of the full-width tile need 4 * n_tile more bytes
+      const dim3 pgrid((unsigned)(std::min(pp.n_windows, num_sms) & ~1), 1);
+      EGN_CUDA_CHECK(launch_pdl_cluster(conv_persist_kernel<false, true>, pgrid, dim3(kPersistThreads), p->pair_smem, st, 2,
+                                        ma, p->map_b, m_res, m_out, pp));
+    } else if (head)
       EGN_CUDA_CHECK(launch_pdl(conv_persist_kernel<true>, grid, dim3(kPersistThreadsHead), p->smem_bytes, st, ma, p->map_b, m_res, m_out, pp));
     else
       EGN_CUDA_CHECK(launch_pdl(conv_persist_kernel<false>, grid, dim3(kPersistThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, pp));

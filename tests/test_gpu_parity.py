@@ -331,18 +331,28 @@ CONV_CASES = [
     (384, 48, 8, 8, 1, 1, 5), (64, 64, 128, 128, 3, 2, 1), (256, 96, 64, 64, 3, 2, 2), (48, 384, 16, 16, 3, 2, 3),
     (35, 66, 64, 64, 3, 2, 2), (35, 66, 64, 64, 1, 2, 2), (66, 66, 4, 4, 3, 1, 5), (48, 33, 64, 64, 1, 1, 2),
     (32, 32, 64, 48, 3, 1, 2), (64, 64, 32, 24, 3, 1, 3), (128, 256, 16, 12, 3, 2, 3), (16, 16, 32, 32, 3, 1, 1),
+    (96, 96, 32, 32, 3, 1, 40),     # 440 windows: several iterations per CTA pair, last pair iteration ragged
 ]
 
 
-@pytest.mark.parametrize('variant', ['auto', 'no_v3', 'v1_only'])
+@pytest.mark.parametrize('variant', ['auto', 'no_pair', 'ksplit', 'no_v3', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
 def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
     """One fused conv (bias + residual + ReLU) through the tcgen05 and the CUDA-core kernels against
     torch's fp32 conv2d on the same fp16-rounded operands.  `variant` restricts which tcgen05 kernel the
-    plan may pick (auto: v3 persistent / v2 window-run / v1 per-tap by shape; no_v3; v1_only), so every
+    plan may pick (auto: v3 persistent -- CTA pairs where the plan splits N -- / v2 window-run / v1 per-tap by
+    shape; no_pair: v3 with the N split over blockIdx.y instead of pairs; ksplit: v3 with two accumulators per
+    M tile; no_v3; v1_only), so every
     kernel is exercised on every shape it supports."""
     import ctypes
     from egonet_b200 import _native as N
+    Cin, Cout, H, W, k, stride, B = case
+    if variant == 'no_pair':
+        monkeypatch.setenv('EGN_TC_PAIR', '0')
+    if variant == 'ksplit':
+        if not (k == 3 and stride == 1 and W >= 24):
+            pytest.skip('K-split accumulators only exist in the persistent kernel')
+        monkeypatch.setenv('EGN_TC_KSPLIT', '2')
     if variant in ('no_v3', 'v1_only'):
         monkeypatch.setenv('EGN_TC_V3', '0')
     if variant == 'v1_only':

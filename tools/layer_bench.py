@@ -47,7 +47,8 @@ def main():
     if args.child:
         return run_child(args)
     table = {}
-    for label, env in (('v3_pers', {}), ('v2_run', {'EGN_TC_V3': '0'}), ('v1_tap', {'EGN_TC_V3': '0', 'EGN_TC_V2': '0'})):
+    for label, env in (('v3_pers', {}), ('v3_nopair', {'EGN_TC_PAIR': '0'}), ('v2_run', {'EGN_TC_V3': '0'}),
+                       ('v1_tap', {'EGN_TC_V3': '0', 'EGN_TC_V2': '0'})):
         e = dict(os.environ, EGN_TC_VERBOSE='1', **env)
         r = subprocess.run([sys.executable, __file__, '--child', '--batch', str(args.batch), '--iters', str(args.iters)],
                            capture_output=True, text=True, env=e)
