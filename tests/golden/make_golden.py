@@ -314,6 +314,29 @@ def golden_pnp(ref):
                        tag + '_converged': np.array(conv), tag + '_digest': np.array([preds.sum(), obs.sum()])})
     save('pnp.npz', **arrays)
 
+def golden_format(ref):
+    """get_pred_str / get_instance_str of the reference (libs/common/format.py:25-61) on seeded detector rows."""
+    import importlib
+    fmt = importlib.import_module('libs.common.format')
+    g = rng(61)
+    n = 7
+    rows = []
+    for i in range(n):
+        row = {'class': ['Car', 'Van', 'Pedestrian'][i % 3], 'truncation': float(g.uniform(0, 1)),
+               'occlusion': float(g.integers(0, 3)), 'alpha': float(g.uniform(-3, 3)),
+               'bbox': [float(v) for v in g.uniform(0, 1200, 4)],
+               'dimensions': [float(v) for v in g.uniform(1, 5, 3)],
+               'locations': [float(v) for v in g.uniform(-30, 60, 3)], 'rot_y': float(g.uniform(-3, 3))}
+        if i % 2 == 0:
+            row['score'] = float(g.uniform(0, 1))
+        rows.append(row)
+    record = {'raw_txt_format': rows, 'euler_angles': g.uniform(-3.2, 3.2, (n, 3)), 'alphas': g.uniform(-3.2, 3.2, n)}
+    out = {'rows': rows, 'euler_angles': record['euler_angles'].tolist(), 'alphas': record['alphas'].tolist(),
+           'pred_str': fmt.get_pred_str(record), 'instance_strs': [fmt.get_instance_str(r) for r in rows]}
+    with open(os.path.join(HERE, 'format.json'), 'w') as f:
+        json.dump(out, f, indent=1)
+    print('format.json')
+
 
 def main():
     ref = import_reference()
@@ -330,6 +353,7 @@ def main():
     golden_loss(ref)
     golden_crop(ref)
     golden_pnp(ref)
+    golden_format(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,
