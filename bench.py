@@ -303,7 +303,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--ref-batch', type=int, default=8)
-    ap.add_argument('--cpu-baseline-crops', type=int, default=16)
+    ap.add_argument('--cpu-baseline-crops', type=int, default=64)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     args = ap.parse_args()
