@@ -212,8 +212,9 @@ def _cb(sd, x, conv, bn, stride=1, pad=0, relu=False, ctx=Exact, fp32_weights=Fa
     else:
         y = F.conv2d(x, sd[conv + '.weight'], sd.get(conv + '.bias'), stride=stride, padding=pad)
         if bn is not None:
+            # ctx.training (oracle/train_ref.py): batch statistics + in-place running-stat update (momentum 0.1)
             y = F.batch_norm(y, sd[bn + '.running_mean'], sd[bn + '.running_var'],
-                             sd[bn + '.weight'], sd[bn + '.bias'], False, 0.1, BN_EPS)
+                             sd[bn + '.weight'], sd[bn + '.bias'], getattr(ctx, 'training', False), 0.1, BN_EPS)
     return F.relu(y) if relu else y
 
 

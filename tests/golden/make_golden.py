@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 
 from _refimport import import_reference  # noqa: E402
-from oracle import configs, crop_ref, egonet_ref, hrnet_ref, lifter_ref, pnp_ref  # noqa: E402
+from oracle import configs, crop_ref, egonet_ref, hrnet_ref, lifter_ref, pnp_ref, train_ref  # noqa: E402
 
 
 def rng(seed):
@@ -337,6 +337,50 @@ def golden_format(ref):
         json.dump(out, f, indent=1)
     print('format.json')
 
+TRAIN_FULL_GRADS = ('conv1.weight', 'stage3.0.branches.1.1.bn1.weight', 'final_layer.bias',
+                    'stage2.0.fuse_layers.1.0.0.0.weight')
+TRAIN_STATS = ('bn1', 'stage4.0.branches.3.1.bn2')
+
+
+def golden_train(ref):
+    """One training-mode forward + backward of the reference HC module (heat-map head, JointsMSELoss with target
+    weights) on Gaussian targets made by the reference's generate_target: loss, a norm of EVERY parameter
+    gradient, a few gradients in full, updated BN running statistics."""
+    import libs.loss.function as LF
+    cfgs = configs.tiny_cfgs('heatmap')
+    hm = cfgs['heatmapModel']
+    model = ref['hrnet'].get_pose_net(cfgs, is_train=True)
+    sd = hrnet_ref.make_weights(cfgs, 5)
+    model.load_state_dict(sd)
+    model.train()
+    B, K = 3, hm['num_joints']
+    x = egonet_ref.synth_crops(B, cfgs, 7)
+    g = rng(71)
+    joints = np.concatenate([g.uniform(-60, hm['input_size'][0] + 60, (B, K, 2)), np.ones((B, K, 1))], 2)
+    vis = (g.uniform(0, 1, (B, K)) > 0.2).astype(np.float32)
+    params = {'num_joints': K, 'target_type': 'gaussian', 'input_size': np.array(hm['input_size']),
+              'heatmap_size': np.array(hm['heatmap_size']), 'sigma': 2, 'use_different_joints_weight': False}
+    tgts, wts = zip(*[ref['img_proc'].generate_target(joints[b], vis[b], params) for b in range(B)])
+    target, weight = torch.from_numpy(np.stack(tgts)), torch.from_numpy(np.stack(wts))
+    out = model(x)
+    loss = LF.JointsMSELoss(True)(out, target, weight)
+    loss.backward()
+    named = dict(model.named_parameters())
+    new_sd = model.state_dict()
+    arrays = {'joints': joints, 'vis': vis, 'target': target.numpy(), 'target_weight': weight.numpy(),
+              'loss': loss.detach().numpy(), 'seed_w': 5, 'seed_x': 7, 'sigma': 2,
+              'grad_names': np.array(list(named.keys())),
+              'grad_norms': np.array([named[k].grad.double().norm().item() for k in named]),
+              'grad_sums': np.array([named[k].grad.double().sum().item() for k in named]),
+              'out_sum': np.array(out.detach().double().sum().item())}
+    for k in TRAIN_FULL_GRADS:
+        arrays['grad__' + k] = named[k].grad.numpy()
+    for k in TRAIN_STATS:
+        arrays['stat__' + k + '.running_mean'] = new_sd[k + '.running_mean'].numpy()
+        arrays['stat__' + k + '.running_var'] = new_sd[k + '.running_var'].numpy()
+        arrays['stat__' + k + '.num_batches_tracked'] = new_sd[k + '.num_batches_tracked'].numpy()
+    save('train_tiny.npz', **arrays)
+
 
 def main():
     ref = import_reference()
@@ -354,6 +398,7 @@ def main():
     golden_crop(ref)
     golden_pnp(ref)
     golden_format(ref)
+    golden_train(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,
