@@ -92,6 +92,7 @@ SIGNATURES = {
                                    POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_void_p]),
     'egn_pnp_refine': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_generate_target': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_double, c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }
 

@@ -9,8 +9,22 @@
 // HBM-bound elementwise + reduction: 8 B read (+4 B written with the gradient) per element; per-thread
 // fp64 partial sums, shuffle + shared reduction, one fp64 atomicAdd per CTA.
 #include "common.h"
+#include "target_math.h"
 
 namespace egn {
+
+// One CTA per (sample, joint) map: Gaussian dot targets of generate_target (img_proc.py:347-409), written
+// once, coalesced (64 x 64 x 4 B per map).
+__global__ void __launch_bounds__(256)
+generate_target_kernel(const double* __restrict__ joints, const float* __restrict__ vis, double in0, double in1,
+                       int hs0, int hs1, double sigma, float* __restrict__ target, float* __restrict__ weight) {
+  const int m = blockIdx.x;
+  const float v = vis ? vis[m] : (float)joints[3 * m + 2];
+  const TargetDot d = target_dot(joints[3 * m], joints[3 * m + 1], v, in0, in1, hs0, hs1, sigma);
+  if (threadIdx.x == 0 && weight) weight[m] = d.weight;
+  float* out = target + (size_t)m * hs0 * hs1;
+  for (int e = threadIdx.x; e < hs0 * hs1; e += blockDim.x) out[e] = target_value(d, e / hs1, e % hs1, hs0, hs1, sigma);
+}
 
 __global__ void __launch_bounds__(256)
 mse_hm_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const float* __restrict__ weight,
@@ -56,5 +70,21 @@ extern "C" int egn_mse_hm_fwd_bwd(const float* pred, const float* target, const 
   EGN_LAUNCH_CHECK("mse_hm_kernel");
   mse_finalize_kernel<<<1, 1, 0, st>>>(acc, loss_out);
   EGN_LAUNCH_CHECK("mse_finalize_kernel");
+  return EGN_OK;
+}
+
+extern "C" int egn_generate_target(const double* joints, const float* joints_vis, int N, int K, int input_size0,
+                                   int input_size1, int heatmap_size0, int heatmap_size1, double sigma, float* target,
+                                   float* target_weight, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(N >= 0 && K > 0 && input_size0 > 0 && input_size1 > 0 && heatmap_size0 > 0 && heatmap_size1 > 0 && sigma > 0,
+              "egn_generate_target: bad shape / sigma");
+  EGN_REQUIRE(N == 0 || (joints && target), "egn_generate_target: null pointer");
+  EGN_REQUIRE((int64_t)N * K <= 0x7fffffff, "egn_generate_target: too many maps");
+  if (int rc = require_device()) return rc;
+  if (N == 0) return EGN_OK;
+  generate_target_kernel<<<N * K, 256, 0, as_stream(stream)>>>(joints, joints_vis, (double)input_size0, (double)input_size1,
+                                                               heatmap_size0, heatmap_size1, sigma, target, target_weight);
+  EGN_LAUNCH_CHECK("generate_target_kernel");
   return EGN_OK;
 }

@@ -202,6 +202,32 @@ def crop_instances_device(images, image_of_crop, centers, scales, resolution, me
     return (out, u8) if return_u8 else out
 
 
+def generate_target_batch(joints, joints_vis, parameters):
+    """N samples of ``generate_target`` [img_proc.py:347-409] in one launch.
+    joints [N,K,3] (crop pixels), joints_vis [N,K]; parameters as upstream (num_joints, target_type,
+    input_size, heatmap_size, sigma).  Returns CUDA fp32 (target [N,K,hs[0],hs[1]], target_weight [N,K,1])."""
+    import numpy as np
+    if parameters['target_type'] != 'gaussian':
+        raise AssertionError('Only support gaussian map now!')          # as upstream :365
+    if parameters.get('use_different_joints_weight'):
+        raise NotImplementedError('use_different_joints_weight has no device implementation')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    j = torch.as_tensor(np.asarray(joints, dtype=np.float64) if not torch.is_tensor(joints) else joints,
+                        dtype=torch.float64).to(dev).contiguous()
+    v = torch.as_tensor(np.asarray(joints_vis, dtype=np.float32) if not torch.is_tensor(joints_vis) else joints_vis,
+                        dtype=torch.float32).to(dev).contiguous()
+    n, k = j.shape[0], j.shape[1]
+    if j.dim() != 3 or j.shape[2] != 3 or tuple(v.shape) != (n, k) or k != parameters['num_joints']:
+        raise ValueError('joints must be [N,K,3] and joints_vis [N,K] with K = num_joints')
+    ins, hs = parameters['input_size'], parameters['heatmap_size']
+    target = torch.empty((n, k, int(hs[0]), int(hs[1])), device=dev, dtype=torch.float32)
+    weight = torch.empty((n, k), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        N.check(N.lib().egn_generate_target(N.ptr(j), N.ptr(v), n, k, int(ins[0]), int(ins[1]), int(hs[0]), int(hs[1]),
+                                            float(parameters['sigma']), N.ptr(target), N.ptr(weight), N.current_stream()))
+    return target, weight.unsqueeze(-1)
+
+
 def to_npy(tensor):
     """[img_proc.py:722-728]"""
     return tensor if isinstance(tensor, np.ndarray) else tensor.data.cpu().numpy()

@@ -310,6 +310,16 @@ EGN_API int egn_pnp_refine(const double* kpts_3d, const double* kpts_2d, int N, 
 EGN_API int egn_mse_hm_fwd_bwd(const float* pred, const float* target, const float* target_weight, int B, int K,
                        int H, int W, float* loss_out, float* grad_out, void* workspace8, void* stream);
 
+/* Gaussian heat-map targets of the training configuration (BASELINE configs[3]).
+ * replaces generate_target libs/common/img_proc.py:347-409 (target_type 'gaussian'), one launch for N samples.
+ * joints device fp64 [N,K,3] (crop pixels; column 2 = visibility when joints_vis is NULL), joints_vis device
+ * fp32 [N,K] or NULL; input_size / heatmap_size as the reference's config lists ([0], [1]): the target is
+ * allocated [K, heatmap_size[0], heatmap_size[1]] exactly as upstream does.
+ * target device fp32 [N,K,heatmap_size0,heatmap_size1]; target_weight device fp32 [N,K] or NULL. */
+EGN_API int egn_generate_target(const double* joints, const float* joints_vis, int N, int K, int input_size0,
+                        int input_size1, int heatmap_size0, int heatmap_size1, double sigma, float* target,
+                        float* target_weight, void* stream);
+
 /* replaces the loops of EgoNet.get_observation_angle_trans / _proj (egonet.py:203-236):
  * alpha[n] = wrap(ry[n] - atan2(-z[n*stride_z], x[n*stride_x] - x_offset) - pi/2).
  * trans: x = translation[:,0], z = translation[:,2], x_offset = 0.

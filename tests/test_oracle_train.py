@@ -42,3 +42,30 @@ def test_train_step_matches_reference_golden(golden):
     # the input state dict is untouched, running statistics moved
     assert torch.equal(sd['bn1.running_mean'], hrnet_ref.make_weights(cfgs, int(g['seed_w']))['bn1.running_mean'])
     assert not torch.equal(new_sd['bn1.running_mean'], sd['bn1.running_mean'])
+
+
+def test_target_kernel_source_on_host_vs_reference_golden(golden):
+    """egonet_b200/csrc/target_math.h compiled for the host: visibility weights exact, dot geometry exact,
+    Gaussian values within 2 ulp of numpy's float32 exp (rtol 3e-7)."""
+    import ctypes
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, 'tests', 'native', 'libtarget_host.so')
+    subprocess.check_call(['g++', '-O2', '-shared', '-fPIC', '-I', os.path.join(root, 'egonet_b200', 'csrc'),
+                           os.path.join(root, 'tests', 'native', 'target_host.cpp'), '-o', so])
+    L = ctypes.CDLL(so)
+    L.host_generate_target.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [ctypes.c_void_p] * 2)
+    g = golden('train_tiny.npz')
+    hm = configs.tiny_cfgs('heatmap')['heatmapModel']
+    joints, vis = np.ascontiguousarray(g['joints']), np.ascontiguousarray(g['vis'])
+    n, k = vis.shape
+    tgt = np.zeros((n, k, hm['heatmap_size'][0], hm['heatmap_size'][1]), np.float32)
+    wgt = np.zeros((n, k), np.float32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.host_generate_target(vp(joints), vp(vis), n, k, hm['input_size'][0], hm['input_size'][1], hm['heatmap_size'][0],
+                           hm['heatmap_size'][1], float(g['sigma']), vp(tgt), vp(wgt))
+    np.testing.assert_array_equal(wgt[..., None], g['target_weight'])
+    np.testing.assert_array_equal(tgt == 0, g['target'] == 0)
+    np.testing.assert_allclose(tgt, g['target'], rtol=3e-7, atol=0)
