@@ -87,11 +87,15 @@ SIGNATURES = {
     'egn_debug_umma_rate': (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_double)]),
     'egn_debug_umma_probe': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    'egn_debug_conv_acc': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     'egn_mse_hm_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_crop_instances': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                    POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_void_p]),
     'egn_pnp_refine': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_rigid_transform': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_similarity_transform': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'egn_refine_with_bbox': (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_generate_target': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_double, c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }

@@ -921,7 +921,7 @@ int64_t egn_hrnet_weight_bytes(const egn_hrnet* h) { return h ? h->weight_bytes 
 static int conv2d_fused_impl(int impl, int dtype, const void* in, const float* w_oihw_host,
                              const float* bias_host, const void* res, void* out, int B, int H, int W,
                              int Cin, int Cout, int ksize, int stride, int relu, void* stream, int iters,
-                             float* avg_ms) {
+                             float* avg_ms, float* acc_out = nullptr) {
   using namespace egn;
   EGN_REQUIRE(in && w_oihw_host && out, "egn_conv2d_fused: null pointer");
   EGN_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "egn_conv2d_fused: bad shape");
@@ -939,6 +939,7 @@ static int conv2d_fused_impl(int impl, int dtype, const void* in, const float* w
   a.OH = (H + 2 * a.pad - ksize) / stride + 1;
   a.OW = (W + 2 * a.pad - ksize) / stride + 1;
   a.in = in; a.out = out; a.res = res;
+  a.heatmap = acc_out;
   const int taps = ksize * ksize;
   std::vector<float> wf((size_t)taps * a.Cin_p * a.Cout_p, 0.f), bias(a.Cout_p, 0.f);
   for (int o = 0; o < Cout; ++o) {
@@ -1032,4 +1033,13 @@ extern "C" int egn_conv2d_bench(int impl, int dtype, const void* in, const float
   EGN_REQUIRE(iters > 0 && avg_ms, "egn_conv2d_bench: iters must be positive");
   return conv2d_fused_impl(impl, dtype, in, w_oihw_host, bias_host, res, out, B, H, W, Cin, Cout, ksize, stride,
                            relu, stream, iters, avg_ms);
+}
+
+extern "C" int egn_debug_conv_acc(int impl, const void* in, const float* w_oihw_host, const float* bias_host,
+                                  void* out, float* acc_out, int B, int H, int W, int Cin, int Cout, int ksize,
+                                  int stride, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(acc_out, "egn_debug_conv_acc: null accumulator output");
+  return conv2d_fused_impl(impl, 1, in, w_oihw_host, bias_host, nullptr, out, B, H, W, Cin, Cout, ksize, stride, 0,
+                           stream, 0, nullptr, acc_out);
 }

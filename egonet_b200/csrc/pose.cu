@@ -47,9 +47,58 @@ __global__ void observation_angle_kernel(const double* __restrict__ ry, const do
   alpha[n] = observation_angle(ry[n], x3d[(size_t)n * stride_x] - x_offset, z3d[(size_t)n * stride_z]);
 }
 
+// one thread per instance: compute_rigid_transform / procrustes_transform (transformation.py:99-141)
+__global__ void rigid_transform_kernel(const double* __restrict__ X, const double* __restrict__ Y,
+                                       const double* __restrict__ W, int w_mode, int N, int P,
+                                       double* __restrict__ R, double* __restrict__ t, double* __restrict__ aligned) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t wstride = w_mode == 2 ? (size_t)P * P : (size_t)P;
+  rigid_transform_one(X + (size_t)n * P * 3, Y + (size_t)n * P * 3, W ? W + n * wstride : nullptr, w_mode, P,
+                      R ? R + (size_t)n * 9 : nullptr, t ? t + (size_t)n * 3 : nullptr,
+                      aligned ? aligned + (size_t)n * P * 3 : nullptr);
+}
+
+// one thread per instance: compute_similarity_transform (transformation.py:48-97)
+__global__ void similarity_transform_kernel(const double* __restrict__ X, const double* __restrict__ Y, int N, int P,
+                                            int optimal_scale, double* __restrict__ d, double* __restrict__ b,
+                                            double* __restrict__ Z, double* __restrict__ T, double* __restrict__ c) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  similarity_transform_one(X + (size_t)n * P * 3, Y + (size_t)n * P * 3, P, optimal_scale, d ? d + n : nullptr,
+                           b ? b + n : nullptr, Z ? Z + (size_t)n * P * 3 : nullptr, T ? T + (size_t)n * 9 : nullptr,
+                           c ? c + (size_t)n * 3 : nullptr);
+}
+
 }  // namespace egn
 
 extern "C" {
+
+int egn_rigid_transform(const double* X, const double* Y, const double* W, int w_mode, int N, int P, double* R_out,
+                        double* t_out, double* aligned_out, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(N >= 0 && P >= 1, "egn_rigid_transform: bad shape");
+  EGN_REQUIRE(w_mode >= 0 && w_mode <= 2 && (w_mode == 0) == (W == nullptr), "egn_rigid_transform: w_mode 0 (W null), 1 ([N,P]) or 2 ([N,P,P])");
+  EGN_REQUIRE(N == 0 || (X && Y), "egn_rigid_transform: null pointer");
+  if (int rc = require_device()) return rc;
+  if (N == 0) return EGN_OK;
+  rigid_transform_kernel<<<ceil_div(N, 64), 64, 0, as_stream(stream)>>>(X, Y, W, w_mode, N, P, R_out, t_out, aligned_out);
+  EGN_LAUNCH_CHECK("rigid_transform_kernel");
+  return EGN_OK;
+}
+
+int egn_similarity_transform(const double* X, const double* Y, int N, int P, int compute_optimal_scale, double* d_out,
+                             double* b_out, double* Z_out, double* T_out, double* c_out, void* stream) {
+  using namespace egn;
+  EGN_REQUIRE(N >= 0 && P >= 1, "egn_similarity_transform: bad shape");
+  EGN_REQUIRE(N == 0 || (X && Y), "egn_similarity_transform: null pointer");
+  if (int rc = require_device()) return rc;
+  if (N == 0) return EGN_OK;
+  similarity_transform_kernel<<<ceil_div(N, 64), 64, 0, as_stream(stream)>>>(X, Y, N, P, compute_optimal_scale ? 1 : 0,
+                                                                             d_out, b_out, Z_out, T_out, c_out);
+  EGN_LAUNCH_CHECK("similarity_transform_kernel");
+  return EGN_OK;
+}
 
 int egn_observation_angle(const double* ry, const double* x3d, int stride_x, const double* z3d,
                           int stride_z, double x_offset, int N, double* alpha, void* stream) {

@@ -117,8 +117,11 @@ EGN_HD void svd3(double A[3][3], double V[3][3], double s[3]) {
   }
 }
 
-// R = argmin ||R X + t - Y|| with the reflection fix of transformation.py:125-132
-EGN_HD void kabsch_rotation(const double H_in[3][3], double R[3][3]) {
+// R = argmin ||R X + t - Y|| with the reflection fix of transformation.py:125-132.
+// s_out (optional): singular values of H, descending; d_out (optional): the sign applied to the
+// smallest one (-1 when the unconstrained optimum is a reflection).
+EGN_HD void kabsch_rotation(const double H_in[3][3], double R[3][3], double* s_out = nullptr,
+                            double* d_out = nullptr) {
   double A[3][3], V[3][3], s[3], U[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -164,6 +167,139 @@ EGN_HD void kabsch_rotation(const double H_in[3][3], double R[3][3]) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
       R[i][j] = V[i][0] * U[j][0] + V[i][1] * U[j][1] + d * V[i][2] * U[j][2];
+  if (s_out) {
+    s_out[0] = s[0]; s_out[1] = s[1]; s_out[2] = s[2];
+  }
+  if (d_out) *d_out = d;
+}
+
+// ---------------------------------------------------------------------------
+// General point-set alignment (transformation.py:48-141), points stored [P,3] row-major.
+// ---------------------------------------------------------------------------
+// compute_rigid_transform(X, Y, W) transformation.py:99-134: least-squares R, t with Y ~ R X + t.
+// Centroids are the UNWEIGHTED means (as upstream); W is null, a [P] diagonal (w_mode 1) or a full
+// [P,P] matrix (w_mode 2): H = Xm W Ym^T.  aligned (optional, [P,3]) = R X + t, i.e. procrustes_transform
+// (transformation.py:136-141).
+EGN_HD void rigid_transform_one(const double* X, const double* Y, const double* W, int w_mode, int P,
+                                double* R_out, double* t_out, double* aligned) {
+  double cX[3] = {0, 0, 0}, cY[3] = {0, 0, 0};
+  for (int i = 0; i < P; ++i)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      cX[a] += X[3 * i + a];
+      cY[a] += Y[3 * i + a];
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    cX[a] /= P;
+    cY[a] /= P;
+  }
+  double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < P; ++i) {
+    // row i of (Xm W): for the diagonal / unweighted forms only column i of W is non-zero
+    if (w_mode == 2) {
+      for (int j = 0; j < P; ++j) {
+        const double wij = W[(size_t)i * P + j];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) H[a][b] += (X[3 * i + a] - cX[a]) * wij * (Y[3 * j + b] - cY[b]);
+      }
+    } else {
+      const double wi = w_mode == 1 ? W[i] : 1.0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) H[a][b] += (X[3 * i + a] - cX[a]) * wi * (Y[3 * i + b] - cY[b]);
+    }
+  }
+  double R[3][3];
+  kabsch_rotation(H, R);
+  double t[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) t[a] = -(R[a][0] * cX[0] + R[a][1] * cX[1] + R[a][2] * cX[2]) + cY[a];
+  if (R_out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R_out[3 * i + j] = R[i][j];
+  }
+  if (t_out) {
+    t_out[0] = t[0]; t_out[1] = t[1]; t_out[2] = t[2];
+  }
+  if (aligned) {
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        aligned[3 * i + a] = R[a][0] * X[3 * i] + R[a][1] * X[3 * i + 1] + R[a][2] * X[3 * i + 2] + t[a];
+  }
+}
+
+// compute_similarity_transform(X, Y, compute_optimal_scale) transformation.py:48-97 (MATLAB procrustes):
+// X = targets, Y = inputs, both [P,3].  out5 = {d, b}; Z [P,3] transformed Y; T [9] rotation (row-major,
+// applied on the right: Z = b * Y T + c); c [3].
+EGN_HD void similarity_transform_one(const double* X, const double* Y, int P, int optimal_scale, double* d_out,
+                                     double* b_out, double* Z, double* T_out, double* c_out) {
+  double muX[3] = {0, 0, 0}, muY[3] = {0, 0, 0};
+  for (int i = 0; i < P; ++i)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      muX[a] += X[3 * i + a];
+      muY[a] += Y[3 * i + a];
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    muX[a] /= P;
+    muY[a] /= P;
+  }
+  double ssX = 0, ssY = 0;
+  for (int i = 0; i < P; ++i)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double x = X[3 * i + a] - muX[a], y = Y[3 * i + a] - muY[a];
+      ssX += x * x;
+      ssY += y * y;
+    }
+  const double normX = sqrt(ssX), normY = sqrt(ssY);
+  // A = X0^T Y0 = U S Vt;  T = V U^T with the reflection fix on V's last column
+  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < P; ++i)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) A[a][b] += ((X[3 * i + a] - muX[a]) / normX) * ((Y[3 * i + b] - muY[b]) / normY);
+  double T[3][3], s[3], d;
+  kabsch_rotation(A, T, s, &d);
+  const double traceTA = s[0] + s[1] + d * s[2];
+  double b, dd;
+  if (optimal_scale) {
+    b = traceTA * normX / normY;
+    dd = 1.0 - traceTA * traceTA;
+  } else {
+    b = 1.0;
+    dd = 1.0 + ssY / ssX - 2.0 * traceTA * normY / normX;
+  }
+  const double zs = optimal_scale ? normX * traceTA : normY;     // Z = zs * (Y0 T) + muX
+  if (Z) {
+    for (int i = 0; i < P; ++i) {
+      const double y0 = (Y[3 * i] - muY[0]) / normY, y1 = (Y[3 * i + 1] - muY[1]) / normY,
+                   y2 = (Y[3 * i + 2] - muY[2]) / normY;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Z[3 * i + a] = zs * (y0 * T[0][a] + y1 * T[1][a] + y2 * T[2][a]) + muX[a];
+    }
+  }
+  if (T_out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) T_out[3 * i + j] = T[i][j];
+  }
+  if (c_out) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c_out[a] = muX[a] - b * (muY[0] * T[0][a] + muY[1] * T[1][a] + muY[2] * T[2][a]);
+  }
+  if (d_out) *d_out = dd;
+  if (b_out) *b_out = b;
 }
 
 EGN_HD double observation_angle(double ry, double x3d, double z3d) {

@@ -148,6 +148,13 @@ EGN_API int egn_conv2d_bench(int impl, int dtype, const void* in, const float* w
                      int Cin, int Cout, int ksize, int stride, int relu, void* stream, int iters,
                      float* avg_ms);
 
+/* Debug: one fp16 conv (no residual, no ReLU) that also writes the UN-ROUNDED fp32 result (accumulator
+ * + bias) as NCHW [B,Cout,OH,OW] to acc_out -- measures the accumulation error of the tensor-core path
+ * against an fp64 reference on fp16-exact operands (tools/probes/acc_precision.py). */
+EGN_API int egn_debug_conv_acc(int impl, const void* in, const float* w_oihw_host, const float* bias_host,
+                       void* out, float* acc_out, int B, int H, int W, int Cin, int Cout, int ksize,
+                       int stride, void* stream);
+
 /* Hardware probe (debug): SM cycles per tcgen05.mma (M=128, K=16, f16, operands in smem) when `ctas`
  * CTAs each issue iters*4*nacc MMAs of width n, rotating over nacc accumulators. */
 EGN_API int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift, int ctas, double* cycles_per_mma);
@@ -281,6 +288,24 @@ EGN_API int egn_crop_instances(const egn_image* images_dev, int n_images, const 
                        uint8_t* out_u8, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* General point-set alignment, batched       */
+/* replaces compute_rigid_transform libs/common/transformation.py:99-134,      */
+/* procrustes_transform :136-141 and compute_similarity_transform :48-97.      */
+/* All pointers device fp64; point sets are [N, P, 3] (one instance = P points */
+/* row-major; the reference's [3, P] arrays transposed).                       */
+/* ------------------------------------------------------------------------- */
+/* Y ~ R X + t.  W: NULL (w_mode 0), per-point weights [N,P] (w_mode 1) or full [N,P,P] matrices (w_mode 2);
+ * centroids are unweighted means, as upstream.  R_out [N,9] row-major, t_out [N,3], aligned_out [N,P,3]
+ * = R X + t (procrustes_transform); each may be NULL. */
+EGN_API int egn_rigid_transform(const double* X, const double* Y, const double* W, int w_mode, int N, int P,
+                        double* R_out, double* t_out, double* aligned_out, void* stream);
+/* MATLAB-style procrustes: X targets, Y inputs.  d_out [N], b_out [N], Z_out [N,P,3] (transformed Y),
+ * T_out [N,9] (Z = b * Y T + c), c_out [N,3]; each may be NULL. */
+EGN_API int egn_similarity_transform(const double* X, const double* Y, int N, int P, int compute_optimal_scale,
+                             double* d_out, double* b_out, double* Z_out, double* T_out, double* c_out,
+                             void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Reprojection refinement                                */
 /* replaces pnp_refine libs/common/transformation.py:143-157:                  */
 /*   cv2.solvePnP(prediction, observation, K, dist, SOLVEPNP_ITERATIVE)        */
@@ -294,6 +319,14 @@ EGN_API int egn_crop_instances(const egn_image* images_dev, int n_images, const 
 /* returned unrefined (upstream keeps the prediction when solvePnP fails).     */
 /* ------------------------------------------------------------------------- */
 typedef enum { EGN_PNP_STATUS_OK = 0, EGN_PNP_STATUS_PLANAR = 1, EGN_PNP_STATUS_DEGENERATE = 2 } egn_pnp_status;
+
+/* replaces refine_with_predicted_bbox tools/inference_legacy.py:518-547 for N instances: pred_rel [N,P,3] with
+ * points 1.. relative to point 0; refined [N,P,3] (absolute); ok int32 [N] = 1 when the refined root stayed
+ * within `threshold` of the predicted one (upstream returns (False, None) otherwise; refined then holds the
+ * absolute unrefined box); status as egn_pnp_refine or NULL. */
+EGN_API int egn_refine_with_bbox(const double* pred_rel, const double* kpts_2d, int N, int P, double fx, double fy,
+                         double cx, double cy, double threshold, int max_iter, double* refined, int32_t* ok,
+                         int32_t* status, void* stream);
 
 EGN_API int egn_pnp_refine(const double* kpts_3d, const double* kpts_2d, int N, int P, double fx, double fy,
                    double cx, double cy, int max_iter, double* refined, double* pose6, double* info,

@@ -154,6 +154,16 @@ def pnp_refine(prediction, observation, intrinsics, dist_coeffs=None):
     return rodrigues(r) @ np.asarray(prediction, np.float64).T + t[:, None]
 
 
+def refine_with_predicted_bbox(pred, observation, intrinsics, threshold=5.):
+    """``tools/inference_legacy.py:518-547``: pred [P,3] with points 1.. relative to point 0 ->
+    (ok, refined [3,P] or None)."""
+    box = np.array(pred, dtype=np.float64)
+    box[1:, :] += box[0, :].reshape(1, 3)
+    refined = pnp_refine(box, observation, intrinsics, None)
+    dist = np.sqrt(np.sum((refined[:, 0] - box[0, :]) ** 2))
+    return (False, None) if dist > threshold else (True, refined)
+
+
 def synth_cases(n, seed, noise_3d=0.02, noise_px=0.4, offset=0.8, points=9):
     """Seeded (prediction [n,P,3], observation [n,P,2]) pairs shaped like the reference's use: a cuboid
     (centre + 8 corners, or the 32-point cuboid + centre) seen by a KITTI camera; the prediction is the true

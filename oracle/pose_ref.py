@@ -4,6 +4,7 @@
   with ``interp_dict['bbox12']`` from ``libs/dataset/KITTI/car_instance.py:63-70``.
 * ``compute_rigid_transform`` -- ``libs/common/transformation.py:99-134`` (Kabsch;
   ``numpy.linalg.svd`` = LAPACK gesdd is third-party, same call as upstream).
+* ``procrustes_transform`` / ``compute_similarity_transform`` -- ``transformation.py:136-141`` / ``:48-97``.
 * ``euler_yxz``               -- ``EgoNet.kpts_to_euler`` ``egonet.py:265-277``:
   upstream calls ``scipy.spatial.transform.Rotation.from_matrix(R).as_euler('yxz')``
   (third-party; scipy 1.5.2 pinned upstream, 1.18.1 here) and reorders to
@@ -39,17 +40,50 @@ def get_template(prediction, interp_coef=(0.332, 0.667)):
     return corners
 
 
-def compute_rigid_transform(X, Y):
-    """Least-squares R, t with R X + t ~ Y for [3,N] point sets."""
+def compute_rigid_transform(X, Y, W=None):
+    """Least-squares R, t with R X + t ~ Y for [3,N] point sets; W optional [N] or [N,N] weights
+    (``transformation.py:112-122``: unweighted centroids, ``H = Xm W Ym^T``)."""
     cX = np.mean(X, axis=1, keepdims=True)
     cY = np.mean(Y, axis=1, keepdims=True)
-    H = (X - cX) @ (Y - cY).T
+    if W is None:
+        H = (X - cX) @ (Y - cY).T
+    else:
+        W = np.asarray(W, dtype=np.float64)
+        H = (X - cX) @ (np.diag(W) if W.ndim == 1 else W) @ (Y - cY).T
     U, S, Vt = np.linalg.svd(H)
     R = Vt.T @ U.T
     if np.linalg.det(R) < 0:
         Vt[-1, :] *= -1
         R = Vt.T @ U.T
     return R, -R @ cX + cY
+
+
+def procrustes_transform(X, Y):
+    """``transformation.py:136-141``: the rigid transform from X to Y applied to X ([3,N])."""
+    R, t = compute_rigid_transform(X, Y)
+    return R @ X + t
+
+
+def compute_similarity_transform(X, Y, compute_optimal_scale=False):
+    """``transformation.py:48-97`` (MATLAB procrustes): X targets [N,M], Y inputs [N,M] ->
+    d, Z, T, b, c."""
+    muX, muY = X.mean(0), Y.mean(0)
+    X0, Y0 = X - muX, Y - muY
+    ssX, ssY = (X0 ** 2.).sum(), (Y0 ** 2.).sum()
+    normX, normY = np.sqrt(ssX), np.sqrt(ssY)
+    X0, Y0 = X0 / normX, Y0 / normY
+    U, s, Vt = np.linalg.svd(X0.T @ Y0, full_matrices=False)
+    V = Vt.T
+    sign = np.sign(np.linalg.det(V @ U.T))
+    V[:, -1] *= sign
+    s[-1] *= sign
+    T = V @ U.T
+    tr = s.sum()
+    if compute_optimal_scale:
+        b, d, Z = tr * normX / normY, 1 - tr ** 2, normX * tr * (Y0 @ T) + muX
+    else:
+        b, d, Z = 1, 1 + ssY / ssX - 2 * tr * normY / normX, normY * (Y0 @ T) + muX
+    return d, Z, T, b, muX - b * (muY @ T)
 
 
 def euler_yxz(R):

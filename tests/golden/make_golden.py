@@ -314,6 +314,65 @@ def golden_pnp(ref):
                        tag + '_converged': np.array(conv), tag + '_digest': np.array([preds.sum(), obs.sum()])})
     save('pnp.npz', **arrays)
 
+def golden_align(ref):
+    """compute_rigid_transform (plain / diagonal W / full W / reflected), procrustes_transform,
+    compute_similarity_transform (both scale modes) of the reference on seeded point sets, and
+    refine_with_predicted_bbox (tools/inference_legacy.py:518-547) on the pnp cases."""
+    tr = ref['transformation']
+    g = rng(91)
+    arrays = {}
+    for P in (8, 9, 32):
+        n = 24
+        X = g.standard_normal((n, 3, P)) * g.uniform(0.5, 3, (n, 1, 1))
+        Y = np.zeros_like(X)
+        from scipy.spatial.transform import Rotation
+        for i in range(n):
+            Rm = Rotation.from_rotvec(g.uniform(-3, 3, 3)).as_matrix()
+            Y[i] = g.uniform(0.5, 2) * (Rm @ X[i]) + g.uniform(-5, 5, (3, 1)) + 0.1 * g.standard_normal((3, P))
+        Y[-1, 0] *= -1                       # mirrored clouds: det(R) < 0 branch
+        Y[-2, 2] *= -1
+        Wd = g.uniform(0.1, 2, (n, P))
+        Wf = g.uniform(0, 1, (n, P, P))
+        tag = 'p%d_' % P
+        arrays[tag + 'X'], arrays[tag + 'Y'], arrays[tag + 'Wd'], arrays[tag + 'Wf'] = X, Y, Wd, Wf
+        for name, Ws in (('plain', [None] * n), ('diag', Wd), ('full', Wf)):
+            Rt = [tr.compute_rigid_transform(X[i], Y[i], Ws[i]) for i in range(n)]
+            arrays[tag + name + '_R'] = np.array([r for r, _ in Rt])
+            arrays[tag + name + '_t'] = np.array([t for _, t in Rt])
+        arrays[tag + 'procrustes'] = np.array([tr.procrustes_transform(X[i], Y[i]) for i in range(n)])
+        for scale in (False, True):
+            outs = [tr.compute_similarity_transform(X[i].T.copy(), Y[i].T.copy(), scale) for i in range(n)]
+            k = tag + ('sim_scale_' if scale else 'sim_')
+            arrays[k + 'd'] = np.array([o[0] for o in outs])
+            arrays[k + 'Z'] = np.array([o[1] for o in outs])
+            arrays[k + 'T'] = np.array([o[2] for o in outs])
+            arrays[k + 'b'] = np.array([float(o[3]) for o in outs])
+            arrays[k + 'c'] = np.array([o[4] for o in outs])
+    # refine_with_predicted_bbox is defined in tools/inference_legacy.py, whose module-level imports need a
+    # display stack; the function only uses ltr.pnp_refine + numpy, so execute its source with those bound
+    import ast
+    src = open('/root/reference/tools/inference_legacy.py').read()
+    fn_src = next(ast.get_source_segment(src, n) for n in ast.parse(src).body
+                  if isinstance(n, ast.FunctionDef) and n.name == 'refine_with_predicted_bbox')
+    ns = {'np': np, 'ltr': tr}
+    exec(compile(fn_src, 'inference_legacy.refine_with_predicted_bbox', 'exec'), ns)
+    K = egonet_ref.KITTI_K
+    preds, obs = pnp_ref.synth_cases(n=32, seed=34, points=9, offset=1.5)
+    rel = preds.copy()
+    rel[:, 1:] -= rel[:, :1]
+    for thr in (5.0, 1.5):
+        oks, outs = [], []
+        for X, uv in zip(rel, obs):
+            ok, r = ns['refine_with_predicted_bbox'](X, uv, K, np.zeros((4, 1)), threshold=thr)
+            oks.append(ok)
+            outs.append(r.T if ok else np.full((9, 3), np.nan))
+        arrays['bbox_thr%g_ok' % thr] = np.array(oks)
+        arrays['bbox_thr%g_refined' % thr] = np.array(outs)
+    arrays['bbox_converged'] = np.array([pnp_ref.solve_pnp_iterative(X, uv, K)[2] < 20 for X, uv in zip(preds, obs)])
+    arrays['bbox_digest'] = np.array([rel.sum(), obs.sum()])
+    save('align.npz', **arrays)
+
+
 def golden_format(ref):
     """get_pred_str / get_instance_str of the reference (libs/common/format.py:25-61) on seeded detector rows."""
     import importlib
@@ -399,6 +458,7 @@ def main():
     golden_pnp(ref)
     golden_format(ref)
     golden_train(ref)
+    golden_align(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,

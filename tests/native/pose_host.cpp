@@ -36,4 +36,19 @@ void host_kabsch(const double* H, double* R) {
   egn::kabsch_rotation(h, r);
   for (int i = 0; i < 9; ++i) R[i] = r[i / 3][i % 3];
 }
+
+void host_rigid_transform(const double* X, const double* Y, const double* W, int w_mode, int N, int P, double* R,
+                          double* t, double* aligned) {
+  const size_t ws = w_mode == 2 ? (size_t)P * P : (size_t)P;
+  for (int n = 0; n < N; ++n)
+    egn::rigid_transform_one(X + (size_t)n * P * 3, Y + (size_t)n * P * 3, W ? W + n * ws : nullptr, w_mode, P,
+                             R + (size_t)n * 9, t + (size_t)n * 3, aligned ? aligned + (size_t)n * P * 3 : nullptr);
+}
+
+void host_similarity_transform(const double* X, const double* Y, int N, int P, int scale, double* d, double* b,
+                               double* Z, double* T, double* c) {
+  for (int n = 0; n < N; ++n)
+    egn::similarity_transform_one(X + (size_t)n * P * 3, Y + (size_t)n * P * 3, P, scale, d + n, b + n,
+                                  Z + (size_t)n * P * 3, T + (size_t)n * 9, c + (size_t)n * 3);
+}
 }
