@@ -206,12 +206,14 @@ class EgoNet(nn.Module):
         return ltr.pose_solve(pred.view(len(pred), -1, 3), k2, K, alpha_mode, want_rotation)
 
     def kpts_to_euler(self, template, prediction):
-        """[egonet.py:265-277] single instance: prediction [3,P]; returns ([x,y,z] angles, T [3,1])."""
-        pose, rot = self._solve(np.asarray(prediction).T[None], want_rotation=True)
-        R = rot[0].cpu().numpy()
-        template = np.asarray(template)
-        t = -R @ template.mean(axis=1, keepdims=True) + np.asarray(prediction).mean(axis=1, keepdims=True)
-        return pose[0, :3].cpu().numpy(), t
+        """[egonet.py:265-277] single instance, template and prediction [3,P] (any template, as upstream):
+        Kabsch on the device (``egn_rigid_transform``), Euler angles of the extrinsic 'yxz' sequence
+        reordered to [x, y, z]; returns (angles [3], T [3,1])."""
+        R, t = ltr.compute_rigid_transform(np.asarray(template, dtype=np.float64),
+                                           np.asarray(prediction, dtype=np.float64))
+        angles = np.array([math.asin(max(-1.0, min(1.0, R[2, 1]))), math.atan2(-R[2, 0], R[2, 2]),
+                           math.atan2(-R[0, 1], R[1, 1])])
+        return angles, t
 
     def get_6d_rep(self, predictions, ax=None, color="black"):
         """[egonet.py:279-295] -> (angles [N,3], translation [N,3]) fp64 numpy."""
@@ -275,6 +277,25 @@ class EgoNet(nn.Module):
                                                     save_dict=save_dict, alpha_mode=alpha_mode)
         return records
 
+    def add_orientation_arrow(self, record):
+        """[egonet.py:157-179] screen-space arrow per instance (a visualisation aid carried in the record):
+        the predicted heading (point 1 - point 5) drawn from the ground-truth centre, projected by K and
+        clipped to 60 px when longer than 50 px.  Vectorised over the instances of the image."""
+        pred = np.asarray(record['kpts_3d_pred'])
+        gt = np.asarray(record['kpts_3d_gt'])
+        K = np.asarray(record['K'])
+        n = len(pred)
+        heading = pred[:, 1] - pred[:, 5]
+        ends = np.stack([gt[:n, 0], gt[:n, 0] + heading], axis=2)          # [n,3,2]
+        proj = np.einsum('ab,nbk->nak', K, ends)
+        arrow = proj[:, :2, :] / proj[:, 2:3, :]                           # [n,2(xy),2(start,end)]
+        vec = arrow[:, :, 1] - arrow[:, :, 0]
+        length = np.linalg.norm(vec, axis=1, keepdims=True)
+        long = length[:, 0] > 50
+        vec[long] = vec[long] / length[long] * 60
+        arrow[:, :, 1] = arrow[:, :, 0] + vec
+        return arrow
+
     def write_annot_dict(self, annot_dict, records):
         """[egonet.py:181-201] pass-through of the caller's annotations."""
         for idx, path in enumerate(annot_dict['path']):
@@ -286,6 +307,8 @@ class EgoNet(nn.Module):
             for key in ('raw_txt_format', 'K'):
                 if key in annot_dict:
                     rec[key] = annot_dict[key][idx]
+            if 'kpts_3d_gt' in annot_dict and 'K' in annot_dict:
+                rec['arrow'] = self.add_orientation_arrow(rec)
         return records
 
     def forward(self, annot_dict):

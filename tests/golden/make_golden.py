@@ -370,6 +370,14 @@ def golden_align(ref):
         arrays['bbox_thr%g_refined' % thr] = np.array(outs)
     arrays['bbox_converged'] = np.array([pnp_ref.solve_pnp_iterative(X, uv, K)[2] < 20 for X, uv in zip(preds, obs)])
     arrays['bbox_digest'] = np.array([rel.sum(), obs.sum()])
+    # EgoNet.add_orientation_arrow (egonet.py:157-179) on seeded records (short and long arrows)
+    ego = ref['egonet'].EgoNet.__new__(ref['egonet'].EgoNet)
+    ga = rng(92)
+    gt = ga.standard_normal((12, 32, 3)) + np.array([0., 1., 20.])
+    gt[:, :, 2] = np.abs(gt[:, :, 2]) + 4
+    pk = gt + ga.standard_normal((12, 32, 3)) * np.linspace(0.05, 4, 12)[:, None, None]
+    arrays['arrow_pred'], arrays['arrow_gt'] = pk, gt
+    arrays['arrow'] = ego.add_orientation_arrow({'kpts_3d_pred': pk, 'kpts_3d_gt': gt, 'K': K})
     save('align.npz', **arrays)
 
 

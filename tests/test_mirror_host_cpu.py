@@ -62,3 +62,15 @@ def test_mirror_crop_geometry_matches_reference_golden(golden):
     for bad in (None, Compose([Normalize()]), Compose([ToTensor(), RandomHorizontalFlip()])):
         with pytest.raises(NotImplementedError):
             img_proc.normalize_params(bad)
+
+
+def test_add_orientation_arrow_vs_reference_golden(golden):
+    """EgoNet.add_orientation_arrow (egonet.py:157-179), host-side record field, vectorised here."""
+    from egonet_b200.libs.model.egonet import EgoNet
+    from oracle.egonet_ref import KITTI_K
+    g = golden('align.npz')
+    ego = EgoNet.__new__(EgoNet)
+    got = ego.add_orientation_arrow({'kpts_3d_pred': g['arrow_pred'], 'kpts_3d_gt': g['arrow_gt'], 'K': KITTI_K})
+    lengths = np.linalg.norm(g['arrow'][:, :, 1] - g['arrow'][:, :, 0], axis=1)
+    assert (lengths < 50).any() and np.isclose(lengths, 60).any()          # both branches present
+    np.testing.assert_allclose(got, g['arrow'], rtol=0, atol=1e-9)
