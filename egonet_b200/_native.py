@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libegonet_b200.so')
 
 EGN_MAX_BRANCHES = 4
 HEAD_HEATMAP, HEAD_COORDINATES = 0, 1
-PREC_FP32, PREC_FP16 = 0, 1
+PREC_FP32, PREC_FP16, PREC_FP16X2 = 0, 1, 2
 CONV_AUTO, CONV_SIMT = 0, 1
 SOFTARGMAX_SOFTMAX, SOFTARGMAX_SUM = 0, 1
 ALPHA_TRANS, ALPHA_PROJ = 0, 1

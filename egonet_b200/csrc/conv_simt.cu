@@ -13,70 +13,89 @@
 namespace egn {
 
 // ---------------------------------------------------------------------------
-// element helpers
+// storage policies: how a logical NHWC element (pixel, channel) of a tensor with Cp padded channels is
+// loaded / stored.  Plain<T>: one T per element.  Split16: two fp16 planes per pixel, [hi: Cp][lo: Cp]
+// (kernels.h, Dtype::F16X2); loads return hi + lo, stores write hi = rn16(v), lo = rn16(v - hi).
 // ---------------------------------------------------------------------------
-template <typename T> struct Elem;
-template <> struct Elem<float> {
-  static __device__ __forceinline__ void load4(const float* p, float v[4]) {
-    const float4 q = *reinterpret_cast<const float4*>(p);
+__device__ __forceinline__ void half4_to_float(const uint2 q, float v[4]) {
+  const __half2 a = *reinterpret_cast<const __half2*>(&q.x);
+  const __half2 b = *reinterpret_cast<const __half2*>(&q.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ uint2 float4_to_half(const float v[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]);
+  const __half2 b = __floats2half2_rn(v[2], v[3]);
+  uint2 q;
+  q.x = *reinterpret_cast<const uint32_t*>(&a);
+  q.y = *reinterpret_cast<const uint32_t*>(&b);
+  return q;
+}
+
+template <typename T> struct Plain;
+template <> struct Plain<float> {
+  using type = float;
+  static __device__ __forceinline__ void load4(const void* base, int64_t pix, int Cp, int c, float v[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + pix * Cp + c);
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
   }
-  static __device__ __forceinline__ void store4(float* p, const float v[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  static __device__ __forceinline__ void store4(void* base, int64_t pix, int Cp, int c, const float v[4]) {
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + pix * Cp + c) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  static __device__ __forceinline__ void load8(const float* p, float v[8]) {
-    load4(p, v);
-    load4(p + 4, v + 4);
+  static __device__ __forceinline__ float load1(const void* base, int64_t pix, int Cp, int c) {
+    return static_cast<const float*>(base)[pix * Cp + c];
   }
-  static __device__ __forceinline__ void store8(float* p, const float v[8]) {
-    store4(p, v);
-    store4(p + 4, v + 4);
-  }
-  static __device__ __forceinline__ float to_f(float v) { return v; }
-  static __device__ __forceinline__ float from_f(float v) { return v; }
 };
-template <> struct Elem<__half> {
-  static __device__ __forceinline__ void load4(const __half* p, float v[4]) {
-    const uint2 q = *reinterpret_cast<const uint2*>(p);
-    const __half2 a = *reinterpret_cast<const __half2*>(&q.x);
-    const __half2 b = *reinterpret_cast<const __half2*>(&q.y);
-    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+template <> struct Plain<__half> {
+  using type = __half;
+  static __device__ __forceinline__ void load4(const void* base, int64_t pix, int Cp, int c, float v[4]) {
+    half4_to_float(*reinterpret_cast<const uint2*>(static_cast<const __half*>(base) + pix * Cp + c), v);
   }
-  static __device__ __forceinline__ void store4(__half* p, const float v[4]) {
-    const __half2 a = __floats2half2_rn(v[0], v[1]);
-    const __half2 b = __floats2half2_rn(v[2], v[3]);
-    uint2 q;
-    q.x = *reinterpret_cast<const uint32_t*>(&a);
-    q.y = *reinterpret_cast<const uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = q;
+  static __device__ __forceinline__ void store4(void* base, int64_t pix, int Cp, int c, const float v[4]) {
+    *reinterpret_cast<uint2*>(static_cast<__half*>(base) + pix * Cp + c) = float4_to_half(v);
   }
-  static __device__ __forceinline__ void load8(const __half* p, float v[8]) {
-    const uint4 q = *reinterpret_cast<const uint4*>(p);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(h[i]);
-      v[2 * i] = f.x;
-      v[2 * i + 1] = f.y;
-    }
+  static __device__ __forceinline__ float load1(const void* base, int64_t pix, int Cp, int c) {
+    return __half2float(static_cast<const __half*>(base)[pix * Cp + c]);
   }
-  static __device__ __forceinline__ void store8(__half* p, const float v[8]) {
-    uint4 q;
-    __half2* h = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = q;
-  }
-  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
-  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
 };
+struct Split16 {
+  static __device__ __forceinline__ void load4(const void* base, int64_t pix, int Cp, int c, float v[4]) {
+    const __half* p = static_cast<const __half*>(base) + pix * (2 * Cp) + c;
+    float lo[4];
+    half4_to_float(*reinterpret_cast<const uint2*>(p), v);
+    half4_to_float(*reinterpret_cast<const uint2*>(p + Cp), lo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += lo[i];
+  }
+  static __device__ __forceinline__ void store4(void* base, int64_t pix, int Cp, int c, const float v[4]) {
+    __half* p = static_cast<__half*>(base) + pix * (2 * Cp) + c;
+    const uint2 hi = float4_to_half(v);
+    float h[4], lo[4];
+    half4_to_float(hi, h);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lo[i] = v[i] - h[i];
+    *reinterpret_cast<uint2*>(p) = hi;
+    *reinterpret_cast<uint2*>(p + Cp) = float4_to_half(lo);
+  }
+  static __device__ __forceinline__ float load1(const void* base, int64_t pix, int Cp, int c) {
+    const __half* p = static_cast<const __half*>(base) + pix * (2 * Cp) + c;
+    return __half2float(p[0]) + __half2float(p[Cp]);
+  }
+};
+
+// Dispatch a kernel template over the storage policy of `dt`.
+#define EGN_DISPATCH_STORAGE(dt, S, ...)                    \
+  do {                                                      \
+    if ((dt) == Dtype::F32) { using S = Plain<float>; __VA_ARGS__; }        \
+    else if ((dt) == Dtype::F16) { using S = Plain<__half>; __VA_ARGS__; }  \
+    else { using S = Split16; __VA_ARGS__; }                \
+  } while (0)
 
 // ---------------------------------------------------------------------------
 // generic conv: 64 pixels x 64 output channels per CTA, K chunks of 16
 // ---------------------------------------------------------------------------
 constexpr int CBM = 64, CBN = 64, CBK = 16, CTHREADS = 256;
 
-template <typename T>
+template <typename S>
 __global__ void __launch_bounds__(CTHREADS)
 conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
   __shared__ __align__(16) float As[CBK][CBM + 4];
@@ -87,8 +106,6 @@ conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
   const int64_t M = (int64_t)p.B * p.OH * p.OW;
   const int64_t m0 = (int64_t)blockIdx.x * CBM;
   const int n0 = blockIdx.y * CBN;
-  const T* __restrict__ in = static_cast<const T*>(p.in);
-
   // A-load role: pixel lp = t/4, channel quad lq = t%4
   const int lp = t >> 2, lq = t & 3;
   const int64_t lm = m0 + lp;
@@ -115,11 +132,11 @@ conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
     const int r = tap / p.ksize, s = tap - r * p.ksize;
     const int ih = loh * p.stride + r - p.pad, iw = low * p.stride + s - p.pad;
     const bool pv = lvalid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-    const T* src = in + (((int64_t)lb * p.H + ih) * p.W + iw) * p.Cin_p;
+    const int64_t spix = ((int64_t)lb * p.H + ih) * p.W + iw;
     const float* wt = wp + (size_t)tap * p.Cin_p * p.Cout_p;
     for (int c0 = 0; c0 < p.Cin_p; c0 += CBK) {
       float a[4] = {0.f, 0.f, 0.f, 0.f};
-      if (pv) Elem<T>::load4(src + c0 + lq * 4, a);
+      if (pv) S::load4(p.in, spix, p.Cin_p, c0 + lq * 4, a);
 #pragma unroll
       for (int c = 0; c < 4; ++c) As[lq * 4 + c][lp] = a[c];
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,8 +163,6 @@ conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
   if (n >= p.Cout_p) return;
   const float4 bias = *reinterpret_cast<const float4*>(p.bias + n);
   const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
-  T* __restrict__ out = static_cast<T*>(p.out);
-  const T* __restrict__ res = static_cast<const T*>(p.res);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + ty * 4 + i;
@@ -155,9 +170,9 @@ conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
-    if (res) {
+    if (p.res) {
       float rv[4];
-      Elem<T>::load4(res + m * p.Cout_p + n, rv);
+      S::load4(p.res, m, p.Cout_p, n, rv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += rv[j];
     }
@@ -182,17 +197,14 @@ conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
         }
       }
     }
-    Elem<T>::store4(out + m * p.Cout_p + n, v);
+    S::store4(p.out, m, p.Cout_p, n, v);
   }
 }
 
 int launch_conv_simt(Dtype dt, const ConvArgs& a, const float* w_packed, cudaStream_t st) {
   const int64_t M = (int64_t)a.B * a.OH * a.OW;
   dim3 grid((unsigned)ceil_div64(M, CBM), (unsigned)ceil_div(a.Cout_p, CBN));
-  if (dt == Dtype::F32)
-    EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<float>, grid, dim3(CTHREADS), 0, st, a, w_packed));
-  else
-    EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<__half>, grid, dim3(CTHREADS), 0, st, a, w_packed));
+  EGN_DISPATCH_STORAGE(dt, S, EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<S>, grid, dim3(CTHREADS), 0, st, a, w_packed)));
   EGN_LAUNCH_CHECK("conv_simt_kernel");
   return EGN_OK;
 }
@@ -213,7 +225,7 @@ constexpr int SPP = SPW + 1;                      // patch row pitch (floats)
 constexpr int STEM_THREADS = 256;
 constexpr int STEM_MAX_CIN = 5;
 
-template <typename T>
+template <typename S>
 __global__ void __launch_bounds__(STEM_THREADS, 2)
 stem_kernel(StemArgs p) {
   extern __shared__ __align__(16) float sm[];
@@ -275,13 +287,13 @@ stem_kernel(StemArgs p) {
   for (int i = 0; i < 4; ++i) {
     const int ox = ox0 + qc + 8 * i;
     if (ox >= p.OW) continue;
-    T* out = static_cast<T*>(p.out) + (((int64_t)b * p.OH + oy) * p.OW + ox) * 64 + cg * 4;
+    const int64_t opix = ((int64_t)b * p.OH + oy) * p.OW + ox;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = fmaxf(acc[i][q * 4 + j] + bias[q * 16 + cg * 4 + j], 0.f);
-      Elem<T>::store4(out + q * 16, v);
+      S::store4(p.out, opix, 64, cg * 4 + q * 16, v);
     }
   }
 }
@@ -290,13 +302,10 @@ int launch_stem(Dtype dt, const StemArgs& a, cudaStream_t st) {
   EGN_REQUIRE(a.Cin >= 1 && a.Cin <= STEM_MAX_CIN, "stem: unsupported input channel count %d", a.Cin);
   const size_t smem = ((size_t)a.Cin * SPH * SPP + 9 * a.Cin * 64 + 64) * sizeof(float);
   dim3 grid(ceil_div(a.OW, STW) * ceil_div(a.OH, STH), a.B);
-  if (dt == Dtype::F32) {
-    EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EGN_CUDA_CHECK(launch_pdl(stem_kernel<float>, grid, dim3(STEM_THREADS), smem, st, a));
-  } else {
-    EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EGN_CUDA_CHECK(launch_pdl(stem_kernel<__half>, grid, dim3(STEM_THREADS), smem, st, a));
-  }
+  EGN_DISPATCH_STORAGE(dt, S, {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EGN_CUDA_CHECK(launch_pdl(stem_kernel<S>, grid, dim3(STEM_THREADS), smem, st, a));
+  });
   EGN_LAUNCH_CHECK("stem_kernel");
   return EGN_OK;
 }
@@ -304,7 +313,7 @@ int launch_stem(Dtype dt, const StemArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // fuse: out = relu(sum_j up(term_j)), 4 channels per thread
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename S>
 __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs p) {
   // 8 channels (16 bytes of fp16) per thread; all terms' loads are issued before the sum so that
   // several independent requests per thread are in flight
@@ -326,7 +335,9 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs p) {
       if (j < p.nterms) {
         const int sh = p.shift[j];
         const int Hs = p.H >> sh, Ws = p.W >> sh;
-        Elem<T>::load8(static_cast<const T*>(p.term[j]) + (((int64_t)b * Hs + (h >> sh)) * Ws + (w >> sh)) * p.Cp + c, v[j]);
+        const int64_t tp = ((int64_t)b * Hs + (h >> sh)) * Ws + (w >> sh);
+        S::load4(p.term[j], tp, p.Cp, c, v[j]);
+        S::load4(p.term[j], tp, p.Cp, c + 4, v[j] + 4);
       }
     }
     float acc[8];
@@ -341,7 +352,9 @@ __global__ void __launch_bounds__(256) fuse_kernel(FuseArgs p) {
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = fmaxf(acc[q], 0.f);
-    Elem<T>::store8(static_cast<T*>(p.out) + (((int64_t)b * p.H + h) * p.W + w) * p.Cp + c, acc);
+    const int64_t op = ((int64_t)b * p.H + h) * p.W + w;
+    S::store4(p.out, op, p.Cp, c, acc);
+    S::store4(p.out, op, p.Cp, c + 4, acc + 4);
   }
 }
 
@@ -349,10 +362,7 @@ int launch_fuse(Dtype dt, const FuseArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.B * a.H * a.W * (a.Cp / 8);
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 8);
-  if (dt == Dtype::F32)
-    EGN_CUDA_CHECK(launch_pdl(fuse_kernel<float>, dim3(blocks), dim3(threads), 0, st, a));
-  else
-    EGN_CUDA_CHECK(launch_pdl(fuse_kernel<__half>, dim3(blocks), dim3(threads), 0, st, a));
+  EGN_DISPATCH_STORAGE(dt, S, EGN_CUDA_CHECK(launch_pdl(fuse_kernel<S>, dim3(blocks), dim3(threads), 0, st, a)));
   EGN_LAUNCH_CHECK("fuse_kernel");
   return EGN_OK;
 }
@@ -360,13 +370,14 @@ int launch_fuse(Dtype dt, const FuseArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // head tail: full-map valid conv + bias + sigmoid; one CTA per crop
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename S>
 __global__ void __launch_bounds__(256) head_tail_kernel(HeadTailArgs p) {
   if (threadIdx.x == 0) pdl_trigger();
   pdl_wait();
   extern __shared__ float xin[];
-  const T* in = static_cast<const T*>(p.in) + (int64_t)blockIdx.x * p.L;
-  for (int e = threadIdx.x; e < p.L; e += blockDim.x) xin[e] = Elem<T>::to_f(in[e]);
+  // the crop's [kh*kw pixels][Cp] map flattened to L = kh*kw*Cp logical elements
+  for (int e = threadIdx.x; e < p.L; e += blockDim.x)
+    xin[e] = S::load1(p.in, (int64_t)blockIdx.x * (p.L / p.Cp) + e / p.Cp, p.Cp, e % p.Cp);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = warp; j < p.Cout; j += blockDim.x / 32) {
@@ -386,13 +397,10 @@ __global__ void __launch_bounds__(256) head_tail_kernel(HeadTailArgs p) {
 int launch_head_tail(Dtype dt, const HeadTailArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)a.L * sizeof(float);
   EGN_REQUIRE(smem <= 200 * 1024, "head tail: map too large (%d elements)", a.L);
-  if (dt == Dtype::F32) {
-    EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EGN_CUDA_CHECK(launch_pdl(head_tail_kernel<float>, dim3(a.B), dim3(256), smem, st, a));
-  } else {
-    EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EGN_CUDA_CHECK(launch_pdl(head_tail_kernel<__half>, dim3(a.B), dim3(256), smem, st, a));
-  }
+  EGN_DISPATCH_STORAGE(dt, S, {
+    EGN_CUDA_CHECK(cudaFuncSetAttribute(head_tail_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EGN_CUDA_CHECK(launch_pdl(head_tail_kernel<S>, dim3(a.B), dim3(256), smem, st, a));
+  });
   EGN_LAUNCH_CHECK("head_tail_kernel");
   return EGN_OK;
 }
@@ -400,8 +408,8 @@ int launch_head_tail(Dtype dt, const HeadTailArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // NHWC (padded) -> fp32 NCHW, for debug taps
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int H,
+template <typename S>
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ in, float* __restrict__ out, int B, int H,
                                     int W, int Cp, int C) {
   const int64_t total = (int64_t)B * C * H * W;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -412,7 +420,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict_
     r /= H;
     const int c = (int)(r % C);
     const int b = (int)(r / C);
-    out[e] = Elem<T>::to_f(in[(((int64_t)b * H + h) * W + w) * Cp + c]);
+    out[e] = S::load1(in, ((int64_t)b * H + h) * W + w, Cp, c);
   }
 }
 
@@ -420,10 +428,7 @@ int launch_nhwc_to_nchw(Dtype dt, const void* in, float* out, int B, int H, int 
                         cudaStream_t st) {
   const int64_t total = (int64_t)B * C * H * W;
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16);
-  if (dt == Dtype::F32)
-    nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(in), out, B, H, W, Cp, C);
-  else
-    nhwc_to_nchw_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(in), out, B, H, W, Cp, C);
+  EGN_DISPATCH_STORAGE(dt, S, (nhwc_to_nchw_kernel<S><<<blocks, 256, 0, st>>>(in, out, B, H, W, Cp, C)));
   EGN_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return EGN_OK;
 }

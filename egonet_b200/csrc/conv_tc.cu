@@ -320,7 +320,39 @@ struct EpiArgs {
   int coord_maps, relu, Cout, Cout_p, OH, OW;
   int dbg;
   unsigned long long* ts;   // this CTA's stamp row or null
+  // fp16x2 split storage (kernels.h): res / out are [pixel][hi: Cout_p | lo: Cout_p]; the tile's products
+  // live in two accumulators `acc_stride` TMEM columns apart (hi*hi terms | the two cross terms) that are
+  // summed here in round-to-nearest fp32
+  int split;
+  uint32_t acc_stride;
 };
+
+// v -> (hi, lo) fp16 planes of 8 values each: hi = rn16(v), lo = rn16(v - hi)
+__device__ __forceinline__ void split_store8(__half* p_hi, __half* p_lo, const float (&f)[8]) {
+  uint4 h, l;
+  __half2* h2 = reinterpret_cast<__half2*>(&h);
+  __half2* l2 = reinterpret_cast<__half2*>(&l);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    const float2 hf = __half22float2(h2[j]);
+    l2[j] = __floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+  }
+  *reinterpret_cast<uint4*>(p_hi) = h;
+  *reinterpret_cast<uint4*>(p_lo) = l;
+}
+// 8 values of a split tensor: hi + lo
+__device__ __forceinline__ void split_load8_add(const __half* p_hi, const __half* p_lo, float* f) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(p_hi)), l = __ldg(reinterpret_cast<const uint4*>(p_lo));
+  const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+  const __half2* l2 = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
+    f[2 * j] += a.x + b.x;
+    f[2 * j + 1] += a.y + b.y;
+  }
+}
 
 struct EpiRow {      // where this thread's accumulator row of M-tile t lands
   bool valid;
@@ -331,7 +363,7 @@ struct EpiRow {      // where this thread's accumulator row of M-tile t lands
 constexpr int kEpiGroup = 2;  // 16-column chunks per group
 
 __device__ __forceinline__ void epi_prefetch(const EpiArgs& e, const EpiRow& r, int n, int nch, uint4 (&buf)[2 * kEpiGroup]) {
-  if (!e.res || !r.valid || (e.dbg & 2)) return;
+  if (!e.res || !r.valid || (e.dbg & 2) || e.split) return;     // split: the residual planes are read in epi_process
   const uint4* rp = reinterpret_cast<const uint4*>(e.res + r.pix * e.Cout_p + n);
 #pragma unroll
   for (int i = 0; i < 2 * kEpiGroup; ++i)
@@ -352,6 +384,18 @@ __device__ __forceinline__ void epi_process(const EpiArgs& e, const EpiRow& r, u
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[c][j] = 0;
   }
+  if (e.split && !(e.dbg & 32)) {
+    // second accumulator (cross terms) of the same columns
+#pragma unroll
+    for (int c = 0; c < kEpiGroup; ++c) {
+      if (c >= nch) break;
+      uint32_t x[16];
+      tmem_ld16(taddr + e.acc_stride + 16u * c, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[c][j] = __float_as_uint(__uint_as_float(v[c][j]) + __uint_as_float(x[j]));
+    }
+  }
   if (!r.valid) return;
 #pragma unroll
   for (int c = 0; c < kEpiGroup; ++c) {
@@ -366,7 +410,13 @@ __device__ __forceinline__ void epi_process(const EpiArgs& e, const EpiRow& r, u
       f[4 * j + 2] = __uint_as_float(v[c][4 * j + 2]) + bq.z;
       f[4 * j + 3] = __uint_as_float(v[c][4 * j + 3]) + bq.w;
     }
-    if (e.res) {
+    if (e.res && e.split) {
+      if (!(e.dbg & 2)) {
+        const __half* rp = e.res + r.pix * (size_t)(2 * e.Cout_p) + nn;
+        split_load8_add(rp, rp + e.Cout_p, f);
+        split_load8_add(rp + 8, rp + e.Cout_p + 8, f + 8);
+      }
+    } else if (e.res) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const __half2* r2 = reinterpret_cast<const __half2*>(&buf[2 * c + h]);
@@ -393,6 +443,16 @@ __device__ __forceinline__ void epi_process(const EpiArgs& e, const EpiRow& r, u
         if (nn + j == e.Cout) f[j] = e.xs[r.ow];
         if (nn + j == e.Cout + 1) f[j] = e.ys[r.oh];
       }
+    }
+    if (e.split) {
+      if (!(e.dbg & 1)) {
+        __half* op = e.out + r.pix * (size_t)(2 * e.Cout_p) + nn;
+        const float (&f0)[8] = *reinterpret_cast<const float (*)[8]>(&f[0]);
+        const float (&f1)[8] = *reinterpret_cast<const float (*)[8]>(&f[8]);
+        split_store8(op, op + e.Cout_p, f0);
+        split_store8(op + 8, op + e.Cout_p + 8, f1);
+      }
+      continue;
     }
     uint4 o[2];
     __half2* o2 = reinterpret_cast<__half2*>(o);
@@ -473,6 +533,7 @@ struct EpiLite {
   __half* out;
   uint32_t bias_s;     // shared-space address of this CTA's bias slice (n_tile floats)
   int relu, Cout_p, dbg;
+  int split;           // fp16x2 storage: res / out are [pixel][hi: Cout_p | lo: Cout_p]
 };
 
 struct LiteItem {
@@ -482,7 +543,7 @@ struct LiteItem {
 };
 
 __device__ __forceinline__ void lite_res_load(const EpiLite& e, const LiteItem& it, int n, uint4 (&rb)[2]) {
-  if (!e.res || !it.valid || (e.dbg & 2)) return;
+  if (!e.res || !it.valid || (e.dbg & 2) || e.split) return;     // split: read in lite_store
   const uint4* rp = reinterpret_cast<const uint4*>(e.res + it.pix * e.Cout_p + n);
   rb[0] = __ldg(rp);
   rb[1] = __ldg(rp + 1);
@@ -500,7 +561,13 @@ __device__ __forceinline__ void lite_store(const EpiLite& e, const LiteItem& it,
     f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bq.z;
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bq.w;
   }
-  if (e.res) {
+  if (e.res && e.split) {
+    if (!(e.dbg & 2)) {
+      const __half* rp = e.res + it.pix * (size_t)(2 * e.Cout_p) + n;
+      split_load8_add(rp, rp + e.Cout_p, f);
+      split_load8_add(rp + 8, rp + e.Cout_p + 8, f + 8);
+    }
+  } else if (e.res) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const __half2* r2 = reinterpret_cast<const __half2*>(&rb[h]);
@@ -515,6 +582,16 @@ __device__ __forceinline__ void lite_store(const EpiLite& e, const LiteItem& it,
   if (e.relu) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (e.split) {
+    if (!(e.dbg & 1)) {
+      __half* op = e.out + it.pix * (size_t)(2 * e.Cout_p) + n;
+      const float (&f0)[8] = *reinterpret_cast<const float (*)[8]>(&f[0]);
+      const float (&f1)[8] = *reinterpret_cast<const float (*)[8]>(&f[8]);
+      split_store8(op, op + e.Cout_p, f0);
+      split_store8(op + 8, op + e.Cout_p + 8, f1);
+    }
+    return;
   }
   uint4 o[2];
   __half2* o2 = reinterpret_cast<__half2*>(o);
@@ -608,6 +685,7 @@ struct EpiStage {
   uint32_t blk_bytes;  // bytes of one channel block (rows_stage * cb * 2, 1024-aligned)
   int cb;              // channels per block: 64 (128-byte rows, SWIZZLE_128B) or 48 (96-byte rows, no swizzle)
   int has_res, relu, dbg;
+  uint32_t lo_off;     // fp16x2 storage: byte offset from a hi-plane block to its lo-plane block (0 = plain fp16)
 };
 
 struct StageRow {
@@ -655,6 +733,34 @@ __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tm
       const __half2* r2 = reinterpret_cast<const __half2*>(q);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = add2(f[j], __half22float2(r2[j]));
+      if (e.lo_off) {
+        q[0] = lds_u4(a0 + e.lo_off);
+        q[1] = lds_u4(a1 + e.lo_off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = add2(f[j], __half22float2(r2[j]));
+      }
+    }
+    if (e.lo_off) {
+      // split output: relu in fp32, hi = rn16(v), lo = rn16(v - hi), both planes converted in place
+      uint4 oh[2], ol[2];
+      __half2* h2 = reinterpret_cast<__half2*>(oh);
+      __half2* l2 = reinterpret_cast<__half2*>(ol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float2 x = f[j];
+        if (e.relu) {
+          x.x = fmaxf(x.x, 0.f);
+          x.y = fmaxf(x.y, 0.f);
+        }
+        h2[j] = __float22half2_rn(x);
+        const float2 hf = __half22float2(h2[j]);
+        l2[j] = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+      }
+      sts_u4(a0, oh[0]);
+      sts_u4(a1, oh[1]);
+      sts_u4(a0 + e.lo_off, ol[0]);
+      sts_u4(a1 + e.lo_off, ol[1]);
+      return;
     }
     uint4 o[2];
     __half2* o2 = reinterpret_cast<__half2*>(o);
@@ -727,6 +833,11 @@ struct TcParams {
   const float* xs;
   const float* ys;
   int coord_maps;
+  // fp16x2 split storage: the activation tensor has cin_a = 2 * Cin_p physical channels ([hi | lo] planes) and
+  // a tap's pipeline stages are the kchunks chunks of [x_hi | x_lo] against [w_hi | w_hi] followed by the
+  // kchunks_h chunks of x_hi against w_lo (weights stored in exactly that stage order); nh = Cin_p / 16 K16
+  // slices per plane.  hi*hi products accumulate in TMEM columns [0, n_tile), the cross terms in [n_tile, 2 n_tile).
+  int split, cin_a, kchunks_h, nh;
 };
 
 template <int SW>
@@ -779,22 +890,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
-    int kcoord = 0;                                  // tap * cin_k + chunk * kc, advanced incrementally
+    int kcoord = 0;                                  // B coordinate of the stage: stages are stored back to back
+    const int kct = p.kchunks + (p.split ? p.kchunks_h : 0);      // stages per tap
     for (int r = 0; r < p.ksize; ++r) {
       for (int q = 0; q < p.ksize; ++q) {
         // stride 2: input row = 2*(oh + dh) + hp, input col = 2*(ow + dw) + wp
         const int er = r - p.pad, eq = q - p.pad;
         const int hp = er & 1, dh = (er - hp) / 2;
         const int wp = eq & 1, dw = (eq - wp) / 2;
-        for (int kcx = 0; kcx < p.kchunks; ++kcx, kcoord += p.kc) {
+        for (int kcx = 0; kcx < kct; ++kcx, kcoord += p.kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          const int c0 = kcx * p.kc;
+          const int c0 = (kcx < p.kchunks ? kcx : kcx - p.kchunks) * p.kc;
           if (elect_one()) {
             mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
             if (p.stride == 1)
               tma_load_4d(smem_a + stage * a_stage, &map_a, &full_bar[stage], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
             else
-              tma_load_5d(smem_a + stage * a_stage, &map_a, &full_bar[stage], wp * p.Cin_p + c0, ow0 + dw, hp, oh0 + dh, b0);
+              tma_load_5d(smem_a + stage * a_stage, &map_a, &full_bar[stage], wp * p.cin_a + c0, ow0 + dw, hp, oh0 + dh, b0);
             tma_load_2d(smem_b + stage * b_stage, &map_b, &full_bar[stage], kcoord, n0);
           }
           if (++stage == (uint32_t)p.stages) {
@@ -810,21 +922,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc_hi = make_smem_desc(0, SW);
     const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
-    const int n_iters = p.taps * p.kchunks;
+    const int kct = p.kchunks + (p.split ? p.kchunks_h : 0);
+    const int n_iters = p.taps * kct;
     uint32_t stage = 0, phase = 0;
+    bool acc_h = false, acc_l = false;               // accumulators already written (split mode)
+    int kcx = 0;
     for (int it = 0; it < n_iters; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint64_t adesc = desc_hi | (uint64_t)(((a_addr0 + stage * a_stage) & 0x3FFFFu) >> 4);
       const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
+      // per K16 slice of this stage (warp-uniform): valid / which accumulator / accumulate flag
+      uint32_t m_valid = 0, m_lo = 0, m_acc = 0;
+#pragma unroll
+      for (int k = 0; k < SW / 32; ++k) {
+        if (!p.split) {
+          m_valid |= 1u << k;
+          if (it | k) m_acc |= 1u << k;
+        } else {
+          const bool g2 = kcx >= p.kchunks;
+          const int sg = (g2 ? kcx - p.kchunks : kcx) * (SW / 32) + k;
+          if (sg >= (g2 ? p.nh : 2 * p.nh)) continue;        // padding slice
+          const bool lo = g2 || sg >= p.nh;
+          m_valid |= 1u << k;
+          if (lo) m_lo |= 1u << k;
+          if (lo ? acc_l : acc_h) m_acc |= 1u << k;
+          if (lo) acc_l = true; else acc_h = true;
+        }
+      }
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < SW / 32; ++k) {
           // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
-          umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          if (m_valid >> k & 1u)
+            umma_f16(tmem_base + ((m_lo >> k & 1u) ? (uint32_t)p.n_tile : 0u), adesc + (uint64_t)(2 * k),
+                     bdesc + (uint64_t)(2 * k), idesc, m_acc >> k & 1u);
         }
         umma_commit(&empty_bar[stage]);  // frees this stage once the MMAs above have read it
       }
+      if (++kcx == kct) kcx = 0;
       if (++stage == (uint32_t)p.stages) {
         stage = 0;
         phase ^= 1u;
@@ -844,7 +980,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     er.ow = ow0 + tw;
     er.valid = row < p.TW * p.TH * p.TB && er.b < p.B && er.oh < p.OH && er.ow < p.OW;
     er.pix = ((size_t)er.b * p.OH + er.oh) * p.OW + er.ow;
-    EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr};
+    EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr,
+              p.split, (uint32_t)p.n_tile};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
             [&](int) { return er; });
   }
@@ -874,6 +1011,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // every weight tile is fetched once per CTA and streamed through a small ring.
 // ---------------------------------------------------------------------------
 constexpr int kMaxChunks = 6;   // Cin_p <= 384
+constexpr int kMaxChunksPersist = 12;   // v3 has no per-chunk barriers; fp16x2 storage doubles the physical channels
 constexpr int kMaxBStages = 6;
 
 struct RunParams {
@@ -1022,7 +1160,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
-              p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr};
+              p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, 0, 0u};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), p.T, p.n_tile, n0, tmem_full_bar, [&](int t) {
       // run position -> window position -> (image, row, column); float reciprocals are exact here
       // (positions < 2^16, margins >= 0.5 / pitch)
@@ -1081,6 +1219,13 @@ struct PersistParams {
   int cb, nblk;         // channels per staging block (64 / 48), blocks per n_tile
   int rows_stage;       // TBW * THW * W pixels per window
   uint32_t blk_bytes;   // bytes of one block, 1024-aligned
+  // fp16x2 split storage (kernels.h): r.Cin_p = 2 * Cin physical channels ([x_hi | x_lo] planes, nh K16 slices each),
+  // the weight matrix holds [w_hi | w_lo] per tap in the same chunking, and a tap issues, per weight slice sb,
+  //   sb <  nh (w_hi):  A slice sb (x_hi) -> accumulator H,  A slice sb + nh (x_lo) -> accumulator L
+  //   sb >= nh (w_lo):  A slice sb - nh (x_hi) -> accumulator L
+  // (ksplit = 2: H and L are summed by the epilogue).  The staging buffer holds nblk_plane hi blocks followed by
+  // nblk_plane lo blocks (nblk = 2 * nblk_plane); out / res tensors have 2 * Cout_p physical channels.
+  int split, nh, nblk_plane;
 };
 
 // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps).
@@ -1136,19 +1281,36 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   //   x: A descriptor start-address offset from the window slot (>>4)   y: same for the weights
   //   z: TMEM column offset of the M tile   w: bit0 accumulate, bit1 first / bit2 last MMA of a weight tile
   {
-    const int ktot = (p.Cin_p + 15) >> 4;                      // K16 slices per tap
-    const int n_mma = p.taps * ktot * p.T;
+    const int ktot = (p.Cin_p + 15) >> 4;                      // K16 slices per tap (both planes in split mode)
+    const int groups = pp.split ? 3 * pp.nh : ktot;            // MMA groups (of T tiles) per tap
+    const int n_mma = p.taps * groups * p.T;
     const int ntap_w = p.halo ? 3 : 1;
     const uint32_t b_stage_t = ((uint32_t)pp.b_rows * 128u + 1023u) & ~1023u;
     for (int i = threadIdx.x; i < n_mma; i += (int)blockDim.x) {
       const int t = i % p.T, kk = i / p.T;
-      const int tap = kk / ktot, kr = kk - tap * ktot;
-      const int c = kr >> 2, k = kr & 3;
+      const int tap = kk / groups, g = kk - tap * groups;
+      // A slice sa, weight slice sb, accumulator, position of this group among the groups using weight slice sb
+      int sa = g, sb = g, lo = 0, first_of_sb = 1, last_of_sb = 1;
+      if (pp.split) {
+        if (g < 2 * pp.nh) {
+          sb = g >> 1;
+          lo = g & 1;
+          sa = sb + lo * pp.nh;
+          first_of_sb = !lo;
+          last_of_sb = lo;
+        } else {
+          sa = g - 2 * pp.nh;
+          sb = pp.nh + sa;
+          lo = 1;
+        }
+      }
+      const int ca = sa >> 2, ka = sa & 3;
+      const int c = sb >> 2, k = sb & 3;
       const int r = tap / ntap_w, q = tap - r * ntap_w;
       const int ksteps_c = (c == p.kchunks - 1) ? ktot - 4 * c : 4;
       uint4 e;
-      e.x = (((uint32_t)c * (uint32_t)p.rows_alloc * 128u + (uint32_t)(r * p.Wp + q) * 128u + (uint32_t)t * 16384u) >> 4) +
-            2u * (uint32_t)k;
+      e.x = (((uint32_t)ca * (uint32_t)p.rows_alloc * 128u + (uint32_t)(r * p.Wp + q) * 128u + (uint32_t)t * 16384u) >> 4) +
+            2u * (uint32_t)ka;
       // weight tile and K16 slot inside it: (tap, chunk) tiles in order, or -- packed -- the full chunks first and
       // then one tile per pair of taps holding both 32-channel tails (slots 0-1: even tap, 2-3: odd tap)
       uint32_t wt = (uint32_t)(tap * p.kchunks + c), ks = (uint32_t)k;
@@ -1161,8 +1323,15 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
       e.y = (pp.b_resident ? (wt * b_stage_t) >> 4 : 0u) + 2u * ks;
-      e.z = (uint32_t)(((kk % pp.ksplit) * p.T + t) * p.n_tile);
-      e.w = (kk >= pp.ksplit ? 1u : 0u) | ((k == 0 && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && t == p.T - 1) ? 4u : 0u);
+      if (pp.split) {
+        e.z = (uint32_t)((lo * p.T + t) * p.n_tile);
+        // first MMA into H is group 0 of tap 0, first into L is group 1 of tap 0
+        e.w = (tap == 0 && g == lo) ? 0u : 1u;
+      } else {
+        e.z = (uint32_t)(((kk % pp.ksplit) * p.T + t) * p.n_tile);
+        e.w = kk >= pp.ksplit ? 1u : 0u;
+      }
+      e.w |= ((k == 0 && first_of_sb && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && last_of_sb && t == p.T - 1) ? 4u : 0u);
       s_issue[i] = e;
     }
   }
@@ -1232,7 +1401,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           // ~2 windows before the epilogue reads them
           const int b0 = bg * p.TBW, h0 = win * p.THW;
           const int rows = p.TBW > 1 ? min(p.TBW, p.B - b0) * p.H : min(p.THW, p.H - h0);
-          l2_prefetch_bulk(p.res + ((size_t)b0 * p.H + h0) * p.W * p.Cout_p, (uint32_t)(rows * p.W * p.Cout_p * 2));
+          const int cpitch = pp.split ? 2 * p.Cout_p : p.Cout_p;
+          l2_prefetch_bulk(p.res + ((size_t)b0 * p.H + h0) * p.W * cpitch, (uint32_t)(rows * p.W * cpitch * 2));
         }
       }
     }
@@ -1277,7 +1447,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
       const uint64_t desc_hi = make_smem_desc(0, 128);
       const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
-      const int n_mma = p.taps * ((p.Cin_p + 15) >> 4) * p.T;
+      const int n_mma = p.taps * (pp.split ? 3 * pp.nh : ((p.Cin_p + 15) >> 4)) * p.T;
       if (pp.b_resident) mbar_wait(w_full, 0);
       uint32_t stage = 0, phase = 0;
       int j = 0;
@@ -1351,6 +1521,10 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         h0 = win * p.THW;
         b0 = bg * p.TBW;
       };
+      // first physical channel of staging block k: hi-plane blocks, then (split storage) the lo-plane blocks
+      auto blk_chan = [&](int k) {
+        return k < pp.nblk_plane ? n0 + k * pp.cb : p.Cout_p + n0 + (k - pp.nblk_plane) * pp.cb;
+      };
       auto fill = [&](int jj) {                 // buffer jj % S is free: fetch window jj's residual (or just release it)
         const int sb = jj % S;
         if (has_res) {
@@ -1359,7 +1533,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_expect_tx(&stage_full[sb], (uint32_t)pp.nblk * (uint32_t)(pp.rows_stage * pp.cb * 2));
           for (int k = 0; k < pp.nblk; ++k)
             tma_load_4d(smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, &map_res, &stage_full[sb],
-                        n0 + k * pp.cb, 0, h0, b0);
+                        blk_chan(k), 0, h0, b0);
         } else {
           mbar_arrive(&stage_full[sb]);
         }
@@ -1372,7 +1546,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           int h0, b0;
           coords(jj, h0, b0);
           for (int k = 0; k < pp.nblk; ++k)
-            tma_store_4d(&map_out, smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, n0 + k * pp.cb, 0, h0,
+            tma_store_4d(&map_out, smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, blk_chan(k), 0, h0,
                          b0);
           bulk_commit();
           bulk_wait_read0();                      // smem of this buffer has been read: it may be refilled
@@ -1391,8 +1565,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
-              nullptr};
-    const EpiLite el{p.res, p.out, smem_u32(s_bias), p.relu, p.Cout_p, p.dbg};
+              nullptr, pp.split, (uint32_t)(p.T * p.n_tile)};
+    const EpiLite el{p.res, p.out, smem_u32(s_bias), p.relu, p.Cout_p, p.dbg, pp.split};
     const uint32_t acc_empty_leader[2] = {kPair ? mapa_rank(&acc_empty[0], 0) : 0u, kPair ? mapa_rank(&acc_empty[1], 0) : 0u};
     int j = 0;
     for (int wb = w0; wb < pp.n_windows; wb += gridDim.x, ++j) {
@@ -1434,7 +1608,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (pp.n_stage) {
           const int sb = j % pp.n_stage;
           const EpiStage es{smem_u32(smem_stage) + (uint32_t)sb * stage_bytes, smem_u32(s_bias), pp.blk_bytes, pp.cb,
-                            p.res != nullptr && !(p.dbg & 2), p.relu, p.dbg};
+                            p.res != nullptr && !(p.dbg & 2), p.relu, p.dbg,
+                            pp.split ? (uint32_t)pp.nblk_plane * pp.blk_bytes : 0u};
           mbar_wait(&stage_full[sb], (uint32_t)((j / pp.n_stage) & 1));
           mbar_wait(&acc_full[slot], ph);
           tc_fence_after();
@@ -1500,6 +1675,9 @@ static EncodeTiledFn get_encode_fn() {
 struct TcConvPlan {
   // shape (batch independent)
   int H, W, Cin_p, OH, OW, Cout_p, Cout, ksize, stride, pad;
+  bool split = false;   // fp16x2 storage: cin_a = 2 * Cin_p physical input channels, 2 * Cout_p physical output channels
+  int cin_a = 0;        // physical channels of the activation tensor
+  int kchunks_h = 0;    // v1, split: chunks of the x_hi * w_lo stage group
   int sw;          // swizzle bytes 32 / 64 / 128
   int kc, kchunks, cin_k, n_tile, n_tiles, stages;
   int TW, TH, TB;
@@ -1558,27 +1736,33 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   TcConvPlan* p = new TcConvPlan();
   p->H = a.H; p->W = a.W; p->Cin_p = a.Cin_p; p->OH = a.OH; p->OW = a.OW;
   p->Cout_p = a.Cout_p; p->Cout = a.Cout; p->ksize = a.ksize; p->stride = a.stride; p->pad = a.pad;
+  p->split = a.split != 0;
+  const bool split = p->split;
+  const int cin_a = split ? 2 * a.Cin_p : a.Cin_p;
+  p->cin_a = cin_a;
   // Always 128-byte swizzle rows (64 channels per pipeline stage).  When Cin is not a multiple of
   // 64 the last chunk of a tap is partial: the weight matrix is zero-padded per tap to a multiple
   // of 64 channels, so whatever the activation box holds in those lanes (TMA zero fill past the
   // channel extent, or the neighbouring pixel's channels in the stride-2 view) is multiplied by 0.
   const int force_sw = getenv("EGN_TC_SWIZZLE") ? atoi(getenv("EGN_TC_SWIZZLE")) : 0;
   p->sw = force_sw ? force_sw : 128;
-  if (force_sw == 0 && a.Cin_p <= 16) p->sw = 32;
-  else if (force_sw == 0 && a.Cin_p <= 32) p->sw = 64;
+  if (force_sw == 0 && cin_a <= 16) p->sw = 32;
+  else if (force_sw == 0 && cin_a <= 32) p->sw = 64;
   p->kc = p->sw / 2;
-  p->kchunks = ceil_div(a.Cin_p, p->kc);
+  p->kchunks = ceil_div(cin_a, p->kc);
+  p->kchunks_h = split ? ceil_div(a.Cin_p, p->kc) : 0;
+  // split mode keeps two accumulators per tile (hi*hi | cross terms): at most 256 columns each in v1
   p->n_tiles = a.Cout_p > 256 ? 2 : 1;
   p->n_tile = a.Cout_p / p->n_tiles;
   p->TW = std::min(a.OW, 128);
   p->TH = std::min(a.OH, 128 / p->TW);
   p->TB = p->TH == a.OH ? std::max(1, 128 / (p->TW * p->TH)) : 1;
-  p->tmem_cols = pow2_cols(p->n_tile);
+  p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
   const size_t a_stage = 128 * (size_t)p->sw;
   const size_t b_stage = ((size_t)p->n_tile * p->sw + 1023) & ~(size_t)1023;
   const size_t stage = a_stage + b_stage;
   const size_t budget = stage > 24 * 1024 ? 176 * 1024 : 80 * 1024;
-  const int n_iters = a.ksize * a.ksize * p->kchunks;
+  const int n_iters = a.ksize * a.ksize * (p->kchunks + p->kchunks_h);
   size_t st_count = std::min<size_t>((size_t)kMaxStages, budget / stage);
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
   p->stages = (int)std::max<size_t>(2, st_count);
@@ -1586,7 +1770,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   // ---- v2 window-run configuration (stride-1 convs) ----
   {
     const char* env = getenv("EGN_TC_V2");
-    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks;
+    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks && !split;
     if (allow) {
       const int halo = a.ksize == 3 ? 1 : 0;
       const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
@@ -1652,7 +1836,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->use_run ? "v2-run" : "v1-tap", p->T, p->THW, p->TBW, p->run_eff,
                 p->smem_bytes / 1024, p->b_stages, p->tmem_cols);
       if (!p->use_run) {
-        p->tmem_cols = pow2_cols(p->n_tile);
+        p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
         p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
       }
     }
@@ -1663,8 +1847,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   // both).  Streaming the weights per window instead costs more L2->SM bandwidth than it saves.
   {
     const char* env = getenv("EGN_TC_V3");
-    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks &&
+    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunksPersist &&
                        (a.ksize == 1 ? a.W >= 32 : a.W >= 24);
+    const int nacc = split ? 2 : 1;                  // accumulators per M tile
+    const int kslices = (cin_a + 15) / 16;           // K16 slices of a tap's weight row
+    const int groups = split ? 3 * (a.Cin_p / 16) : kslices;   // MMA groups per tap
     if (allow) {
       const int halo = a.ksize == 3 ? 1 : 0;
       const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
@@ -1680,9 +1867,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         const int n_tiles = base_tiles * split;
         if (a.Cout_p % (16 * n_tiles)) continue;
         const int n_tile = a.Cout_p / n_tiles;
-        if (n_tile > 256 || n_tile < 16) continue;
+        if (n_tile > 256 / nacc || n_tile < 16) continue;
         const size_t b_stage_bytes = ((size_t)n_tile * 128 + 1023) & ~(size_t)1023;
-        const int Tmax = std::min(8, 256 / n_tile);
+        const int Tmax = std::min(8, 256 / nacc / n_tile);
         for (int T = 1; T <= Tmax; ++T) {
           for (int multi = 0; multi < 2; ++multi) {
             int THW, TBW;
@@ -1703,9 +1890,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
             const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
             const size_t fixed = 1024 + 256 + (size_t)n_tile * 4 +
-                                 (size_t)a.ksize * a.ksize * ((a.Cin_p + 15) / 16) * T * 16;   // barriers, bias, issue table
+                                 (size_t)a.ksize * a.ksize * groups * T * 16;   // barriers, bias, issue table
             // resident weights: the 32-channel tail chunks of a 3x3 conv are packed two taps per tile
-            const bool can_pack = a.ksize == 3 && p->kchunks >= 2 && a.Cin_p % 64 == 32 && !getenv("EGN_TC_NOPACK");
+            const bool can_pack = a.ksize == 3 && p->kchunks >= 2 && cin_a % 64 == 32 && !getenv("EGN_TC_NOPACK");
             const int w_tiles_res = can_pack ? a.ksize * a.ksize * (p->kchunks - 1) + (a.ksize * a.ksize + 1) / 2 : w_tiles;
             size_t smem = a_bytes + (size_t)w_tiles_res * b_stage_bytes + fixed;
             int resident = 1, bst = 0;
@@ -1740,14 +1927,14 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const int n_win = windows * ceil_div(256, TBW);
             const double mma_cyc = n_tile <= 32 ? 40.0 : n_tile <= 64 ? 40.0 + (n_tile - 32) * 0.25
                                  : n_tile <= 128 ? 48.0 + (n_tile - 64) * 0.25 : 64.0 + (n_tile - 128) * 0.68;
-            const double t_mma = (double)a.ksize * a.ksize * ((a.Cin_p + 15) / 16) * T * mma_cyc;
+            const double t_mma = (double)a.ksize * a.ksize * groups * T * mma_cyc;
             const double t_w = resident ? 0.0 : (double)w_tiles * 2400.0;
             const double t_a = (double)p->kchunks * rows_win * 128 / 48.0;      // window load, ~48 B/cycle/SM
             for (int S = max_stage; S >= 0; --S) {
               if (S && !cb) continue;
-              const size_t smem_s = smem + (size_t)S * nblk * blk_bytes;
+              const size_t smem_s = smem + (size_t)S * nblk * blk_bytes * nacc;     // split: hi and lo planes staged
               if (smem_s > smem_cap) continue;
-              const double t_epi = (double)T * (n_tile / 16) * (S ? 100.0 : 250.0);
+              const double t_epi = (double)T * (n_tile / 16) * (S ? 100.0 : 250.0) * nacc;
               const double t_win = std::max(std::max(S ? t_mma : 1.5 * t_mma, t_epi), std::max(t_w, t_a)) +
                                    (S == 1 ? 4000.0 : 0.0) + 300.0;
               const double est = ceil_div(n_win * n_tiles, 148) * t_win;
@@ -1760,7 +1947,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
                 p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
                 p->smem_bytes = smem_s;
-                p->tmem_cols = pow2_cols(2 * T * n_tile);
+                p->tmem_cols = pow2_cols(2 * nacc * T * n_tile);
                 p->n_stage = S; p->cb = cb; p->nblk = nblk; p->rows_stage = rows_stage; p->blk_bytes = (uint32_t)blk_bytes;
                 p->pack_tail = resident && can_pack;
                 p->w_tiles = resident ? w_tiles_res : w_tiles;
@@ -1781,11 +1968,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       {
         const char* pe = getenv("EGN_TC_PAIR");
         // per CTA the pair keeps the split's weights and windows but stages / biases the full N
-        const size_t pair_smem = p->smem_bytes + (size_t)p->n_stage * p->nblk * p->blk_bytes + 4 * (size_t)p->n_tile;
+        const size_t pair_smem = p->smem_bytes + (size_t)p->n_stage * p->nblk * p->blk_bytes * nacc + 4 * (size_t)p->n_tile;
         p->use_pair = p->use_persist && !(pe && atoi(pe) == 0) && base_tiles == 1 && p->n_tiles == 2 && p->b_resident &&
-                      (2 * p->n_tile) % 16 == 0 && 2 * p->T * 2 * p->n_tile <= 512 && pair_smem <= 227 * 1024;
+                      (2 * p->n_tile) % 16 == 0 && 2 * nacc * p->T * 2 * p->n_tile <= 512 && pair_smem <= 227 * 1024;
         if (p->use_pair) p->pair_smem = pair_smem;
-        if (p->use_pair) p->tmem_cols = pow2_cols(2 * p->T * 2 * p->n_tile);
+        if (p->use_pair) p->tmem_cols = pow2_cols(2 * nacc * p->T * 2 * p->n_tile);
       }
       if (getenv("EGN_TC_VERBOSE") && p->use_persist && p->use_pair) fprintf(stderr, "[egn] (next line) CTA-pair mode\n");
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
@@ -1795,21 +1982,43 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->blk_bytes, p->cb);
     }
   }
-  // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][tap][Cin_k] fp16, Cin_k = kchunks * kc (zero padded)
+  // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][K] fp16, zero padded to whole kc-channel chunks.
+  //   plain fp16           K = taps * cin_k, tap row = [w (Cin_p)]
+  //   fp16x2, v3           K = taps * cin_k, tap row = [w_hi (Cin_p) | w_lo (Cin_p)]   (cross pairing by the issue table)
+  //   fp16x2, v1           K = taps * (kchunks + kchunks_h) * kc, tap row = [w_hi | w_hi] chunks, then [w_lo] chunks
+  //                        (stage order of conv_tc_kernel: A = [x_hi | x_lo] then A = x_hi again)
+  // w_hi = rn16(w), w_lo = rn16(w - w_hi).
   const int taps = a.ksize * a.ksize;
   const int cin_k = p->kchunks * p->kc;
   p->cin_k = cin_k;
   const bool pack = p->use_persist && p->pack_tail;
+  const bool v1_split = split && !p->use_persist;
   const int full_k = (p->kchunks - 1) * 64;              // channels of a tap that live in full 64-wide chunks
-  const size_t K = pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * cin_k;
+  const size_t tap_k = v1_split ? (size_t)(p->kchunks + p->kchunks_h) * p->kc : (size_t)cin_k;
+  const size_t K = pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * tap_k;
   std::vector<__half> w((size_t)a.Cout_p * K, __float2half_rn(0.f));
   for (int o = 0; o < a.Cout_p; ++o)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < a.Cin_p; ++c) {
-        size_t k = (size_t)t * cin_k + c;
-        if (pack) k = c < full_k ? (size_t)t * full_k + c
-                                 : (size_t)taps * full_k + (size_t)(t >> 1) * 64 + (size_t)(t & 1) * 32 + (c - full_k);
-        w[(size_t)o * K + k] = __float2half_rn(wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o]);
+        const float wv = wf[((size_t)t * a.Cin_p + c) * a.Cout_p + o];
+        const __half hi = __float2half_rn(wv);
+        const __half lo = __float2half_rn(wv - __half2float(hi));
+        auto put = [&](int pos, __half v) {              // pos: channel position inside the tap row
+          size_t k = (size_t)t * tap_k + pos;
+          if (pack) k = pos < full_k ? (size_t)t * full_k + pos
+                                     : (size_t)taps * full_k + (size_t)(t >> 1) * 64 + (size_t)(t & 1) * 32 + (pos - full_k);
+          w[(size_t)o * K + k] = v;
+        };
+        if (!split) {
+          put(c, hi);
+        } else if (!v1_split) {
+          put(c, hi);
+          put(a.Cin_p + c, lo);
+        } else {
+          put(c, hi);
+          put(a.Cin_p + c, hi);
+          put(p->kchunks * p->kc + c, lo);
+        }
       }
   p->w_bytes = w.size() * sizeof(__half);
   if (cudaMalloc(&p->d_w, p->w_bytes) != cudaSuccess ||
@@ -1845,7 +2054,7 @@ size_t tc_conv_plan_weight_bytes(const TcConvPlan* p) { return p ? p->w_bytes : 
 // [B][OH][OW][Cout_p] tensor seen through the staging box of the persistent kernel's TMA epilogue
 static int make_io_map(TcConvPlan* p, const void* ptr, int B, CUtensorMap* m) {
   EncodeTiledFn enc = get_encode_fn();
-  const cuuint64_t C = p->Cout_p, W = p->OW, H = p->OH;
+  const cuuint64_t C = (p->split ? 2 : 1) * p->Cout_p, W = p->OW, H = p->OH;     // fp16x2: [hi | lo] planes
   const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
   const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
   const cuuint32_t box[4] = {(cuuint32_t)p->cb, (cuuint32_t)p->OW, (cuuint32_t)p->THW, (cuuint32_t)p->TBW};
@@ -1863,7 +2072,7 @@ static int make_io_map(TcConvPlan* p, const void* ptr, int B, CUtensorMap* m) {
 
 static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   EncodeTiledFn enc = get_encode_fn();
-  const cuuint64_t C = p->Cin_p, W = p->W, H = p->H;
+  const cuuint64_t C = p->cin_a, W = p->W, H = p->H;      // physical channels (fp16x2: [hi | lo] planes)
   CUresult r;
   if (p->use_run || p->use_persist) {
     const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
@@ -1932,7 +2141,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   if (p->use_persist) {
     PersistParams pp{};
     RunParams& rp = pp.r;
-    rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->Cin_p;
+    rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->cin_a;
     rp.taps = p->ksize * p->ksize; rp.relu = a.relu;
     rp.halo = p->halo; rp.Wp = p->Wp; rp.Hw = p->Hw; rp.THW = p->THW; rp.TBW = p->TBW;
     rp.win_per_img = ceil_div(p->H, p->THW);
@@ -1951,6 +2160,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.out = static_cast<__half*>(a.out);
     rp.heatmap = a.heatmap; rp.xs = a.xs; rp.ys = a.ys; rp.coord_maps = a.coord_maps;
     rp.dbg = getenv("EGN_TC_DBG") ? atoi(getenv("EGN_TC_DBG")) : 0;
+    pp.split = p->split ? 1 : 0;
+    pp.nh = p->Cin_p / 16;
     // L2 bulk prefetch of the residual rows by the A producer (direct, non-staged epilogue only):
     // EGN_TC_RES_PREFETCH = 2 (default) only when the output channels are not split over blockIdx.y, 1 always,
     // 0 never.  A split layer would prefetch the all-channel rows once per half -- 2x the residual DRAM traffic
@@ -1984,12 +2195,15 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
         ks = ks_env;
         while (ks > 1 && (2 * ks * p->T * rp.n_tile > 512 || ks > ksteps)) --ks;
       }
+      if (p->split) ks = 2;          // fp16x2: accumulator H (hi*hi) and L (cross terms), summed by the epilogue
       pp.ksplit = ks;
       rp.tmem_cols = pow2_cols(2 * ks * p->T * rp.n_tile);
     }
     CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
     if (p->n_stage && !head) {
-      pp.n_stage = p->n_stage; pp.cb = p->cb; pp.nblk = pair ? 2 * p->nblk : p->nblk; pp.rows_stage = p->rows_stage;
+      pp.n_stage = p->n_stage; pp.cb = p->cb; pp.rows_stage = p->rows_stage;
+      pp.nblk_plane = pair ? 2 * p->nblk : p->nblk;
+      pp.nblk = (p->split ? 2 : 1) * pp.nblk_plane;
       pp.blk_bytes = p->blk_bytes;
       std::lock_guard<std::mutex> lock(p->mu);
       for (int which = 0; which < 2; ++which) {
@@ -2103,6 +2317,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   }
   TcParams tp{};
   tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
+  tp.split = p->split ? 1 : 0; tp.cin_a = p->cin_a; tp.kchunks_h = p->kchunks_h; tp.nh = p->Cin_p / 16;
   tp.taps = p->ksize * p->ksize; tp.ksize = p->ksize; tp.stride = p->stride; tp.pad = p->pad; tp.relu = a.relu;
   tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
   tp.tiles_w = ceil_div(p->OW, p->TW);

@@ -533,6 +533,7 @@ static ConvArgs conv_shape(const egn_hrnet* h, const Op& op, int B) {
   a.pad = op.pad;
   a.relu = op.relu;
   a.coord_maps = op.coord_maps ? 1 : 0;
+  a.split = h->dt == Dtype::F16X2 ? 1 : 0;
   return a;
 }
 
@@ -625,6 +626,7 @@ static int run_ops(egn_hrnet* h, const float* x, int batch, float* heatmap_out, 
         a.logits = logits_out;
         a.B = batch;
         a.L = ti.H * ti.W * ti.Cp;
+        a.Cp = ti.Cp;
         a.Cout = h->weights[op.wi].Cout;
         if (int rc = launch_head_tail(h->dt, a, st)) return rc;
         break;
@@ -667,11 +669,12 @@ int egn_hrnet_create(const egn_hrnet_cfg* cfg, egn_hrnet** out) {
                   "branch widths must stay constant across stages");
     }
   }
-  EGN_REQUIRE(c.precision == EGN_PREC_FP32 || c.precision == EGN_PREC_FP16, "unknown precision %d", c.precision);
+  EGN_REQUIRE(c.precision == EGN_PREC_FP32 || c.precision == EGN_PREC_FP16 || c.precision == EGN_PREC_FP16X2,
+              "unknown precision %d", c.precision);
   EGN_REQUIRE(c.conv_impl == EGN_CONV_AUTO || c.conv_impl == EGN_CONV_SIMT, "unknown conv_impl %d", c.conv_impl);
   egn_hrnet* h = new egn_hrnet();
   h->cfg = c;
-  h->dt = c.precision == EGN_PREC_FP32 ? Dtype::F32 : Dtype::F16;
+  h->dt = c.precision == EGN_PREC_FP32 ? Dtype::F32 : (c.precision == EGN_PREC_FP16 ? Dtype::F16 : Dtype::F16X2);
   build_keys(h);
   if (int rc = build_graph(h)) {
     set_error("egn_hrnet_create: %s", h->build_error.c_str());
@@ -683,7 +686,7 @@ int egn_hrnet_create(const egn_hrnet_cfg* cfg, egn_hrnet** out) {
   // which convs go to the tensor cores
   for (Op& op : h->ops) {
     if (op.kind != Op::CONV) continue;
-    op.use_tc = c.precision == EGN_PREC_FP16 && c.conv_impl == EGN_CONV_AUTO &&
+    op.use_tc = c.precision != EGN_PREC_FP32 && c.conv_impl == EGN_CONV_AUTO &&
                 tc_conv_supported(conv_shape(h, op, 1));
     if (op.use_tc) ++h->n_tc;
   }
@@ -899,7 +902,7 @@ int egn_hrnet_op_info(const egn_hrnet* h, int i, egn_op_info* o) {
     o->ksize = kh;
     const int64_t opix = op.kind == Op::TAIL ? 1 : (int64_t)o->OH * o->OW;
     o->macs = (int64_t)w.Cout * w.Cin * kh * kw * opix;
-    o->weight_bytes = (int64_t)w.Cout_p * w.Cin_p * kh * kw * ((op.kind == Op::CONV && !w.force_fp32 && h->dt == Dtype::F16 && op.use_tc) ? 2 : 4);
+    o->weight_bytes = (int64_t)w.Cout_p * w.Cin_p * kh * kw * ((op.kind == Op::CONV && !w.force_fp32 && h->dt == Dtype::F16 && op.use_tc) ? 2 : 4);   // fp16x2: hi + lo = 4 bytes
     snprintf(o->name, sizeof(o->name), "%s", w.conv_key.c_str());
   } else if (op.kind == Op::FUSE) {
     snprintf(o->name, sizeof(o->name), "%s", h->tensors[op.out].tap.c_str());
@@ -927,8 +930,9 @@ static int conv2d_fused_impl(int impl, int dtype, const void* in, const float* w
   EGN_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "egn_conv2d_fused: bad shape");
   EGN_REQUIRE(ksize == 1 || ksize == 3, "egn_conv2d_fused: ksize must be 1 or 3");
   EGN_REQUIRE(stride == 1 || stride == 2, "egn_conv2d_fused: stride must be 1 or 2");
-  EGN_REQUIRE(dtype == 0 || dtype == 1, "egn_conv2d_fused: dtype 0 (fp32) or 1 (fp16)");
-  EGN_REQUIRE(impl == 0 || (impl == 1 && dtype == 1), "egn_conv2d_fused: the tcgen05 path is fp16 only");
+  EGN_REQUIRE(dtype >= 0 && dtype <= 2, "egn_conv2d_fused: dtype 0 (fp32), 1 (fp16) or 2 (fp16x2)");
+  EGN_REQUIRE(impl == 0 || (impl == 1 && dtype != 0), "egn_conv2d_fused: the tcgen05 path is fp16 / fp16x2 only");
+  const Dtype dt = dtype == 0 ? Dtype::F32 : (dtype == 1 ? Dtype::F16 : Dtype::F16X2);
   if (int rc = require_device()) return rc;
   ConvArgs a{};
   a.B = B; a.H = H; a.W = W;
@@ -939,6 +943,7 @@ static int conv2d_fused_impl(int impl, int dtype, const void* in, const float* w
   a.OH = (H + 2 * a.pad - ksize) / stride + 1;
   a.OW = (W + 2 * a.pad - ksize) / stride + 1;
   a.in = in; a.out = out; a.res = res;
+  a.split = dtype == 2 ? 1 : 0;
   a.heatmap = acc_out;
   const int taps = ksize * ksize;
   std::vector<float> wf((size_t)taps * a.Cin_p * a.Cout_p, 0.f), bias(a.Cout_p, 0.f);
@@ -992,13 +997,13 @@ static int conv2d_fused_impl(int impl, int dtype, const void* in, const float* w
       rc = EGN_ERR_CUDA;
     } else {
       cudaMemcpy(d_w, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice);
-      rc = launch_conv_simt(dtype == 0 ? Dtype::F32 : Dtype::F16, a, d_w, st);
+      rc = launch_conv_simt(dt, a, d_w, st);
       if (!rc && iters > 0) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, st);
-        for (int i = 0; i < iters && !rc; ++i) rc = launch_conv_simt(dtype == 0 ? Dtype::F32 : Dtype::F16, a, d_w, st);
+        for (int i = 0; i < iters && !rc; ++i) rc = launch_conv_simt(dt, a, d_w, st);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;

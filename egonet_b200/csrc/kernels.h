@@ -10,9 +10,14 @@
 
 namespace egn {
 
-enum class Dtype : int { F32 = 0, F16 = 1 };
+// Activation storage.  F16X2 ("split"): every logical element is an unevaluated sum hi + lo of two fp16 values
+// (hi = rn16(v), lo = rn16(v - hi): ~22 significant bits), stored per pixel as two planes [hi: Cp][lo: Cp] --
+// physically an fp16 NHWC tensor with 2 * Cp channels.  The tensor-core kernels then compute
+// x * w = x_hi * w_hi + x_lo * w_hi + x_hi * w_lo (three fp16 MMAs into the same fp32 accumulator), which holds the
+// reference's fp32 results to ~1e-6 relative per layer.
+enum class Dtype : int { F32 = 0, F16 = 1, F16X2 = 2 };
 
-inline size_t dtype_size(Dtype d) { return d == Dtype::F32 ? 4 : 2; }
+inline size_t dtype_size(Dtype d) { return d == Dtype::F16 ? 2 : 4; }   // bytes per logical element
 
 // One fused conv launch: out = act(conv(in, w) + bias [+ res]).
 struct ConvArgs {
@@ -22,6 +27,7 @@ struct ConvArgs {
   const float* bias;     // [Cout_p] fp32, BN shift folded in, zero in pad lanes
   int B, H, W, Cin_p, OH, OW, Cout_p, Cout;
   int ksize, stride, pad, relu;
+  int split;             // 1: in / res / out are F16X2 split tensors (tcgen05 path: error-compensated MMAs)
   // head1 extras
   float* heatmap;        // fp32 NCHW [B, Cout, OH, OW] copy of the un-rounded result, or null
   const float* xs;       // [OW] / [OH] coordinate-map values written to channels
@@ -60,7 +66,7 @@ struct HeadTailArgs {
   const float* bias;     // [Cout]
   float* coords;         // [B, Cout] sigmoid output, or null
   float* logits;         // [B, Cout] or null
-  int B, L, Cout;        // L = kh*kw*Cp
+  int B, L, Cout, Cp;    // L = kh*kw*Cp logical elements per crop
 };
 int launch_head_tail(Dtype dt, const HeadTailArgs& a, cudaStream_t st);
 

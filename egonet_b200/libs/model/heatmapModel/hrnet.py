@@ -66,7 +66,7 @@ def _engine_cfg(cfgs, in_channels, precision, conv_impl, keep_taps):
     return c
 
 
-_PRECISIONS = {'fp32': N.PREC_FP32, 'fp16': N.PREC_FP16}
+_PRECISIONS = {'fp32': N.PREC_FP32, 'fp16': N.PREC_FP16, 'fp16x2': N.PREC_FP16X2}
 
 
 class PoseHighResolutionNet(nn.Module):

@@ -64,12 +64,17 @@ EGN_API int egn_device_ok(void);
 typedef enum { EGN_HEAD_HEATMAP = 0, EGN_HEAD_COORDINATES = 1 } egn_head_type;
 
 typedef enum {
-  EGN_PREC_FP32 = 0, /* fp32 storage + fp32 CUDA-core convs: the 1e-4 parity mode */
-  EGN_PREC_FP16 = 1  /* fp16 NHWC storage, fp32 accumulation, tcgen05 tensor cores */
+  EGN_PREC_FP32 = 0,  /* fp32 storage + fp32 CUDA-core convs (exact comparator)              */
+  EGN_PREC_FP16 = 1,  /* fp16 NHWC storage, fp32 accumulation, tcgen05 tensor cores        */
+  EGN_PREC_FP16X2 = 2 /* split storage (every activation / weight an unevaluated sum of two
+                         fp16 values, ~22 significant bits) and error-compensated tcgen05
+                         convs: x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in fp32 TMEM
+                         accumulators.  The tensor-core mode that holds the reference's fp32
+                         results to the 1e-4 parity bound.                                  */
 } egn_precision;
 
 typedef enum {
-  EGN_CONV_AUTO = 0, /* tcgen05 kernels wherever the layer shape allows (fp16 mode) */
+  EGN_CONV_AUTO = 0, /* tcgen05 kernels wherever the layer shape allows (fp16 / fp16x2) */
   EGN_CONV_SIMT = 1  /* force the CUDA-core kernels (debug comparator)            */
 } egn_conv_impl;
 
@@ -133,9 +138,9 @@ EGN_API int egn_hrnet_read_tap(egn_hrnet* h, const char* name, int batch, const 
                        float* out, int dims[3], void* stream);
 
 /* One fused conv layer, out = act(conv(in, w) + bias [+ res]), for per-layer parity tests
- * (synchronous).  impl: 0 = CUDA-core kernel, 1 = tcgen05 kernel (fp16 only).  dtype: 0 = fp32,
- * 1 = fp16 storage.  in/res/out: device NHWC with channels padded to a multiple of 16
- * (pad lanes zero); w: HOST fp32 torch OIHW; bias: HOST fp32 [Cout] or NULL.
+ * (synchronous).  impl: 0 = CUDA-core kernel, 1 = tcgen05 kernel (fp16 / fp16x2).  dtype: 0 = fp32,
+ * 1 = fp16, 2 = fp16x2 split storage ([B,H,W,2*Cp] fp16: hi plane then lo plane per pixel).
+ * in/res/out: device NHWC with channels padded to a multiple of 16 (pad lanes zero); w: HOST fp32 torch OIHW; bias: HOST fp32 [Cout] or NULL.
  * ksize 1 (pad 0) or 3 (pad 1), stride 1 or 2. */
 EGN_API int egn_conv2d_fused(int impl, int dtype, const void* in, const float* w_oihw_host,
                      const float* bias_host, const void* res, void* out, int B, int H, int W,

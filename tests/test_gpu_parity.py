@@ -130,12 +130,20 @@ HC_CASES = [('tiny', configs.tiny_cfgs), ('tiny_heatmap', lambda: configs.tiny_c
             ('ped', configs.ped_cfgs), ('demo', configs.demo_cfgs)]
 
 
+EXACT_MODES = [('fp32', 'auto'), ('fp16x2', 'auto'), ('fp16x2', 'simt')]
+
+
+@pytest.mark.parametrize('precision,impl', EXACT_MODES, ids=['%s-%s' % m for m in EXACT_MODES])
 @pytest.mark.parametrize('tag,mk', HC_CASES, ids=[c[0] for c in HC_CASES])
-def test_hc_fp32_mode_vs_reference_golden(golden, tag, mk):
-    """fp32 precision mode against the upstream module's outputs: 1e-4 on coordinates."""
+def test_hc_exact_modes_vs_reference_golden(golden, tag, mk, precision, impl):
+    """The two modes that carry the parity claim against the upstream module's outputs -- 1e-4 on coordinates,
+    index-exact arg-max: 'fp16x2' (tcgen05 tensor cores, error-compensated split operands: the benchmarked
+    mode) and 'fp32' (CUDA-core comparator)."""
     cfgs = mk()
     g = golden('hrnet_%s.npz' % tag)
-    m = _hc(cfgs, 'fp32')
+    m = _hc(cfgs, precision, conv_impl=impl)
+    if precision == 'fp16x2' and impl == 'auto':
+        assert m.stats()['tc_launches'] > 0.9 * m.stats()['launches'] - 40      # really on the tensor cores
     x = egonet_ref.synth_crops(int(g['batch']), cfgs, int(g['seed_x'])).to(DEV)
     out = m(x)
     maps = (out[0] if isinstance(out, tuple) else out).cpu().numpy()
@@ -148,9 +156,10 @@ def test_hc_fp32_mode_vs_reference_golden(golden, tag, mk):
         np.testing.assert_allclose(out[1].cpu().numpy(), g['coords'], rtol=0, atol=1e-4)
 
 
-def test_hc_fp32_per_stage_taps_vs_oracle():
+@pytest.mark.parametrize('precision', ['fp32', 'fp16x2'])
+def test_hc_exact_modes_per_stage_taps_vs_oracle(precision):
     cfgs = configs.tiny_cfgs()
-    m = _hc(cfgs, 'fp32', keep_taps=True)
+    m = _hc(cfgs, precision, keep_taps=True)
     sd = hrnet_ref.make_weights(cfgs, 1)
     x = egonet_ref.synth_crops(3, cfgs, 0)
     taps = {}
@@ -387,6 +396,63 @@ def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
         outs[impl] = out
     # the two kernels see identical operands: they may differ by fp32 summation order only
     assert (outs[0].float() - outs[1].float()).abs().max().item() <= 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def _split16(x_nchw):
+    """NCHW fp32 -> fp16x2 split NHWC [B,H,W,2*Cp]: per pixel the hi plane (rn16(v)) then the lo plane (rn16(v - hi))."""
+    B, C, H, W = x_nchw.shape
+    Cp = (C + 15) // 16 * 16
+    v = x_nchw.permute(0, 2, 3, 1).float()
+    hi = v.to(torch.float16)
+    lo = (v - hi.float()).to(torch.float16)
+    out = torch.zeros((B, H, W, 2 * Cp), device=x_nchw.device, dtype=torch.float16)
+    out[..., :C] = hi
+    out[..., Cp:Cp + C] = lo
+    return out.contiguous()
+
+
+def _unsplit(t, C):
+    Cp = t.shape[-1] // 2
+    return (t[..., :C].double() + t[..., Cp:Cp + C].double()).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize('variant', ['auto', 'no_pair', 'v1_only'])
+@pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
+def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
+    """One fused conv in fp16x2 split storage (three error-compensated tcgen05 MMAs per product, two TMEM
+    accumulators) against torch's fp64 conv2d on the values the split tensors represent.  Bound: 1e-5 of the
+    output scale -- fp32-level (what remains is the tensor core's truncating fp32 accumulation, ~2e-8 per
+    K16 step, profiles/r02_acc_precision.md) -- 100x tighter than the plain fp16 path's rounding."""
+    from egonet_b200 import _native as N
+    Cin, Cout, H, W, k, stride, B = case
+    if variant == 'no_pair':
+        if not (k == 3 and stride == 1 and W >= 24):
+            pytest.skip('CTA pairs only exist in the persistent kernel')
+        monkeypatch.setenv('EGN_TC_PAIR', '0')
+    if variant == 'v1_only':
+        monkeypatch.setenv('EGN_TC_V3', '0')
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)
+    x = torch.randn((B, Cin, H, W), generator=g).to(DEV)
+    w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5)
+    bias = torch.randn((Cout,), generator=g)
+    pad = 1 if k == 3 else 0
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    xin = _split16(x)
+    res = _split16(torch.randn((B, Cout, OH, OW), generator=g).to(DEV))
+    Cout_p = res.shape[-1] // 2
+    ref = torch.nn.functional.conv2d(_unsplit(xin, Cin), w.double().to(DEV), bias.double().to(DEV), stride=stride, padding=pad)
+    ref = torch.relu(ref + _unsplit(res, Cout))
+    wc, bc = w.contiguous(), bias.contiguous()
+    tol = 1e-5 * max(1.0, ref.abs().max().item())
+    for impl in (0, 1):
+        out = torch.full((B, OH, OW, 2 * Cout_p), float('nan'), device=DEV, dtype=torch.float16)
+        N.check(N.lib().egn_conv2d_fused(impl, 2, N.ptr(xin), N.ptr(wc), N.ptr(bc), N.ptr(res), N.ptr(out),
+                                         B, H, W, Cin, Cout, k, stride, 1, N.current_stream()))
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all(), 'impl %d left unwritten / non-finite outputs' % impl
+        assert (out[..., Cout:Cout_p] == 0).all() and (out[..., Cout_p + Cout:] == 0).all(), 'pad lanes must stay zero'
+        err = (_unsplit(out, Cout) - ref).abs().max().item()
+        assert err <= tol, 'impl %d: %g (tol %g)' % (impl, err, tol)
 
 
 # --------------------------------------------------------------------------- training-config loss (row a12, loss end)
