@@ -305,7 +305,7 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=8)
     ap.add_argument('--cpu-baseline-crops', type=int, default=64)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32', 'fp16x2'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

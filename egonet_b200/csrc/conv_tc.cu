@@ -1982,6 +1982,14 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->blk_bytes, p->cb);
     }
   }
+  if (!p->use_persist && !p->use_run) {
+    // v1 after a rejected window-run / persistent plan: its own TMEM and shared-memory footprint
+    p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
+    p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+  }
+  if (getenv("EGN_TC_VERBOSE") && !p->use_persist && !p->use_run)
+    fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v1-tap n_tile=%d stages=%d smem=%zuKB tmem=%u\n", a.ksize, a.ksize,
+            a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->stages, p->smem_bytes / 1024, p->tmem_cols);
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][K] fp16, zero padded to whole kc-channel chunks.
   //   plain fp16           K = taps * cin_k, tap row = [w (Cin_p)]
   //   fp16x2, v3           K = taps * cin_k, tap row = [w_hi (Cin_p) | w_lo (Cin_p)]   (cross pairing by the issue table)
