@@ -1226,6 +1226,8 @@ struct PersistParams {
   // (ksplit = 2: H and L are summed by the epilogue).  The staging buffer holds nblk_plane hi blocks followed by
   // nblk_plane lo blocks (nblk = 2 * nblk_plane); out / res tensors have 2 * Cout_p physical channels.
   int split, nh, nblk_plane;
+  int a_slots;          // input-window slots in smem: 2 (window j+1 loads while j is multiplied) or 1 (load and MMA
+                        // phases of consecutive windows serialise; the epilogue still overlaps -- TMEM stays double buffered)
 };
 
 // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps).
@@ -1254,7 +1256,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int w_off = kPair ? (int)crank : 0;
   const int w0 = (int)blockIdx.x - w_off;
   uint8_t* smem_a = smem;                                   // 2 slots
-  uint8_t* smem_b = smem + 2 * (size_t)a_slot;
+  uint8_t* smem_b = smem + (size_t)pp.a_slots * a_slot;
   uint8_t* smem_stage = smem_b + (size_t)b_slots * b_stage;                  // n_stage x nblk x blk_bytes (1024-aligned)
   const uint32_t stage_bytes = (uint32_t)pp.nblk * pp.blk_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + (size_t)pp.n_stage * stage_bytes);
@@ -1379,8 +1381,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int j = 0;
     for (int wb = w0; wb < pp.n_windows; wb += gridDim.x, ++j) {
       const int w = wb + w_off;
-      const int slot = j & 1;
-      mbar_wait(&a_empty[slot], (uint32_t)((j >> 1) & 1) ^ 1u);
+      const int slot = pp.a_slots == 2 ? (j & 1) : 0;
+      mbar_wait(&a_empty[slot], (uint32_t)(((pp.a_slots == 2 ? j >> 1 : j) & 1) ^ 1));
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
       if (!(p.dbg & 8) && elect_one()) {
         if constexpr (kPair) {
@@ -1454,16 +1456,18 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int w = w0; w < pp.n_windows; w += gridDim.x, ++j) {
         const int slot = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        const int aslot = pp.a_slots == 2 ? slot : 0;                   // input-window slot (accumulator sets always alternate)
+        const uint32_t aph = pp.a_slots == 2 ? ph : (uint32_t)(j & 1);
         if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
         mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
         if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 1] = gtime();
-        if (!(p.dbg & 8)) mbar_wait(&a_full[slot], ph);                 // window landed
+        if (!(p.dbg & 8)) mbar_wait(&a_full[aslot], aph);               // window landed
         tc_fence_after();
         if (p.ts && j < 8) {
           p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
           p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 6] = (unsigned long long)clock64();
         }
-        const uint32_t a_lo = a_lo0 + (((uint32_t)slot * a_slot) >> 4);
+        const uint32_t a_lo = a_lo0 + (((uint32_t)aslot * a_slot) >> 4);
         const uint32_t d0 = tmem_base + (uint32_t)(slot * acc_cols);
         if constexpr (kPair) {
 #pragma unroll 4
@@ -1471,7 +1475,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint4 e = s_issue[i];
             umma_f16_pair(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
           }
-          umma_commit_pair(&a_empty[slot]);     // both CTAs' window slots may be refilled
+          umma_commit_pair(&a_empty[aslot]);    // both CTAs' window slots may be refilled
           umma_commit_pair(&acc_full[slot]);    // both CTAs' accumulator halves complete
           continue;
         }
@@ -1500,7 +1504,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         }
-        umma_commit(&a_empty[slot]);      // window slot may be refilled
+        umma_commit(&a_empty[aslot]);     // window slot may be refilled
         umma_commit(&acc_full[slot]);     // accumulators complete
         if (p.ts && j < 8) {
           p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 3] = gtime();
@@ -1690,6 +1694,7 @@ struct TcConvPlan {
   size_t pair_smem = 0;       // dynamic smem per CTA in pair mode
   bool pack_tail = false;     // weight matrix stored with the 32-channel tail chunks of two taps per tile (see PersistParams)
   int w_tiles = 0;            // resident weight tiles per CTA
+  int a_slots = 2;            // input-window slots of the persistent kernel (PersistParams::a_slots)
   int b_resident = 0;
   int n_stage = 0, cb = 0, nblk = 0, rows_stage = 0;   // staged (TMA) epilogue of the persistent kernel
   uint32_t blk_bytes = 0;
@@ -1888,7 +1893,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const int rows_win = TBW * Hw * Wp;
             if (rows_win - 2 * lead > 128 * T) continue;
             const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
-            const size_t a_bytes = 2 * (size_t)p->kchunks * rows_alloc * 128;
+            // fp16x2 windows are twice the bytes: also try a single window slot (the measured fp16 plans keep two)
+            for (int a_slots = 2; a_slots >= (split ? 1 : 2); --a_slots) {
+            const size_t a_bytes = (size_t)a_slots * p->kchunks * rows_alloc * 128;
             const size_t fixed = 1024 + 256 + (size_t)n_tile * 4 +
                                  (size_t)a.ksize * a.ksize * groups * T * 16;   // barriers, bias, issue table
             // resident weights: the 32-channel tail chunks of a 3x3 conv are packed two taps per tile
@@ -1898,7 +1905,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             int resident = 1, bst = 0;
             if (smem > smem_cap) {
               // weights streamed through a ring, once per window: only worth it when a window holds >= 2 M tiles
-              if (T < 2 || getenv("EGN_TC_V3_NOSTREAM")) continue;
+              // (fp16x2: 2x the tiles per window -- measured 512 us vs 345 us for the per-tap kernel on 96ch@32x32)
+              if (T < 2 || split || getenv("EGN_TC_V3_NOSTREAM")) continue;
               resident = 0;
               bst = std::min(kMaxBStages, w_tiles);
               smem = a_bytes + bst * b_stage_bytes + fixed;
@@ -1935,7 +1943,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
               const size_t smem_s = smem + (size_t)S * nblk * blk_bytes * nacc;     // split: hi and lo planes staged
               if (smem_s > smem_cap) continue;
               const double t_epi = (double)T * (n_tile / 16) * (S ? 100.0 : 250.0) * nacc;
-              const double t_win = std::max(std::max(S ? t_mma : 1.5 * t_mma, t_epi), std::max(t_w, t_a)) +
+              const double t_mm = (S ? t_mma : 1.5 * t_mma) + (a_slots == 1 ? t_a : 0.0);   // one slot: load, then multiply
+              const double t_win = std::max(std::max(t_mm, t_epi), std::max(t_w, t_a)) +
                                    (S == 1 ? 4000.0 : 0.0) + 300.0;
               const double est = ceil_div(n_win * n_tiles, 148) * t_win;
               if (est < best) {
@@ -1951,7 +1960,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->n_stage = S; p->cb = cb; p->nblk = nblk; p->rows_stage = rows_stage; p->blk_bytes = (uint32_t)blk_bytes;
                 p->pack_tail = resident && can_pack;
                 p->w_tiles = resident ? w_tiles_res : w_tiles;
+                p->a_slots = a_slots;
               }
+            }
             }
           }
         }
@@ -1976,8 +1987,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
       if (getenv("EGN_TC_VERBOSE") && p->use_persist && p->use_pair) fprintf(stderr, "[egn] (next line) CTA-pair mode\n");
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
-        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d: v3-persist T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
-                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, p->T, p->THW, p->TBW, p->run_eff,
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v3-persist a_slots=%d T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
+                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->a_slots, p->T, p->THW, p->TBW, p->run_eff,
                 p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->b_resident, p->b_stages, p->tmem_cols, p->n_stage, p->nblk,
                 p->blk_bytes, p->cb);
     }
@@ -2170,6 +2181,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.dbg = getenv("EGN_TC_DBG") ? atoi(getenv("EGN_TC_DBG")) : 0;
     pp.split = p->split ? 1 : 0;
     pp.nh = p->Cin_p / 16;
+    pp.a_slots = p->a_slots;
     // L2 bulk prefetch of the residual rows by the A producer (direct, non-staged epilogue only):
     // EGN_TC_RES_PREFETCH = 2 (default) only when the output channels are not split over blockIdx.y, 1 always,
     // 0 never.  A split layer would prefetch the all-channel rows once per half -- 2x the residual DRAM traffic

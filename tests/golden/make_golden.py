@@ -198,26 +198,27 @@ def golden_pose(ref):
                                                 np.array([[707., 0, 604], [0, 707, 180], [0, 0, 1]])))
 
 
-def golden_pipeline(ref):
-    """EgoNet.get_keypoints -> lift_2d_to_3d -> gather_lifting_results on the tiny config."""
-    cfgs = configs.tiny_cfgs()
+def golden_pipeline(ref, tag='tiny', cfgs=None, paths=None):
+    """EgoNet.get_keypoints -> lift_2d_to_3d -> gather_lifting_results of the upstream class
+    (tiny config: 6 crops in 3 images; demo config = the benchmarked HRNet-W48: 8 crops in 3 images)."""
+    cfgs = cfgs or configs.tiny_cfgs()
+    paths = paths or ['img_a.png'] * 2 + ['img_b.png'] * 3 + ['img_c.png']
     ego = ref['egonet'].EgoNet(cfgs, pre_trained=False).eval()
     hc_sd = hrnet_ref.make_weights(cfgs, 1)
     l_sd = lifter_ref.make_weights(cfgs, 11)
     ego.HC.load_state_dict(hc_sd)
     ego.L.load_state_dict(l_sd)
     ego.LS = lifter_ref.make_stats(cfgs, 12)
-    n = 6
+    n = len(paths)
     crops = egonet_ref.synth_crops(n, cfgs, 0)
     recs = egonet_ref.synth_boxes(n, cfgs, 2)
-    paths = ['img_a.png'] * 2 + ['img_b.png'] * 3 + ['img_c.png']
     for r, p in zip(recs, paths):
         r.update(path=p, label=-1, score=-1.0)
     with torch.no_grad():
         records = ego.get_keypoints(crops, [dict(r) for r in recs], is_cuda=False)
         records = ego.lift_2d_to_3d(records, cuda=False)
     out = {'kpts_2d': [], 'kpts_3d': [], 'euler': [], 'translation': [], 'alpha_trans': [], 'alpha_proj': []}
-    for p in ('img_a.png', 'img_b.png', 'img_c.png'):
+    for p in sorted(set(paths)):
         rec = records[p]
         rec['K'] = egonet_ref.KITTI_K
         for mode in ('trans', 'proj'):
@@ -227,8 +228,9 @@ def golden_pipeline(ref):
         out['kpts_3d'].append(rec['kpts_3d_pred'])
         out['euler'].append(rec['euler_angles'])
         out['translation'].append(rec['translation'])
-    save('pipeline_tiny.npz', **{k: np.concatenate(v, 0) for k, v in out.items()},
-         centers=np.array([r['center'] for r in recs]), scales=np.array([r['scale'] for r in recs]))
+    save('pipeline_%s.npz' % tag, **{k: np.concatenate(v, 0) for k, v in out.items()},
+         centers=np.array([r['center'] for r in recs]), scales=np.array([r['scale'] for r in recs]),
+         paths=np.array(paths))
 
 
 def golden_loss(ref):
@@ -461,6 +463,7 @@ def main():
     golden_lifter(ref)
     golden_pose(ref)
     golden_pipeline(ref)
+    golden_pipeline(ref, 'demo', configs.demo_cfgs(), ['img_a.png'] * 3 + ['img_b.png'] * 4 + ['img_c.png'])
     golden_loss(ref)
     golden_crop(ref)
     golden_pnp(ref)
