@@ -4,8 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
 
 One "step" = one pass of the whole per-crop path over one batch of synthetic 256x256 crops:
-HC (HRNet-W48 heat-maps + coordinate head, fp16 tcgen05 convs) -> heat-map decode (hard arg-max and
-soft-argmax of the 33 maps) -> inverse crop affine -> lifter -> pose solve.  Workload = BASELINE.json
+HC (HRNet-W48 heat-maps + coordinate head, tcgen05 convs) -> heat-map decode (hard arg-max and
+soft-argmax of the 33 maps) -> inverse crop affine -> lifter -> pose solve.  The headline mode is
+`fp16x2`: error-compensated split-fp16 tensor-core convs, the mode whose results meet the 1e-4 parity
+bound against the reference (tests/test_gpu_parity.py); the plain fp16 mode (faster, ~1e-3 on
+coordinates) is timed beside it in `config.fast_mode_fp16` with its measured error.  Workload = BASELINE.json
 configs[2] ("full inference: heatmap + lifter + pose, batch=256, 1xB200" -- the configuration whose
 stages are exactly the metric's "heatmap+lift+pose"), per GPU; the batch-64 figure of configs[1] is
 reported alongside in `config.batch64`.
@@ -153,7 +156,7 @@ def profile_hc(ego, x, passes=3):
     return classes, float(acc.sum())
 
 
-def roofline_block(classes, total_ms, pk, batch):
+def roofline_block(classes, total_ms, pk, batch, precision='fp16'):
     name, c = max(classes.items(), key=lambda kv: kv[1]['ms'])
     dur = c['ms'] / c['launches'] * 1e-3                      # seconds per launch
     bytes_per_launch = (c['act_bytes'] + c['weight_bytes']) / c['launches']
@@ -171,7 +174,8 @@ def roofline_block(classes, total_ms, pk, batch):
            'avg_launch_us': round(dur * 1e6, 2), 'algorithmic_bytes_per_launch': int(bytes_per_launch),
            'flops_per_launch': int(flops_per_launch)}
     try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(name)
+        table = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        tr = table.get(name + ' | ' + precision) or (table.get(name) if precision == 'fp16' else None)
         if tr and tr['batch'] == batch:
             blk['traffic'] = tr['bytes']
             blk['traffic_source'] = 'ncu --set full capture of this kernel class at this batch size (profiles/)'
@@ -219,6 +223,104 @@ def side_stages(ego, recs, B, K, dev, pk_hbm):
                                       'algorithmic bytes = the fp32 crops written'},
             'pnp_refine': {'ms_per_batch': round(ms_pnp, 4), 'instances_per_s': round(B / ms_pnp * 1e3, 1),
                            'points': 33, 'note': 'optional stage (disabled in the reference\'s maintained path)'}}
+
+
+def fast_mode_block(cfgs, dev, x_sets, centers, scales, K, exact_model, B):
+    """The plain fp16 tensor-core mode on the same batches: crops/s and its measured error against the
+    headline (fp16x2) mode's coordinates and poses on the same crops."""
+    fast_cfgs = json.loads(json.dumps(cfgs))
+    fast_cfgs['heatmapModel']['b200_precision'] = 'fp16'
+    fast = build_model(fast_cfgs, dev)
+    for i in range(3):
+        one_step(fast, x_sets[i % len(x_sets)], centers, scales, K)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(10):
+        one_step(fast, x_sets[i % len(x_sets)], centers, scales, K)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    of = fast.forward_crops(x_sets[0], centers, scales, K=K, alpha_mode='proj', return_all=True)
+    oe = exact_model.forward_crops(x_sets[0], centers, scales, K=K, alpha_mode='proj', return_all=True)
+    return {'crops_per_s': round(B / ms * 1e3, 1), 'ms_per_step': round(ms, 4),
+            'coords_err_vs_headline_mode': float((of['coords'] - oe['coords']).abs().max()),
+            'euler_err_vs_headline_mode_rad': float((of['pose'][:, :3] - oe['pose'][:, :3]).abs().max()),
+            'note': 'b200_precision=fp16: single fp16 operands (the reference is fp32: this mode misses the 1e-4 '
+                    'parity bound and is opt-in)'}
+
+
+def e2e_images_block(ego, cfgs, dev, K, steps):
+    """End to end through the reference's own entry, EgoNet.forward(annot_dict) + post_process, from decoded
+    uint8 images in HOST memory: per step 16 KITTI-sized images x 16 boxes = 256 crops.  Inside the timed
+    region: H2D of the images, device crop front-end, HC, affine, lifter, pose, D2H of the records."""
+    from egonet_b200 import synth
+    g = np.random.Generator(np.random.PCG64(77))
+    n_img, per = 16, 16
+    images = [g.integers(0, 256, (375, 1242, 3), dtype=np.uint8) for _ in range(n_img)]
+    boxes = []
+    for i in range(n_img):
+        recs = synth.boxes(per, cfgs, 300 + i)
+        boxes.append(np.array([r['bbox'] for r in recs]) if 'bbox' in recs[0] else None)
+    if boxes[0] is None:                      # synth.boxes carries centre / scale only: rebuild corner boxes
+        boxes = []
+        for i in range(n_img):
+            cx, cy = g.uniform(50, 1190, per), g.uniform(120, 330, per)
+            w, h = g.uniform(30, 400, per), g.uniform(25, 250, per)
+            boxes.append(np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1))
+    annot = {'path': ['img_%02d.png' % i for i in range(n_img)], 'boxes': boxes, 'images': images,
+             'K': [K] * n_img}
+    import contextlib
+    import io
+
+    def run():
+        with contextlib.redirect_stdout(io.StringIO()):        # post_process prints one line per image, as upstream
+            rec = ego(annot)
+            return ego.post_process(rec, alpha_mode='proj')
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {'crops_per_s': round(n_img * per / dt, 1), 'ms_per_step': round(dt * 1e3, 3), 'images_per_step': n_img,
+            'crops_per_step': n_img * per, 'h2d_bytes_per_step': int(sum(im.nbytes for im in images)),
+            'note': 'EgoNet.forward(annot_dict) + post_process: uint8 images from host memory, device crop '
+                    'front-end, record dicts back on the host (wall clock around synchronised steps)'}
+
+
+def stream4096_block(ego, dev_sets, centers, scales, K, world, rank, dist, B):
+    """BASELINE configs[4]: a 4096-crop stream block-partitioned over the ranks (4096 / world each), processed
+    in micro-batches of B, ONE all_gather of the [4096/world, 7] pose records at the end."""
+    per_rank = 4096 // world
+    n_micro = max(1, per_rank // B)
+    poses = torch.empty((n_micro * B, 7), device=centers.device, dtype=torch.float64)
+    gathered = torch.empty((world * n_micro * B, 7), device=centers.device, dtype=torch.float64) if dist else None
+
+    def run():
+        for i in range(n_micro):
+            poses[i * B:(i + 1) * B] = one_step(ego, dev_sets[i % len(dev_sets)], centers, scales, K)
+        if dist:
+            dist.all_gather_into_tensor(gathered, poses)
+    run()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run()
+    b.record()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=centers.device, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {'crops': world * n_micro * B, 'ms': round(ms, 3), 'crops_per_s': round(world * n_micro * B / ms * 1e3, 1),
+            'micro_batch': B, 'micro_batches_per_rank': n_micro, 'gathers': 1 if dist else 0}
 
 
 # ----------------------------------------------------------------------------- CPU oracle legs
@@ -302,10 +404,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--ref-batch', type=int, default=8)
-    ap.add_argument('--cpu-baseline-crops', type=int, default=64)
+    ap.add_argument('--ref-batch', type=int, default=16)
+    ap.add_argument('--cpu-baseline-crops', type=int, default=16, help='crops per CPU pass (same batch as --ref-batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32', 'fp16x2'])
+    ap.add_argument('--precision', default='fp16x2', choices=['fp16', 'fp32', 'fp16x2'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -421,8 +523,19 @@ def main():
             q1.record()
             torch.cuda.synchronize()
             b64 = 64 * 10 / (q0.elapsed_time(q1) * 1e-3)
+        # ---- BASELINE configs[4]: the 4096-crop stream with a single gather (all ranks take part)
+        stream = stream4096_block(ego, dev_sets, centers, scales, K, world, rank, dist, B)
         # ---- per-kernel-class timing for the roofline block (rank 0)
         classes, hc_ms = profile_hc(ego, dev_sets[0]) if rank == 0 else ({}, 0.0)
+        fast_mode = e2e_img = None
+        if rank == 0:
+            try:
+                if args.precision == 'fp16x2':
+                    fast_mode = fast_mode_block(cfgs, dev, dev_sets, centers, scales, K, ego, B)
+                e2e_img = e2e_images_block(ego, cfgs, dev, K, max(3, min(args.steps, 10)))
+            except Exception as e:  # reported next to the headline numbers, never instead of them
+                fast_mode = fast_mode or {'error': '%s: %s' % (type(e).__name__, e)}
+                e2e_img = e2e_img or {'error': '%s: %s' % (type(e).__name__, e)}
         # ---- stages either side of the path, timed alone for reference
         extras = None
         if rank == 0:
@@ -447,7 +560,7 @@ def main():
     line = {
         'metric': METRIC, 'value': round(value, 1), 'unit': 'crops/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16' if args.precision == 'fp16' else 'f32',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp16': 'f16', 'fp32': 'f32', 'fp16x2': 'f16x2'}[args.precision],
         'data': 'synthetic',
         'config': {'workload': 'configs[2]: full per-crop inference (HRNet-W48 heatmap+coords, argmax+soft-argmax '
                                'decode, inverse affine, lifter, pose solve), 256x256 crops, batch %d per GPU' % B,
@@ -465,8 +578,18 @@ def main():
     }
     if extras:
         line['config']['side_stages'] = extras
+    line['config']['stream4096'] = stream
+    if fast_mode:
+        line['config']['fast_mode_fp16'] = fast_mode
+    if e2e_img:
+        line['config']['e2e_images'] = e2e_img
+    line['config']['parity'] = ('hc_precision=%s; ' % args.precision) + {
+        'fp16x2': 'meets the 1e-4 bound vs the reference goldens (coords 4.8e-6, Euler 8.4e-6 rad on the demo config: '
+                  'profiles/r02_parity_report.json, tests/test_gpu_parity.py)',
+        'fp32': 'CUDA-core comparator, meets the 1e-4 bound',
+        'fp16': 'fast mode: ~1e-3 on coordinates, misses the 1e-4 bound'}[args.precision]
     if classes:
-        line['roofline'] = roofline_block(classes, hc_ms, pk, B)
+        line['roofline'] = roofline_block(classes, hc_ms, pk, B, args.precision)
         line['hc_roofline'] = {
             'tensor_frac': round(value / world * 2 * st['macs_per_crop'] / (pk['bf16_tflops_sustained'] * 1e12), 4),
             'hbm_frac': round(value / world * (st['act_bytes_per_crop'] + st['weight_bytes'] / B) / (pk['hbm_gbs'] * 1e9), 4),
@@ -481,9 +604,9 @@ def main():
             r, _ = cpu_pipeline_rate(cfgs, 4, 1, t)
             if r > best_r:
                 best_t, best_r = t, r
-        rate, times = cpu_pipeline_rate(cfgs, args.cpu_baseline_crops, 3, best_t)
+        rate, times = cpu_pipeline_rate(cfgs, args.cpu_baseline_crops, 5, best_t)
         line['cpu_baseline'] = {'value': round(rate, 3), 'unit': 'crops/s', 'cores': best_t, 'kind': 'port',
-                                'sample': '3 timed passes of %d crops (+1 warm-up) of the same workload, oracle port on '
+                                'sample': '5 timed passes of %d crops (+1 warm-up; the reference arm uses the same batch) of the same workload, oracle port on '
                                           'torch-CPU fp32 with the best of {8,16,32,64,%d} threads on a %d-core host '
                                           '(median %.2f s/pass)' % (args.cpu_baseline_crops, ncpu, ncpu, float(np.median(times)))}
     print(json.dumps(line))

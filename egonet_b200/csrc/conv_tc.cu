@@ -2127,13 +2127,43 @@ static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   return EGN_OK;
 }
 
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) and the SM count are PER DEVICE: a process that
+// runs HC on several GPUs (torch.cuda.set_device, one thread per GPU, model.to('cuda:1')) must opt in on each.
+// Returns the SM count of the current device (0 after setting the error on failure).
+static int device_setup() {
+  constexpr int kMaxDev = 64;
+  static std::mutex mu;
+  static int sms[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
+    set_error("conv_tc: cudaGetDevice failed or ordinal out of range");
+    return 0;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (sms[dev]) return sms[dev];
+  cudaError_t e = cudaSuccess;
+  auto opt_in = [&](const void* fn, int bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  };
+  opt_in((const void*)conv_tc_kernel<128>, 200 * 1024);
+  opt_in((const void*)conv_tc_kernel<64>, 200 * 1024);
+  opt_in((const void*)conv_tc_kernel<32>, 200 * 1024);
+  opt_in((const void*)conv_run_kernel, 200 * 1024 + 2048);
+  opt_in((const void*)conv_persist_kernel<false>, 227 * 1024);
+  opt_in((const void*)conv_persist_kernel<true>, 227 * 1024);
+  opt_in((const void*)conv_persist_kernel<false, true>, 227 * 1024);
+  int n = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("conv_tc: per-device kernel setup failed on device %d: %s", dev, cudaGetErrorString(e));
+    return 0;
+  }
+  sms[dev] = n;
+  return n;
+}
+
 template <int SW>
 static int launch_sw(TcConvPlan* p, const CUtensorMap& ma, const TcParams& tp, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   EGN_CUDA_CHECK(launch_pdl(conv_tc_kernel<SW>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, tp));
   EGN_LAUNCH_CHECK("conv_tc_kernel");
   return EGN_OK;
@@ -2144,6 +2174,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     set_error("launch_conv_tc: null plan");
     return EGN_ERR_STATE;
   }
+  const int num_sms = device_setup();
+  if (!num_sms) return EGN_ERR_CUDA;
   CUtensorMap ma;
   {
     std::lock_guard<std::mutex> lock(p->mu);
@@ -2241,19 +2273,6 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       }
       if (!a.res) m_res = m_out;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
-    }
-    static int num_sms = 0;
-    if (!num_sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     dim3 grid((unsigned)std::min(pp.n_windows, num_sms), (unsigned)p->n_tiles);
     if (pair) {
       // one cluster of two CTAs per SM pair; the extra bias floats of the full-width tile need 4 * n_tile more bytes
@@ -2309,11 +2328,6 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     if (getenv("EGN_TC_TS")) {
       if (!d_ts) cudaMalloc(&d_ts, 8192 * 8 * sizeof(unsigned long long));
       if (n_cta <= 8192) rp.ts = d_ts;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-      EGN_CUDA_CHECK(cudaFuncSetAttribute(conv_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 2048));
-      attr_set = true;
     }
     dim3 grid((unsigned)(rp.win_per_img * ceil_div(a.B, p->TBW)), (unsigned)p->n_tiles);
     EGN_CUDA_CHECK(launch_pdl(conv_run_kernel, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, rp));

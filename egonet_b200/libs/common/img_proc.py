@@ -87,6 +87,24 @@ def modify_bbox(bbox, target_ar, enlarge=1.1):
     return resize_bbox(b[0], b[1], b[2], b[3], target_ar=target_ar)
 
 
+def modify_bbox_batch(bboxes, target_ar, enlarge=1.1):
+    """``modify_bbox`` [img_proc.py:411-459] for an [n,4] array of boxes at once (same float64 operations in
+    the same order, so every row equals the per-box function bit for bit).
+    Returns (bbox_resize [n,4], centers [n,2], scales [n,2])."""
+    b = np.asarray(bboxes).reshape(-1, 4)          # arithmetic in the boxes' own dtype, as the per-box function
+    left, top, right, bottom = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    w, h = (right - left) * enlarge, (bottom - top) * enlarge
+    cx, cy = (left + right) / 2, (top + bottom) / 2
+    left, top, right, bottom = cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h
+    w, h = right - left, bottom - top
+    cx, cy = (left + right) / 2, (top + bottom) / 2
+    tall = h / w > target_ar
+    nw, nh = h * (1 / target_ar), w * target_ar
+    box = np.where(tall[:, None], np.stack([cx - 0.5 * nw, top, cx + 0.5 * nw, bottom], 1),
+                   np.stack([left, cy - 0.5 * nh, right, cy + 0.5 * nh], 1))
+    return box, np.stack([cx, cy], 1), np.stack([(box[:, 2] - box[:, 0]) / SIZE, (box[:, 3] - box[:, 1]) / SIZE], 1)
+
+
 def get_affine_transform(center, scale, rot, output_size, shift=None, inv=0):
     """[img_proc.py:26-64] host-side crop affine for ``cv2.warpAffine`` (crop_instances
     is host code upstream as well).  Three float32 reference points per side exactly
@@ -180,24 +198,41 @@ def crop_instances_device(images, image_of_crop, centers, scales, resolution, me
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or im.stride(2) != 1 or im.stride(1) != 3:
             raise ValueError('image %d must be uint8 [H,W,3] with packed pixels' % k)
         table[k] = N.Image(im.data_ptr(), im.shape[0], im.shape[1], im.stride(0), 3)
-    table_dev = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
-    ce = torch.as_tensor(np.asarray(centers, dtype=np.float64) if not torch.is_tensor(centers) else centers,
-                         dtype=torch.float64).to(dev).contiguous().view(-1, 2)
-    sc = torch.as_tensor(np.asarray(scales, dtype=np.float64) if not torch.is_tensor(scales) else scales,
-                         dtype=torch.float64).to(dev).contiguous().view(-1, 2)
-    n = ce.shape[0]
     idx_host = np.asarray(image_of_crop, dtype=np.int32).reshape(-1)
-    if len(idx_host) != n or sc.shape[0] != n:
-        raise ValueError('centers / scales / image_of_crop disagree on the number of crops')
+    n = len(idx_host)
     if n and (idx_host.min() < 0 or idx_host.max() >= len(images)):
         raise ValueError('image_of_crop out of range')
-    idx = torch.as_tensor(idx_host).to(dev)
+    if torch.is_tensor(centers) and centers.is_cuda and torch.is_tensor(scales) and scales.is_cuda:
+        ce = centers.to(torch.float64).contiguous().view(-1, 2)
+        sc = scales.to(torch.float64).contiguous().view(-1, 2)
+        ce_h = sc_h = np.zeros((0, 2))
+    else:
+        ce_h = np.ascontiguousarray(np.asarray(centers.cpu() if torch.is_tensor(centers) else centers, dtype=np.float64)).reshape(-1, 2)
+        sc_h = np.ascontiguousarray(np.asarray(scales.cpu() if torch.is_tensor(scales) else scales, dtype=np.float64)).reshape(-1, 2)
+        ce = sc = None
+    if (ce is not None and (ce.shape[0] != n or sc.shape[0] != n)) or (ce is None and (len(ce_h) != n or len(sc_h) != n)):
+        raise ValueError('centers / scales / image_of_crop disagree on the number of crops')
+    # one host buffer, ONE H2D copy for the whole call: [centers | scales | image table | image_of_crop]
+    tbytes = bytes(table)
+    meta = np.zeros(ce_h.nbytes + sc_h.nbytes + len(tbytes) + idx_host.nbytes, dtype=np.uint8)
+    o_sc, o_tab = ce_h.nbytes, ce_h.nbytes + sc_h.nbytes
+    o_idx = o_tab + len(tbytes)                        # table entries are 24 bytes: 4-byte alignment holds
+    meta[:o_sc] = ce_h.view(np.uint8).reshape(-1)
+    meta[o_sc:o_tab] = sc_h.view(np.uint8).reshape(-1)
+    meta[o_tab:o_idx] = np.frombuffer(tbytes, dtype=np.uint8)
+    meta[o_idx:] = idx_host.view(np.uint8)
+    meta_dev = torch.from_numpy(meta).to(dev, non_blocking=True)
+    base = meta_dev.data_ptr()
+    import ctypes as _ct
+    p_ce = N.ptr(ce) if ce is not None else _ct.c_void_p(base)
+    p_sc = N.ptr(sc) if sc is not None else _ct.c_void_p(base + o_sc)
+    p_tab, p_idx = _ct.c_void_p(base + o_tab), _ct.c_void_p(base + o_idx)
     out = torch.empty((n, 3, height, width), device=dev, dtype=torch.float32)
     u8 = torch.empty((n, height, width, 3), device=dev, dtype=torch.uint8) if return_u8 else None
     m3 = (ctypes.c_float * 3)(*(mean if mean is not None else [0., 0., 0.]))
     s3 = (ctypes.c_float * 3)(*(std if std is not None else [1., 1., 1.]))
     with torch.cuda.device(dev):
-        N.check(N.lib().egn_crop_instances(N.ptr(table_dev), len(images), N.ptr(idx), N.ptr(ce), N.ptr(sc), n,
+        N.check(N.lib().egn_crop_instances(p_tab, len(images), p_idx, p_ce, p_sc, n,
                                            width, height, m3, s3, N.ptr(out), N.ptr(u8), N.current_stream()))
     return (out, u8) if return_u8 else out
 

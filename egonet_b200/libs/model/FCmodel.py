@@ -108,8 +108,11 @@ class FCModel(nn.Module):
             raise RuntimeError('the native lifter has no CPU path: input must be a CUDA tensor')
         L = N.lib()
         with torch.cuda.device(kpts_2d.device):
-            if self._dirty:
+            # the engine's weights live on the device that was current at the last sync: a handle is bound to
+            # one device (and one stream at a time); an input on another GPU re-uploads them there
+            if self._dirty or getattr(self, '_weights_device', None) != x.device.index:
                 self._sync()
+                self._weights_device = x.device.index
             x = kpts_2d.detach().to(torch.float64).contiguous()
             n = x.shape[0]
             out = torch.empty((n, self.output_size), device=x.device, dtype=torch.float64)

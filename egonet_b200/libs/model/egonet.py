@@ -116,18 +116,19 @@ class EgoNet(nn.Module):
             images.append(image.to(dev, non_blocking=True))
             labels = annot_dict['labels'][img_idx] if 'labels' in annot_dict else -np.ones(n, dtype=np.int64)
             scores = annot_dict['scores'][img_idx] if 'scores' in annot_dict else -np.ones(n)
-            for k, bbox in enumerate(boxes):
-                bbox = lip.to_npy(bbox)
-                ret = lip.modify_bbox(bbox, target_ar)
-                image_of_crop.append(len(images) - 1)
-                centers.append(ret['c'])
-                scales.append(ret['s'])
-                records.append({'path': path, 'center': ret['c'], 'scale': ret['s'], 'bbox': bbox,
-                                'bbox_resize': ret['bbox'], 'rotation': 0., 'label': labels[k],
+            # all boxes of the image at once (row-wise identical to modify_bbox per box)
+            boxes_np = boxes if isinstance(boxes, np.ndarray) else np.stack([lip.to_npy(b) for b in boxes])
+            resized, cs, ss = lip.modify_bbox_batch(boxes_np, target_ar)
+            image_of_crop.extend([len(images) - 1] * n)
+            centers.append(cs)
+            scales.append(ss)
+            for k in range(n):
+                records.append({'path': path, 'center': cs[k], 'scale': ss[k], 'bbox': boxes_np[k],
+                                'bbox_resize': list(resized[k]), 'rotation': 0., 'label': labels[k],
                                 'score': scores[k]})
         if not records:
             return torch.empty((0, 3, int(resolution[1]), int(resolution[0])), device=dev), records
-        crops = lip.crop_instances_device(images, image_of_crop, np.array(centers), np.array(scales),
+        crops = lip.crop_instances_device(images, image_of_crop, np.concatenate(centers), np.concatenate(scales),
                                           resolution, mean, std)
         return crops, records
 

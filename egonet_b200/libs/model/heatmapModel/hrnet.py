@@ -13,8 +13,8 @@ pointer to the native engine (``egn_hrnet_forward``), which replays the whole
 network as fused sm_100a kernels.  BatchNorm folding / repacking happens lazily
 before the first forward after the parameters changed.
 
-Inference only: ``forward`` in training mode raises (the reference's train path
-is out of scope).
+``forward`` in eval mode is the inference engine; in training mode it runs the
+train-mode forward of the native training engine (see ``libs/trainer``).
 """
 import ctypes
 import logging
@@ -74,9 +74,11 @@ class PoseHighResolutionNet(nn.Module):
 
     Extra (optional) config keys, all under ``cfgs['heatmapModel']`` and all with
     defaults so reference YAML files work unchanged:
-      ``b200_precision``: ``'fp16'`` (default; tcgen05 tensor cores, fp16 NHWC
-      activations, fp32 accumulation) or ``'fp32'`` (fp32 storage and CUDA-core
-      convolutions -- the mode that meets the 1e-4 parity bound).
+      ``b200_precision``: ``'fp16x2'`` (default; tcgen05 tensor cores with
+      error-compensated split-fp16 operands and fp32 accumulation -- meets the 1e-4
+      parity bound against the reference's fp32 results), ``'fp16'`` (opt-in fast mode:
+      single fp16 operands, ~1e-3 on coordinates) or ``'fp32'`` (fp32 storage and
+      CUDA-core convolutions, the exact comparator).
       ``b200_conv_impl``: ``'auto'`` | ``'simt'``; ``b200_keep_taps``: bool.
     """
 
@@ -88,7 +90,7 @@ class PoseHighResolutionNet(nn.Module):
         self.head_type = hm['head_type']
         self.pixel_shuffle = hm.get('pixel_shuffle', False)
         self.pretrained_layers = hm['extra'].get('pretrained_layers', ['*'])
-        self._precision = _PRECISIONS[kwargs.get('precision', hm.get('b200_precision', 'fp16'))]
+        self._precision = _PRECISIONS[kwargs.get('precision', hm.get('b200_precision', 'fp16x2'))]
         impl = kwargs.get('conv_impl', hm.get('b200_conv_impl', 'auto'))
         if os.environ.get('EGN_CONV_IMPL'):        # debugging aid: force 'simt' for a whole process
             impl = os.environ['EGN_CONV_IMPL']
@@ -170,8 +172,11 @@ class PoseHighResolutionNet(nn.Module):
             raise ValueError('expected input [B,%d,%d,%d], got %s' % (
                 self._in_channels, hm['input_size'][1], hm['input_size'][0], tuple(x.shape)))
         with torch.cuda.device(x.device):
-            if self._dirty:
+            # the engine's folded weights and tensor maps live on the device that was current at the last sync: a
+            # handle is bound to one device (and one stream at a time); an input on another GPU re-uploads them
+            if self._dirty or getattr(self, '_weights_device', None) != x.device.index:
                 self._sync_weights()
+                self._weights_device = x.device.index
             x = x.detach().float().contiguous()
             B = x.shape[0]
             maps, coords, _ = self.run(x)

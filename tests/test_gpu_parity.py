@@ -514,3 +514,21 @@ def test_heatmap_mse_loss_vs_reference_golden(golden):
     ref = 0.5 * ((big - tgt) ** 2).double().mean()
     assert float(loss) == pytest.approx(float(ref), rel=1e-5)
     assert torch.allclose(grad, (big - tgt) / big.numel(), rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs two GPUs in one process')
+def test_one_process_two_devices():
+    """Kernel attributes (dynamic shared-memory opt-in, SM count) are per device and the engine re-uploads its
+    weights when the input lives on another GPU: the same model object gives identical results on cuda:0 and cuda:1."""
+    cfgs = configs.tiny_cfgs()
+    ego = _egonet(cfgs, 'fp16x2')
+    crops = egonet_ref.synth_crops(5, cfgs, 3)
+    recs = egonet_ref.synth_boxes(5, cfgs, 4)
+    centers = np.array([r['center'] for r in recs])
+    scales = np.array([r['scale'] for r in recs])
+    outs = []
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            outs.append(ego.forward_crops(crops.to('cuda:%d' % d), centers, scales, K=egonet_ref.KITTI_K,
+                                          alpha_mode='proj').cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

@@ -74,3 +74,19 @@ def test_add_orientation_arrow_vs_reference_golden(golden):
     lengths = np.linalg.norm(g['arrow'][:, :, 1] - g['arrow'][:, :, 0], axis=1)
     assert (lengths < 50).any() and np.isclose(lengths, 60).any()          # both branches present
     np.testing.assert_allclose(got, g['arrow'], rtol=0, atol=1e-9)
+
+
+def test_modify_bbox_batch_rows_equal_per_box_function():
+    """The vectorised crop geometry used by EgoNet.crop_instances equals modify_bbox (img_proc.py:411-459, itself
+    pinned to the reference golden above) row by row, bit for bit, for float64 / float32 / integer boxes."""
+    from egonet_b200.libs.common import img_proc as lip
+    rng = np.random.Generator(np.random.PCG64(3))
+    x0, y0 = rng.uniform(0, 1100, 200), rng.uniform(0, 300, 200)
+    boxes = np.stack([x0, y0, x0 + rng.uniform(5, 400, 200), y0 + rng.uniform(5, 250, 200)], 1)
+    for arr in (boxes, boxes.astype(np.float32), boxes.astype(np.int64)):
+        for ar in (1.0, 256 / 192):
+            box, c, s = lip.modify_bbox_batch(arr, ar)
+            for i in range(len(arr)):
+                ref = lip.modify_bbox(arr[i], ar)
+                assert np.array_equal(np.asarray(ref['bbox'], dtype=box.dtype), box[i])
+                assert np.array_equal(ref['c'], c[i]) and np.array_equal(ref['s'], s[i])
