@@ -110,9 +110,9 @@ class FCModel(nn.Module):
         with torch.cuda.device(kpts_2d.device):
             # the engine's weights live on the device that was current at the last sync: a handle is bound to
             # one device (and one stream at a time); an input on another GPU re-uploads them there
-            if self._dirty or getattr(self, '_weights_device', None) != x.device.index:
+            if self._dirty or getattr(self, '_weights_device', None) != kpts_2d.device.index:
                 self._sync()
-                self._weights_device = x.device.index
+                self._weights_device = kpts_2d.device.index
             x = kpts_2d.detach().to(torch.float64).contiguous()
             n = x.shape[0]
             out = torch.empty((n, self.output_size), device=x.device, dtype=torch.float64)
