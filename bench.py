@@ -270,6 +270,9 @@ def e2e_images_block(ego, cfgs, dev, K, steps):
             boxes.append(np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1))
     annot = {'path': ['img_%02d.png' % i for i in range(n_img)], 'boxes': boxes, 'images': images,
              'K': [K] * n_img}
+    if ego.pth_trans is None:                 # what tools/inference.py takes from the dataset (car_instance.py:522-531)
+        import torchvision.transforms as tvt
+        ego.pth_trans = tvt.Compose([tvt.ToTensor(), tvt.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
     import contextlib
     import io
 

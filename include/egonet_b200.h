@@ -348,6 +348,49 @@ EGN_API int egn_pnp_refine(const double* kpts_3d, const double* kpts_2d, int N, 
 EGN_API int egn_mse_hm_fwd_bwd(const float* pred, const float* target, const float* target_weight, int B, int K,
                        int H, int W, float* loss_out, float* grad_out, void* workspace8, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Training step of HC (BASELINE configs[3])             */
+/* replaces the loop body of libs/trainer/trainer.py:183-198 for the heat-map  */
+/* head: model.train() forward (hrnet.py:563-614 with nn.BatchNorm2d in        */
+/* training mode, hrnet.py:63-133, 282-300), loss.backward() through it, and   */
+/* the optimiser update (libs/optimizer/optimizer.py:9-41).  fp32 throughout   */
+/* (the reference trains in fp32), BatchNorm sums in fp64.                     */
+/*                                                                             */
+/* Parameters and gradients are ONE flat fp32 device buffer each, owned by the */
+/* caller, laid out in state_dict order: entry i of egn_hrnet_weight_key       */
+/* starts at element egn_hrnet_train_param_offset(t, i) (-1 for the int64      */
+/* num_batches_tracked entries, which the caller keeps).                       */
+/* ------------------------------------------------------------------------- */
+typedef struct egn_hrnet_train egn_hrnet_train;
+
+/* cfg as for egn_hrnet_create (precision / conv_impl / keep_taps ignored); head_type must be EGN_HEAD_HEATMAP. */
+EGN_API int egn_hrnet_train_create(const egn_hrnet_cfg* cfg, egn_hrnet_train** out);
+EGN_API void egn_hrnet_train_destroy(egn_hrnet_train* t);
+EGN_API int64_t egn_hrnet_train_flat_size(const egn_hrnet_train* t);            /* floats in the flat buffer */
+EGN_API int64_t egn_hrnet_train_param_offset(const egn_hrnet_train* t, int i);
+EGN_API int egn_hrnet_train_param_trainable(const egn_hrnet_train* t, int i);  /* 1 parameter, 0 buffer    */
+EGN_API size_t egn_hrnet_train_workspace_bytes(const egn_hrnet_train* t, int batch);
+EGN_API int64_t egn_hrnet_train_flops_per_sample(const egn_hrnet_train* t);    /* 3 x 2 x conv MACs        */
+
+/* Train-mode forward.  flat_params: device fp32 (running statistics inside it are updated in place with
+ * `momentum` when update_running_stats != 0, as nn.BatchNorm2d does); x: device fp32 NCHW [B,C,H,W];
+ * heatmap_out: device fp32 [B,K,hh,hw].  The workspace keeps every activation for the backward pass. */
+EGN_API int egn_hrnet_forward_train(egn_hrnet_train* t, float* flat_params, const float* x, int batch,
+                            float* heatmap_out, float momentum, int update_running_stats, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Backward of the last forward (same batch, same workspace).  grad_heatmap: device fp32 [B,K,hh,hw] =
+ * d loss / d heatmap_out; flat_grads: device fp32, overwritten with d loss / d parameter (flat layout). */
+EGN_API int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float* grad_heatmap, int batch,
+                       float* flat_grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Optimiser updates over flat device buffers with torch.optim semantics (optimizer.py:19-27): step counts from 1;
+ * trainable_mask (device uint8 [n], NULL = all) skips frozen entries / buffers. */
+EGN_API int egn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  const uint8_t* trainable_mask, int64_t n, int step, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, void* stream);
+EGN_API int egn_sgd_step(float* params, const float* grads, float* momentum_buf, const uint8_t* trainable_mask,
+                 int64_t n, int step, float lr, float momentum, float weight_decay, int nesterov, void* stream);
+
 /* Gaussian heat-map targets of the training configuration (BASELINE configs[3]).
  * replaces generate_target libs/common/img_proc.py:347-409 (target_type 'gaussian'), one launch for N samples.
  * joints device fp64 [N,K,3] (crop pixels; column 2 = visibility when joints_vis is NULL), joints_vis device
