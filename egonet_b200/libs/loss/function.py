@@ -3,8 +3,8 @@
 ``JointsMSELoss`` keeps the upstream constructor and ``forward(output, target, target_weight, meta)``
 signature [function.py:22-46]; ``calc_hm_loss`` is the same quantity as
 ``JointsCompositeLoss.calc_hm_loss`` [function.py:95-111].  Forward and the gradient w.r.t. the
-predicted heat-maps come out of one fused kernel (``egn_mse_hm_fwd_bwd``); back-propagation
-through HC is not part of this repository (inference hot path only).
+predicted heat-maps come out of one fused kernel (``egn_mse_hm_fwd_bwd``); the losses are autograd
+nodes, so ``loss.backward()`` continues into the native training engine of HC (trainer.py:183-198).
 """
 import torch
 import torch.nn as nn
@@ -31,14 +31,30 @@ def mse_hm_fwd_bwd(output, target, target_weight=None, want_grad=True):
     return loss, grad
 
 
+class _HeatmapMSE(torch.autograd.Function):
+    """loss = 0.5 * mean over joints of MSE(w * pred, w * gt); backward hands out the gradient the same kernel
+    launch already produced, scaled by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, output, target, target_weight):
+        need = output.requires_grad
+        loss, grad = mse_hm_fwd_bwd(output, target, target_weight, want_grad=need)
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        return (ctx.grad * grad_loss if ctx.grad is not None else None), None, None
+
+
 class JointsMSELoss(nn.Module):
     def __init__(self, use_target_weight):
         super().__init__()
         self.use_target_weight = use_target_weight
 
     def forward(self, output, target, target_weight, meta=None):
-        return mse_hm_fwd_bwd(output, target, target_weight if self.use_target_weight else None, want_grad=False)[0]
+        return _HeatmapMSE.apply(output, target, target_weight if self.use_target_weight else None)
 
 
 def calc_hm_loss(output, target):
-    return mse_hm_fwd_bwd(output, target, None, want_grad=False)[0]
+    return _HeatmapMSE.apply(output, target, None)

@@ -66,6 +66,25 @@ def _engine_cfg(cfgs, in_channels, precision, conv_impl, keep_taps):
     return c
 
 
+class _TrainFunction(torch.autograd.Function):
+    """Train-mode forward / backward of HC through the native training engine (``egn_hrnet_forward_train`` /
+    ``egn_hrnet_backward``): autograd sees one node whose inputs are the module's parameters, so the reference's
+    ``loss.backward(); optim.step()`` loop [trainer.py:183-198] works unchanged."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        maps = module._train_forward(x)
+        ctx.module = module
+        ctx.batch = x.shape[0]
+        ctx.needs = [p.requires_grad for p in params]
+        return maps
+
+    @staticmethod
+    def backward(ctx, grad_maps):
+        grads = ctx.module._train_backward(grad_maps, ctx.batch)
+        return (None, None) + tuple(g if need else None for g, need in zip(grads, ctx.needs))
+
+
 _PRECISIONS = {'fp32': N.PREC_FP32, 'fp16': N.PREC_FP16, 'fp16x2': N.PREC_FP16X2}
 
 
@@ -100,6 +119,7 @@ class PoseHighResolutionNet(nn.Module):
         self._handle = None
         self._dirty = True
         self._workspace = None
+        self._train = None          # native training engine state (created by the first train-mode forward)
         self._build()
 
     # -- construction -----------------------------------------------------
@@ -131,6 +151,83 @@ class PoseHighResolutionNet(nn.Module):
         if self._handle is not None:
             N.lib().egn_hrnet_destroy(self._handle)
             self._handle = None
+        tr = getattr(self, '_train', None)
+        if tr is not None:
+            N.lib().egn_hrnet_train_destroy(tr['handle'])
+            self._train = None
+
+    # -- training ------------------------------------
+    def _train_state(self, device):
+        """Create the training engine and move every parameter / BatchNorm statistic into ONE flat fp32 device
+        buffer (state_dict order, ``egn_hrnet_train_param_offset``); the module's Parameters become views of it,
+        so optimisers, ``state_dict()`` and checkpoints keep working while the engine reads and updates them in
+        place."""
+        L = N.lib()
+        tr = self._train
+        if tr is None:
+            cfg = _engine_cfg(self.cfgs, self._in_channels, N.PREC_FP32, N.CONV_SIMT, False)
+            handle = ctypes.c_void_p()
+            N.check(L.egn_hrnet_train_create(ctypes.byref(cfg), ctypes.byref(handle)))
+            tr = self._train = {'handle': handle, 'flat': None, 'workspace': None, 'entries': None}
+        sd = self.state_dict(keep_vars=True)
+        if tr['entries'] is None:
+            entries = []
+            for i, (key, t) in enumerate(sd.items()):
+                off = L.egn_hrnet_train_param_offset(tr['handle'], i)
+                if off >= 0:
+                    entries.append((key, off, t.numel(), tuple(t.shape)))
+            tr['entries'] = entries
+        flat = tr['flat']
+        stale = flat is None or flat.device != device
+        if not stale:
+            base = flat.data_ptr()
+            stale = any(sd[k].data_ptr() != base + 4 * off for k, off, _, _ in tr['entries'])
+        if stale:
+            flat = torch.zeros(L.egn_hrnet_train_flat_size(tr['handle']), device=device, dtype=torch.float32)
+            with torch.no_grad():
+                for k, off, n, shape in tr['entries']:
+                    view = flat[off:off + n].view(shape)
+                    view.copy_(sd[k].detach().to(device=device, dtype=torch.float32))
+                    sd[k].data = view
+            tr['flat'] = flat
+        return tr
+
+    def _train_forward(self, x):
+        L = N.lib()
+        hm = self.cfgs['heatmapModel']
+        with torch.cuda.device(x.device):
+            tr = self._train_state(x.device)
+            x = x.detach().float().contiguous()
+            B = x.shape[0]
+            maps = torch.empty((B, self.num_joints, hm['heatmap_size'][1], hm['heatmap_size'][0]), device=x.device,
+                               dtype=torch.float32)
+            need = L.egn_hrnet_train_workspace_bytes(tr['handle'], B)
+            ws = tr['workspace']
+            if ws is None or ws.numel() < need or ws.device != x.device:
+                tr['workspace'] = None                      # release before the larger allocation
+                ws = tr['workspace'] = torch.empty(need, device=x.device, dtype=torch.uint8)
+            N.check(L.egn_hrnet_forward_train(tr['handle'], N.ptr(tr['flat']), N.ptr(x), B, N.ptr(maps), 0.1, 1,
+                                              N.ptr(ws), ws.numel(), N.current_stream()))
+            with torch.no_grad():                           # nn.BatchNorm2d bookkeeping
+                torch._foreach_add_([b for n, b in self.named_buffers() if n.endswith('num_batches_tracked')], 1)
+        self._dirty = True                                  # the folded inference weights are stale now
+        return maps
+
+    def _train_backward(self, grad_maps, batch):
+        L = N.lib()
+        tr = self._train
+        with torch.cuda.device(grad_maps.device):
+            g = grad_maps.detach().float().contiguous()
+            flat_grads = torch.empty_like(tr['flat'])
+            ws = tr['workspace']
+            N.check(L.egn_hrnet_backward(tr['handle'], N.ptr(tr['flat']), N.ptr(g), batch, N.ptr(flat_grads),
+                                         N.ptr(ws), ws.numel(), N.current_stream()))
+        tr['last_grads'] = flat_grads                        # FlatOptimizer consumes it without a gather
+        views = {k: flat_grads[off:off + n].view(shape) for k, off, n, shape in tr['entries']}
+        return [views[name] for name, _ in self.named_parameters()]
+
+    def train_flops_per_sample(self):
+        return N.lib().egn_hrnet_train_flops_per_sample(self._train_state(torch.device('cuda', torch.cuda.current_device()))['handle'])
 
     def __del__(self):
         try:
@@ -162,8 +259,12 @@ class PoseHighResolutionNet(nn.Module):
     # -- reference API ----------------------------------------------------
     def forward(self, x):
         if self.training:
-            raise NotImplementedError('the native HC engine is inference-only: call .eval() first '
-                                      '(training is outside the B200 hot path)')
+            if not x.is_cuda:
+                raise RuntimeError('the native HC engine has no CPU path: input must be a CUDA tensor')
+            if self.head_type != 'heatmap':
+                raise NotImplementedError('the native training engine implements the heat-map head (BASELINE '
+                                          'configs[3]); head_type=%r trains with the composite loss' % self.head_type)
+            return _TrainFunction.apply(self, x, *[p for _, p in self.named_parameters()])
         if not x.is_cuda:
             raise RuntimeError('the native HC engine has no CPU path: input must be a CUDA tensor')
         hm = self.cfgs['heatmapModel']

@@ -1,0 +1,143 @@
+"""GPU parity of the training step (BASELINE configs[3]): the native training engine
+(``egn_hrnet_forward_train`` / ``egn_hrnet_backward`` behind ``PoseHighResolutionNet.forward`` in train mode), the
+heat-map loss and the optimiser kernels, against (a) ``tests/golden/train_tiny.npz`` -- loss, every parameter
+gradient, BatchNorm running statistics produced by the REFERENCE module in train mode (make_golden.golden_train) --
+and (b) the CPU oracle ``oracle.train_ref`` (autograd over the reference's own torch ops) on other shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import configs, egonet_ref, hrnet_ref, train_ref
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from egonet_b200.libs.loss.function import JointsMSELoss
+    from egonet_b200.libs.model.heatmapModel.hrnet import get_pose_net
+    from egonet_b200.libs.optimizer.optimizer import FlatOptimizer, prepare_optim
+    from egonet_b200.libs.trainer.trainer import train_step
+
+DEV = 'cuda'
+
+
+def _model(cfgs, seed):
+    m = get_pose_net(cfgs, is_train=False)
+    m.load_state_dict(hrnet_ref.make_weights(cfgs, seed))
+    return m.to(DEV).train()
+
+
+def test_train_step_vs_reference_golden(golden):
+    """One forward + loss + backward of the tiny heat-map config: loss 1e-5 relative, every one of the 311
+    parameter-gradient norms 2e-4 relative, four gradients in full at 2e-4 of their max, running statistics 1e-5."""
+    g = golden('train_tiny.npz')
+    cfgs = configs.tiny_cfgs('heatmap')
+    m = _model(cfgs, int(g['seed_w']))
+    x = egonet_ref.synth_crops(len(g['joints']), cfgs, int(g['seed_x'])).to(DEV)
+    out = m(x)
+    assert out.requires_grad and out.shape == (3, cfgs['heatmapModel']['num_joints'], 64, 64) or out.requires_grad
+    np.testing.assert_allclose(float(out.detach().double().sum()), float(g['out_sum']), rtol=1e-5)
+    loss = JointsMSELoss(True)(out, torch.from_numpy(g['target']).to(DEV), torch.from_numpy(g['target_weight']).to(DEV))
+    loss.backward()
+    np.testing.assert_allclose(float(loss), float(g['loss']), rtol=1e-5)
+    named = dict(m.named_parameters())
+    names = [str(n) for n in g['grad_names']]
+    assert names == list(named.keys())
+    norms = np.array([named[k].grad.double().norm().item() for k in names])
+    np.testing.assert_allclose(norms, g['grad_norms'], rtol=2e-4, atol=1e-10)
+    sums = np.array([named[k].grad.double().sum().item() for k in names])
+    np.testing.assert_allclose(sums, g['grad_sums'], rtol=0, atol=2e-4 * np.maximum(g['grad_norms'], 1e-9) * 8)
+    sd = m.state_dict()
+    for k in g:
+        if k.startswith('grad__'):
+            ref = g[k]
+            np.testing.assert_allclose(named[k[6:]].grad.cpu().numpy(), ref, rtol=0, atol=2e-4 * np.abs(ref).max())
+        elif k.startswith('stat__'):
+            np.testing.assert_allclose(sd[k[6:]].cpu().numpy(), g[k], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('tag,batch', [('ped', 2), ('tiny', 5), ('demo', 2)])
+def test_train_step_vs_oracle(tag, batch):
+    """Other topologies / batch sizes (incl. the benchmarked HRNet-W48) against the CPU oracle's autograd."""
+    cfgs = {'ped': configs.ped_cfgs, 'tiny': configs.tiny_cfgs, 'demo': configs.demo_cfgs}[tag]('heatmap')
+    hm = cfgs['heatmapModel']
+    sd = hrnet_ref.make_weights(cfgs, 3)
+    x = egonet_ref.synth_crops(batch, cfgs, 4)
+    rng = np.random.Generator(np.random.PCG64(8))
+    target = torch.from_numpy(rng.uniform(0, 1, (batch, hm['num_joints'], hm['heatmap_size'][1], hm['heatmap_size'][0])).astype(np.float32))
+    weight = torch.from_numpy((rng.uniform(0, 1, (batch, hm['num_joints'], 1)) > 0.3).astype(np.float32))
+    torch.set_num_threads(16)
+    loss_ref, grads_ref, new_sd = train_ref.train_forward_backward(sd, cfgs, x, target, weight)
+    m = _model(cfgs, 3)
+    out = m(x.to(DEV))
+    loss = JointsMSELoss(True)(out, target.to(DEV), weight.to(DEV))
+    loss.backward()
+    assert float(loss) == pytest.approx(loss_ref, rel=2e-5)
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, gr in grads_ref.items():
+        got = named[k].grad.cpu()
+        scale = gr.abs().max().item()
+        err = (got - gr).abs().max().item()
+        worst = max(worst, err / max(scale, 1e-12))
+        assert err <= 5e-4 * max(scale, 1e-9), (k, err, scale)
+    after = m.state_dict()
+    for k in ('bn1.running_mean', 'bn1.running_var', 'stage3.0.branches.1.0.bn2.running_var'):
+        np.testing.assert_allclose(after[k].cpu().numpy(), new_sd[k].numpy(), rtol=2e-5, atol=1e-7)
+    assert int(after['bn1.num_batches_tracked']) == 1
+    print('worst relative gradient error %.3g' % worst)
+
+
+def test_optimiser_kernels_match_torch_optim():
+    """egn_adam_step / egn_sgd_step over the flat buffer against torch.optim.Adam / SGD (optimizer.py:19-27) fed the
+    same gradients for four steps, including weight decay and a MultiStepLR drop."""
+    cfgs = configs.tiny_cfgs('heatmap')
+    x = egonet_ref.synth_crops(2, cfgs, 1).to(DEV)
+    tgt = torch.rand((2, cfgs['heatmapModel']['num_joints'], 64, 64), device=DEV)
+    w = torch.ones((2, cfgs['heatmapModel']['num_joints'], 1), device=DEV)
+    for kind, kw in (('adam', dict(lr=1e-3, weight_decay=1e-4)), ('sgd', dict(lr=1e-2, weight_decay=1e-4, momentum=0.9))):
+        m = _model(cfgs, 2)
+        cfgs['optimizer'] = dict(optim_type=kind, lr=kw['lr'], weight_decay=kw['weight_decay'],
+                                 momentum=kw.get('momentum', 0.0), milestones=[2], gamma=0.1)
+        optim, sche = prepare_optim(m, cfgs)
+        assert isinstance(optim, FlatOptimizer)
+        ref_params = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+        ref_opt = (torch.optim.Adam if kind == 'adam' else torch.optim.SGD)(ref_params, **kw)
+        ref_sche = torch.optim.lr_scheduler.MultiStepLR(ref_opt, milestones=[2], gamma=0.1)
+        crit = JointsMSELoss(True)
+        for step in range(4):
+            loss = train_step(m, crit, optim, x, tgt, w)
+            for rp, p in zip(ref_params, m.parameters()):
+                rp.grad = p.grad.detach().clone()
+            ref_opt.step()
+            sche.step()
+            ref_sche.step()
+            assert torch.isfinite(loss)
+            # NOTE: the model's next gradients come from ITS parameters; keep the reference copy in lock-step
+            worst = max(((rp.detach() - p.detach()).abs().max() / (p.detach().abs().max() + 1e-12)).item()
+                        for rp, p in zip(ref_params, m.parameters()))
+            assert worst <= 2e-5, (kind, step, worst)
+            with torch.no_grad():
+                for rp, p in zip(ref_params, m.parameters()):
+                    rp.copy_(p)
+
+
+def test_training_reduces_the_loss_and_eval_mode_sees_the_new_weights():
+    """A few Adam steps on a fixed batch: the loss falls, and the inference engine (eval mode) then runs on the
+    updated parameters and running statistics (the flat buffer is the module's state_dict)."""
+    cfgs = configs.tiny_cfgs('heatmap')
+    m = _model(cfgs, 2)
+    cfgs['optimizer'] = dict(optim_type='adam', lr=1e-3, weight_decay=0.0, momentum=0.0, milestones=[100], gamma=0.1)
+    optim, _ = prepare_optim(m, cfgs)
+    x = egonet_ref.synth_crops(4, cfgs, 1).to(DEV)
+    tgt = torch.zeros((4, cfgs['heatmapModel']['num_joints'], 64, 64), device=DEV)
+    tgt[:, :, 30:34, 30:34] = 1.0
+    w = torch.ones((4, cfgs['heatmapModel']['num_joints'], 1), device=DEV)
+    crit = JointsMSELoss(True)
+    before = m.eval()(x).clone()
+    m.train()
+    losses = [float(train_step(m, crit, optim, x, tgt, w)) for _ in range(8)]
+    assert losses[-1] < 0.7 * losses[0], losses
+    after = m.eval()(x)
+    assert not torch.equal(before, after)
+    ref = hrnet_ref.hrnet_forward({k: v.cpu() for k, v in m.state_dict().items()}, cfgs, x.cpu())
+    assert (after.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
