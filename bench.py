@@ -294,6 +294,54 @@ def e2e_images_block(ego, cfgs, dev, K, steps):
                     'front-end, record dicts back on the host (wall clock around synchronised steps)'}
 
 
+def train_block(dev, batch, steps, pk):
+    """BASELINE configs[3]: heat-map network forward + MSE loss + backward + Adam step at batch 128 on one GPU,
+    through the reference-shaped API (model(data) -> loss_func -> loss.backward() -> optim.step(), trainer.py:183-198)
+    on the native training engine.  fp32 arithmetic (the reference trains in fp32; a bf16 tensor-core path is not
+    built), synthetic crops and Gaussian-like targets resident in HBM."""
+    from egonet_b200 import synth
+    from egonet_b200.libs.loss.function import JointsMSELoss
+    from egonet_b200.libs.model.heatmapModel.hrnet import get_pose_net
+    from egonet_b200.libs.optimizer.optimizer import prepare_optim
+    from egonet_b200.libs.trainer.trainer import train_step
+    cfgs = synth.demo_cfgs('heatmap')
+    hm = cfgs['heatmapModel']
+    model = get_pose_net(cfgs, is_train=False)
+    model.load_state_dict(synth.hc_weights(model.state_dict(), 1))
+    model = model.to(dev).train()
+    cfgs['optimizer'] = dict(optim_type='adam', lr=1e-4, weight_decay=0.0, momentum=0.0, milestones=[1000], gamma=0.1)
+    optim, _ = prepare_optim(model, cfgs)
+    crit = JointsMSELoss(True)
+    xs = [synth.crops(batch, cfgs, 50 + i).to(dev) for i in range(2)]
+    g = torch.Generator().manual_seed(9)
+    tgt = torch.rand((batch, hm['num_joints'], hm['heatmap_size'][1], hm['heatmap_size'][0]), generator=g).to(dev)
+    w = torch.ones((batch, hm['num_joints'], 1), device=dev)
+    losses = []
+    for i in range(2):
+        losses.append(float(train_step(model, crit, optim, xs[i % 2], tgt, w)))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = train_step(model, crit, optim, xs[i % 2], tgt, w)
+    b.record()
+    torch.cuda.synchronize()
+    losses.append(float(loss))
+    ms = a.elapsed_time(b) / steps
+    flops = model.train_flops_per_sample()
+    rate = batch / ms * 1e3
+    ws_gb = model._train['workspace'].numel() / 1e9
+    del model, optim
+    torch.cuda.empty_cache()
+    return {'metric': 'samples/sec (heat-map forward + MSE loss + backward + Adam step)', 'value': round(rate, 2),
+            'unit': 'samples/s', 'batch': batch, 'steps': steps, 'ms_per_step': round(ms, 2), 'dtype': 'f32',
+            'flops_per_sample': int(flops), 'achieved_tflops': round(rate * flops / 1e12, 2),
+            'frac_of_bf16_tensor_peak': round(rate * flops / 1e12 / pk['bf16_tflops_sustained'], 4),
+            'workspace_gb': round(ws_gb, 1), 'loss_first_last': [round(losses[0], 6), round(losses[-1], 6)],
+            'note': 'configs[3] asks for bf16: this engine is fp32 on CUDA cores (reference precision, parity-tested '
+                    'against the reference module and an fp64 oracle); convs are 64x64-tile FFMA kernels'}
+
+
 def stream4096_block(ego, dev_sets, centers, scales, K, world, rank, dist, B):
     """BASELINE configs[4]: a 4096-crop stream block-partitioned over the ranks (4096 / world each), processed
     in micro-batches of B, ONE all_gather of the [4096/world, 7] pose records at the end."""
@@ -410,6 +458,10 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=16)
     ap.add_argument('--cpu-baseline-crops', type=int, default=16, help='crops per CPU pass (same batch as --ref-batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='inference', choices=['inference', 'train'],
+                    help="'train': BASELINE configs[3] (batch 128 training step) as the headline line")
+    ap.add_argument('--train-batch', type=int, default=128)
+    ap.add_argument('--no-train', action='store_true', help='skip the configs[3] block of the default line')
     ap.add_argument('--precision', default='fp16x2', choices=['fp16', 'fp32', 'fp16x2'])
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -429,6 +481,31 @@ def main():
         dist = dist_mod
         dist.init_process_group('nccl', device_id=dev)
 
+    if args.workload == 'train':
+        # configs[3] is the 1-GPU case; N > 1 = data parallel (one process per GPU, 128 samples per rank, ONE
+        # all-reduce of the flat gradient buffer per step: libs/trainer/trainer.py::allreduce_gradients)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        blk = train_block(dev, args.train_batch, args.steps, peaks())
+        t = torch.tensor([blk['ms_per_step']], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            clocks = sampler.stop()
+            ms = float(t[0])
+            blk['ms_per_step'] = round(ms, 2)
+            blk['value'] = round(world * args.train_batch / ms * 1e3, 2)
+            line = {'metric': blk['metric'], 'value': blk['value'], 'unit': blk['unit'], 'n_gpus': world, 'steps': args.steps,
+                    'warmup': 2, 'ms_per_step': blk['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+                    'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                    'config': {'workload': 'configs[3]: train_IGRs path, heat-map forward + backward with the MSE loss + Adam, '
+                                           'batch %d per GPU%s' % (args.train_batch, ', gradients all-reduced (1 collective / step)' if dist else ''),
+                               **blk}, 'clocks': clocks}
+            print(json.dumps(line))
+        if dist:
+            dist.destroy_process_group()
+        return
     from egonet_b200 import synth
     cfgs = synth.demo_cfgs()
     cfgs['heatmapModel']['b200_precision'] = args.precision
@@ -526,6 +603,22 @@ def main():
             q1.record()
             torch.cuda.synchronize()
             b64 = 64 * 10 / (q0.elapsed_time(q1) * 1e-3)
+            # the same batch through EgoNet.forward_crops: eager launches vs ONE CUDA-graph replay per step
+            b64_fc = {}
+            try:
+                for name, fn in (('eager', ego.forward_crops), ('cuda_graph', ego.forward_crops_graphed)):
+                    for i in range(3):
+                        fn(x64[i % n_sets], c64, s64, K=K, alpha_mode='proj')
+                    torch.cuda.synchronize()
+                    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    q0.record()
+                    for i in range(10):
+                        fn(x64[i % n_sets], c64, s64, K=K, alpha_mode='proj')
+                    q1.record()
+                    torch.cuda.synchronize()
+                    b64_fc[name] = round(64 * 10 / (q0.elapsed_time(q1) * 1e-3), 1)
+            except Exception as e:
+                b64_fc['error'] = '%s: %s' % (type(e).__name__, e)
         # ---- BASELINE configs[4]: the 4096-crop stream with a single gather (all ranks take part)
         stream = stream4096_block(ego, dev_sets, centers, scales, K, world, rank, dist, B)
         # ---- per-kernel-class timing for the roofline block (rank 0)
@@ -567,7 +660,9 @@ def main():
         'data': 'synthetic',
         'config': {'workload': 'configs[2]: full per-crop inference (HRNet-W48 heatmap+coords, argmax+soft-argmax '
                                'decode, inverse affine, lifter, pose solve), 256x256 crops, batch %d per GPU' % B,
-                   'batch64': {'crops_per_s': round(b64, 1), 'note': 'configs[1] batch size, same path, 1 GPU'} if b64 else None,
+                   'batch64': {'crops_per_s': round(b64, 1), 'forward_crops': b64_fc,
+                               'note': 'configs[1] batch size, same path, 1 GPU; forward_crops = HC + affine + lifter + pose '
+                                       '(no heat-map decode) launched eagerly vs replayed from one CUDA graph'} if b64 else None,
                    'batch_per_gpu': B, 'global_batch': world * B, 'sharding': 'crops block-partitioned across ranks, '
                    'NCCL all_gather of [B,7] poses per step' if world > 1 else 'single GPU',
                    'l2': 'rotating %d distinct input batches (%.0f MB) > 126 MB L2; activation workspace %.0f MB' % (
@@ -582,6 +677,13 @@ def main():
     if extras:
         line['config']['side_stages'] = extras
     line['config']['stream4096'] = stream
+    if world == 1 and not args.no_train:
+        try:
+            del ego, dev_sets, host_sets
+            torch.cuda.empty_cache()
+            line['config']['train_configs3'] = train_block(dev, args.train_batch, 3, pk)
+        except Exception as e:
+            line['config']['train_configs3'] = {'error': '%s: %s' % (type(e).__name__, e)}
     if fast_mode:
         line['config']['fast_mode_fp16'] = fast_mode
     if e2e_img:

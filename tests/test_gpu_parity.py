@@ -532,3 +532,19 @@ def test_one_process_two_devices():
             outs.append(ego.forward_crops(crops.to('cuda:%d' % d), centers, scales, K=egonet_ref.KITTI_K,
                                           alpha_mode='proj').cpu())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_forward_crops_graphed_equals_eager():
+    """The CUDA-graph replay of the whole path returns exactly what the eager launches return (batch 64 =
+    BASELINE configs[1] size, then a different batch through a second graph, then new inputs through the first)."""
+    cfgs = configs.demo_cfgs()
+    ego = _egonet(cfgs, 'fp16x2')
+    for n, seed in ((64, 5), (7, 6), (64, 8)):
+        crops = egonet_ref.synth_crops(n, cfgs, seed).to(DEV)
+        recs = egonet_ref.synth_boxes(n, cfgs, seed + 1)
+        centers = np.array([r['center'] for r in recs])
+        scales = np.array([r['scale'] for r in recs])
+        eager = ego.forward_crops(crops, centers, scales, K=egonet_ref.KITTI_K, alpha_mode='proj')
+        graphed = ego.forward_crops_graphed(crops, centers, scales, K=egonet_ref.KITTI_K, alpha_mode='proj')
+        assert torch.equal(eager, graphed), n
+    assert len(ego._graphs) == 2

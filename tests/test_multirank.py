@@ -75,3 +75,49 @@ def test_single_process_gather_is_identity():
     assert sharding.all_gather_records(x, 2) is x
     with pytest.raises(ValueError):
         sharding.all_gather_records(x, 3)
+
+
+def _grad_worker(rank, world, port, q):
+    """Data-parallel gradient averaging of libs/trainer/trainer.py over gloo: flat-buffer path (one collective)
+    and the per-parameter fallback."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from egonet_b200.libs.trainer.trainer import allreduce_gradients
+
+        class Flat(torch.nn.Module):                       # stands in for a natively trained module
+            def __init__(self):
+                super().__init__()
+                self.a = torch.nn.Parameter(torch.zeros(3))
+                self.b = torch.nn.Parameter(torch.zeros(2, 2))
+                flat = torch.arange(8, dtype=torch.float32) * (rank + 1)
+                self._train = {'last_grads': flat}
+                self.a.grad, self.b.grad = flat[:3], flat[4:8].view(2, 2)      # views, as the engine hands them out
+
+        m = Flat()
+        n1 = allreduce_gradients(m)
+        mean_scale = sum(r + 1 for r in range(world)) / world
+        ok = n1 == 1 and torch.allclose(m.a.grad, torch.arange(3.) * mean_scale) and \
+            torch.allclose(m.b.grad, (torch.arange(4.) + 4).view(2, 2) * mean_scale)
+        plain = torch.nn.Linear(2, 2)
+        for p in plain.parameters():
+            p.grad = torch.full_like(p, float(rank))
+        n2 = allreduce_gradients(plain)
+        ok = ok and n2 == 2 and all(torch.allclose(p.grad, torch.full_like(p, (world - 1) / 2)) for p in plain.parameters())
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
