@@ -1035,6 +1035,10 @@ struct RunParams {
   int img_rows;              // Hw * Wp
   int dbg;   // tuning experiments (EGN_TC_DBG): 1 no stores, 2 no residual, 4 no MMA, 8 no A load, 16 no B loads
   unsigned long long* ts;  // optional [grid][8] globaltimer stamps (EGN_TC_TS=1)
+  // fp16x2 split storage in the window-run kernel (v2): Cin_p counts the physical channels ([x_hi | x_lo] planes of
+  // run_nh K16 slices each), the streamed weight matrix holds [w_hi | w_lo] per tap, and weight slice sb pairs with
+  // activation slices as in PersistParams (hi*hi -> accumulator H, cross terms -> accumulator L = H + T * n_tile)
+  int run_split, run_nh;
 };
 
 __global__ void __launch_bounds__(kTcThreads, 2)
@@ -1120,9 +1124,15 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
     uint32_t stage = 0, phase = 0, accumulate = 0;
     bool first_tap = true;
+    if (p.run_split && !(p.dbg & 8)) {
+      // cross pairing reads activation chunks out of order: the whole window must have landed
+      for (int c = 0; c < p.kchunks; ++c) mbar_wait(&a_full[c], 0);
+      first_tap = false;
+    }
     for (int r = 0; r < ntap; ++r) {
       for (int q = 0; q < ntap; ++q) {
         const uint32_t shift = (uint32_t)(r * p.Wp + q) * 128u;   // row shift of this tap inside the window
+        const bool tap0 = r == 0 && q == 0;
         for (int c = 0; c < p.kchunks; ++c) {
           if (first_tap && !(p.dbg & 8)) {
             mbar_wait(&a_full[c], 0);
@@ -1134,11 +1144,29 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint64_t bd0 = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
           const int ksteps = (c == p.kchunks - 1) ? last_ksteps : 4;
           if (!(p.dbg & 4) && elect_one()) {
-            for (int k = 0; k < ksteps; ++k) {
-              uint64_t ad = ad0 + (uint64_t)(2 * k);
-              uint32_t d = tmem_base;
-              for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile)
-                umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)(k > 0));
+            if (!p.run_split) {
+              for (int k = 0; k < ksteps; ++k) {
+                uint64_t ad = ad0 + (uint64_t)(2 * k);
+                uint32_t d = tmem_base;
+                for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile)
+                  umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)(k > 0));
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                const int sb = 4 * c + k;                       // weight slice of this tap
+                const int npart = sb < p.run_nh ? 2 : 1;
+                for (int part = 0; part < npart; ++part) {
+                  const int lo = sb < p.run_nh ? part : 1;      // accumulator: 0 = H, 1 = L
+                  const int sa = sb < p.run_nh ? sb + part * p.run_nh : sb - p.run_nh;
+                  uint64_t ad = desc_hi | (uint64_t)(((a_addr0 + (uint32_t)(sa >> 2) * a_chunk + shift) & 0x3FFFFu) >> 4);
+                  ad += (uint64_t)(2 * (sa & 3));
+                  uint32_t d = tmem_base + (uint32_t)(lo * p.T * p.n_tile);
+                  // H is first written by (tap 0, slice 0, x_hi), L by (tap 0, slice 0, x_lo)
+                  const uint32_t acc = (tap0 && sb == 0) ? 0u : 1u;
+                  for (int t = 0; t < p.T; ++t, ad += (128u * 128u) >> 4, d += (uint32_t)p.n_tile)
+                    umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, acc);
+                }
+              }
             }
           }
           accumulate = 1u;
@@ -1160,7 +1188,8 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
-              p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, 0, 0u};
+              p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, p.run_split,
+              (uint32_t)(p.T * p.n_tile)};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), p.T, p.n_tile, n0, tmem_full_bar, [&](int t) {
       // run position -> window position -> (image, row, column); float reciprocals are exact here
       // (positions < 2^16, margins >= 0.5 / pitch)
@@ -1775,7 +1804,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   // ---- v2 window-run configuration (stride-1 convs) ----
   {
     const char* env = getenv("EGN_TC_V2");
-    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks && !split;
+    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks;
     if (allow) {
       const int halo = a.ksize == 3 ? 1 : 0;
       const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
@@ -1783,7 +1812,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const size_t b_stage_bytes = ((size_t)p->n_tile * 128 + 1023) & ~(size_t)1023;
       const int n_it = taps_n * p->kchunks;
       float best = 0.f;
-      const int Tmax = std::min(8, 512 / p->n_tile);
+      const int nacc2 = split ? 2 : 1;                 // fp16x2: accumulators H and L per M tile
+      const int Tmax = std::min(8, 512 / nacc2 / p->n_tile);
       for (int T = 1; T <= Tmax; ++T) {
         for (int multi = 0; multi < 2; ++multi) {
           int THW, TBW;
@@ -1817,9 +1847,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
           const int windows = multi ? 1 : ceil_div(a.H, THW);
           const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
                                    : (double)a.H * a.W / ((double)windows * T * 128);
-          const bool two_per_sm = smem <= 112 * 1024 && pow2_cols(T * p->n_tile) <= 256;
+          const bool two_per_sm = smem <= 112 * 1024 && pow2_cols(nacc2 * T * p->n_tile) <= 256;
           const int ctas = windows * ceil_div(64, TBW) * p->n_tiles;
-          const double cta_cost = T + 0.6 * rows_win / 128.0 + 0.7;
+          const double cta_cost = (split ? 1.5 : 1.0) * T + 0.6 * rows_win / 128.0 * (split ? 2 : 1) + 0.7;
           const double est = ceil_div(ctas, 148) * cta_cost * (two_per_sm ? 0.7 : 1.0);
           const float score = (float)(1.0 / est);
           if (score > best) {
@@ -1828,7 +1858,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
             p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
             p->smem_bytes = smem;
-            p->tmem_cols = pow2_cols(T * p->n_tile);
+            p->tmem_cols = pow2_cols(nacc2 * T * p->n_tile);
           }
         }
       }
@@ -2003,7 +2033,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->stages, p->smem_bytes / 1024, p->tmem_cols);
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][K] fp16, zero padded to whole kc-channel chunks.
   //   plain fp16           K = taps * cin_k, tap row = [w (Cin_p)]
-  //   fp16x2, v3           K = taps * cin_k, tap row = [w_hi (Cin_p) | w_lo (Cin_p)]   (cross pairing by the issue table)
+  //   fp16x2, v2 / v3      K = taps * cin_k, tap row = [w_hi (Cin_p) | w_lo (Cin_p)]   (cross pairing by the issuer)
   //   fp16x2, v1           K = taps * (kchunks + kchunks_h) * kc, tap row = [w_hi | w_hi] chunks, then [w_lo] chunks
   //                        (stage order of conv_tc_kernel: A = [x_hi | x_lo] then A = x_hi again)
   // w_hi = rn16(w), w_lo = rn16(w - w_hi).
@@ -2011,7 +2041,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   const int cin_k = p->kchunks * p->kc;
   p->cin_k = cin_k;
   const bool pack = p->use_persist && p->pack_tail;
-  const bool v1_split = split && !p->use_persist;
+  const bool v1_split = split && !p->use_persist && !p->use_run;
   const int full_k = (p->kchunks - 1) * 64;              // channels of a tap that live in full 64-wide chunks
   const size_t tap_k = v1_split ? (size_t)(p->kchunks + p->kchunks_h) * p->kc : (size_t)cin_k;
   const size_t K = pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * tap_k;
@@ -2303,7 +2333,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   }
   if (p->use_run) {
     RunParams rp{};
-    rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->Cin_p;
+    rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->cin_a;
+    rp.run_split = p->split ? 1 : 0; rp.run_nh = p->Cin_p / 16;
     rp.taps = p->ksize * p->ksize; rp.relu = a.relu;
     rp.halo = p->halo; rp.Wp = p->Wp; rp.Hw = p->Hw; rp.THW = p->THW; rp.TBW = p->TBW;
     rp.win_per_img = ceil_div(p->H, p->THW);

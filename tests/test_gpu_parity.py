@@ -457,7 +457,7 @@ def _unsplit(t, C):
     return (t[..., :C].double() + t[..., Cp:Cp + C].double()).permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize('variant', ['auto', 'no_pair', 'v1_only'])
+@pytest.mark.parametrize('variant', ['auto', 'no_pair', 'no_v3', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
 def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
     """One fused conv in fp16x2 split storage (three error-compensated tcgen05 MMAs per product, two TMEM
@@ -470,8 +470,10 @@ def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
         if not (k == 3 and stride == 1 and W >= 24):
             pytest.skip('CTA pairs only exist in the persistent kernel')
         monkeypatch.setenv('EGN_TC_PAIR', '0')
-    if variant == 'v1_only':
+    if variant in ('no_v3', 'v1_only'):
         monkeypatch.setenv('EGN_TC_V3', '0')
+    if variant == 'v1_only':
+        monkeypatch.setenv('EGN_TC_V2', '0')
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)
     x = torch.randn((B, Cin, H, W), generator=g).to(DEV)
     w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5)
