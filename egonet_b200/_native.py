@@ -103,10 +103,11 @@ SIGNATURES = {
     'egn_hrnet_train_param_trainable': (c_int, [c_void_p, c_int]),
     'egn_hrnet_train_workspace_bytes': (c_size_t, [c_void_p, c_int]),
     'egn_hrnet_train_flops_per_sample': (c_int64, [c_void_p]),
-    'egn_hrnet_forward_train': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p]),
-    'egn_hrnet_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'egn_hrnet_forward_train': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    'egn_hrnet_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'egn_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int] + [c_float] * 5 + [c_void_p]),
     'egn_sgd_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_int, c_void_p]),
+    'egn_coord_loss_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     'egn_generate_target': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_double, c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }

@@ -452,6 +452,57 @@ __global__ void bias_grad_kernel(const double* __restrict__ acc, int C, float* _
 }
 
 // ---------------------------------------------------------------------------
+// coordinate head tail (hrnet.py:457-458, 607-608): a valid kh x kw conv over the whole kh x kw map (= a linear
+// layer over L = kh*kw*Cp inputs) + bias + sigmoid.  Forward is head_tail_kernel (conv_simt.cu); backward here.
+// ---------------------------------------------------------------------------
+// OIHW [Cout][Cin][kh*kw] -> [Cout][tap][Cp] (pad lanes stay zero)
+__global__ void pack_tail_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int Cp, float* __restrict__ out) {
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tp = (int)(e % taps);
+    const int ci = (int)((e / taps) % Cin);
+    const int co = (int)(e / ((int64_t)taps * Cin));
+    out[((size_t)co * taps + tp) * Cp + ci] = w[e];
+  }
+}
+// dlogit = dcoords * c * (1 - c)
+__global__ void tail_dlogit_kernel(const float* __restrict__ dcoords, const float* __restrict__ coords, int n,
+                                   float* __restrict__ dlogit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dlogit[i] = dcoords[i] * coords[i] * (1.f - coords[i]);
+}
+// dW[j][tap][ci] (written straight to OIHW), dbias[j]
+__global__ void tail_wgrad_kernel(const float* __restrict__ dlogit, const float* __restrict__ xin, int B, int Cout, int Cin,
+                                  int taps, int Cp, float* __restrict__ dw_oihw, float* __restrict__ dbias) {
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tp = (int)(e % taps);
+    const int ci = (int)((e / taps) % Cin);
+    const int j = (int)(e / ((int64_t)taps * Cin));
+    const int L = taps * Cp;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dlogit[(size_t)b * Cout + j], xin[(size_t)b * L + tp * Cp + ci], s);
+    dw_oihw[e] = s;
+    if (tp == 0 && ci == 0) {
+      float sb = 0.f;
+      for (int b = 0; b < B; ++b) sb += dlogit[(size_t)b * Cout + j];
+      dbias[j] = sb;
+    }
+  }
+}
+// dxin[b][e] (+)= sum_j dlogit[b][j] * W[j][e]
+__global__ void tail_dgrad_kernel(const float* __restrict__ dlogit, const float* __restrict__ w, int B, int Cout, int L,
+                                  float* __restrict__ dxin, int accumulate) {
+  const int64_t total = (int64_t)B * L;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / L), i = (int)(e % L);
+    float s = 0.f;
+    for (int j = 0; j < Cout; ++j) s = fmaf(dlogit[(size_t)b * Cout + j], w[(size_t)j * L + i], s);
+    dxin[e] = accumulate ? dxin[e] + s : s;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // optimisers over flat buffers (libs/optimizer/optimizer.py:9-41: torch.optim.Adam / SGD semantics)
 // ---------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -511,6 +562,11 @@ struct egn_hrnet_train {
   std::vector<ConvT> convs;                // indexed by op index (unused entries for FUSE ops)
   float* dw_scratch = nullptr;             // largest [taps][Cin_p][Cout_p]
   size_t dw_scratch_elems = 0;
+  // coordinate head (head_type 'coordinates'): linspace coordinate maps, the tail's packed weights, per-batch
+  // coords / logits / dlogit scratch (sized at the first forward with a larger batch)
+  float *d_xs = nullptr, *d_ys = nullptr, *w_tail = nullptr, *tail_io = nullptr;
+  int tail_io_batch = 0;
+  int head1_op = -1, tail_op = -1;
   // workspace plan (per-crop element offsets; multiplied by the batch at run time)
   std::vector<int64_t> out_off, grad_off;  // per tensor
   std::vector<int64_t> y_off;              // per op (pre-BN conv output), -1 when the op has none
@@ -533,6 +589,7 @@ static void free_train(egn_hrnet_train* t) {
     cudaFree(c.sums); cudaFree(c.acc);
   }
   cudaFree(t->dw_scratch);
+  cudaFree(t->d_xs); cudaFree(t->d_ys); cudaFree(t->w_tail); cudaFree(t->tail_io);
   if (t->g) egn_hrnet_destroy(t->g);
 }
 
@@ -559,6 +616,22 @@ static int ensure_device_buffers(egn_hrnet_train* t) {
   }
   t->dw_scratch_elems = biggest;
   EGN_CUDA_CHECK(cudaMalloc(&t->dw_scratch, biggest * sizeof(float)));
+  if (t->tail_op >= 0) {
+    const egn_hrnet_cfg& c = t->g->cfg;
+    std::vector<float> xs(c.heatmap_w), ys(c.heatmap_h);     // numpy.linspace(0, 1, n).astype(float32), hrnet.py:461-466
+    for (int i = 0; i < c.heatmap_w; ++i) xs[i] = c.heatmap_w > 1 ? (float)((double)i / (double)(c.heatmap_w - 1)) : 0.f;
+    for (int i = 0; i < c.heatmap_h; ++i) ys[i] = c.heatmap_h > 1 ? (float)((double)i / (double)(c.heatmap_h - 1)) : 0.f;
+    if (c.heatmap_w > 1) xs.back() = 1.f;
+    if (c.heatmap_h > 1) ys.back() = 1.f;
+    EGN_CUDA_CHECK(cudaMalloc(&t->d_xs, xs.size() * sizeof(float)));
+    EGN_CUDA_CHECK(cudaMalloc(&t->d_ys, ys.size() * sizeof(float)));
+    EGN_CUDA_CHECK(cudaMemcpy(t->d_xs, xs.data(), xs.size() * sizeof(float), cudaMemcpyHostToDevice));
+    EGN_CUDA_CHECK(cudaMemcpy(t->d_ys, ys.data(), ys.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const egn_hrnet_train::ConvT& ct = t->convs[t->tail_op];
+    const size_t wn = (size_t)ct.Cout * ct.taps * ct.Cin_p;
+    EGN_CUDA_CHECK(cudaMalloc(&t->w_tail, wn * sizeof(float)));
+    EGN_CUDA_CHECK(cudaMemset(t->w_tail, 0, wn * sizeof(float)));
+  }
   return EGN_OK;
 }
 
@@ -574,10 +647,6 @@ extern "C" {
 int egn_hrnet_train_create(const egn_hrnet_cfg* cfg, egn_hrnet_train** out) {
   using namespace egn;
   EGN_REQUIRE(cfg && out, "egn_hrnet_train_create: null argument");
-  EGN_REQUIRE(cfg->head_type == EGN_HEAD_HEATMAP,
-              "egn_hrnet_train_create: the training engine implements the heat-map head (BASELINE configs[3]: "
-              "heat-map forward + backward with the MSE loss); the coordinate head trains with the composite loss "
-              "(SURVEY.md 8f row 2), which is not built");
   egn_hrnet_cfg c = *cfg;
   c.precision = EGN_PREC_FP32;
   c.conv_impl = EGN_CONV_SIMT;
@@ -609,7 +678,20 @@ int egn_hrnet_train_create(const egn_hrnet_cfg* cfg, egn_hrnet_train** out) {
   t->convs.resize(g->ops.size());
   for (size_t i = 0; i < g->ops.size(); ++i) {
     const Op& op = g->ops[i];
+    if (op.kind == Op::TAIL) {
+      const ConvWeights& w = g->weights[op.wi];
+      egn_hrnet_train::ConvT& ct = t->convs[i];
+      ct.Cin = w.Cin; ct.Cout = w.Cout; ct.ksize = 0;
+      ct.taps = (w.k / 1000) * (w.k % 1000);            // kh * kw (encoded by the graph builder)
+      ct.Cin_p = g->tensors[op.in].Cp;
+      ct.Cout_p = w.Cout;
+      ct.w_off = flat_index(t, w.conv_key + ".weight");
+      ct.bias_off = flat_index(t, w.conv_key + ".bias");
+      t->tail_op = (int)i;
+      continue;
+    }
     if (op.kind != Op::CONV && op.kind != Op::STEM) continue;
+    if (op.write_heatmap) t->head1_op = (int)i;
     const ConvWeights& w = g->weights[op.wi];
     egn_hrnet_train::ConvT& ct = t->convs[i];
     ct.Cin = w.Cin; ct.Cout = w.Cout; ct.ksize = w.k; ct.taps = w.k * w.k;
@@ -691,10 +773,11 @@ int64_t egn_hrnet_train_flops_per_sample(const egn_hrnet_train* t) {
 }
 
 int egn_hrnet_forward_train(egn_hrnet_train* t, float* flat_params, const float* x, int batch, float* heatmap_out,
-                            float momentum, int update_running_stats, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            float* coords_out, float momentum, int update_running_stats, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   using namespace egn;
   EGN_REQUIRE(t && flat_params && x && heatmap_out, "egn_hrnet_forward_train: null argument");
+  EGN_REQUIRE(!coords_out || t->tail_op >= 0, "egn_hrnet_forward_train: coords_out needs the coordinate head");
   EGN_REQUIRE(batch > 0, "egn_hrnet_forward_train: batch must be positive");
   if (int rc = require_device()) return rc;
   if (!workspace || workspace_bytes < egn_hrnet_train_workspace_bytes(t, batch)) {
@@ -726,6 +809,31 @@ int egn_hrnet_forward_train(egn_hrnet_train* t, float* flat_params, const float*
       if (int rc = launch_fuse(Dtype::F32, a, st)) return rc;
       continue;
     }
+    if (op.kind == Op::TAIL) {
+      egn_hrnet_train::ConvT& ct = t->convs[i];
+      if (t->tail_io_batch < batch) {
+        cudaFree(t->tail_io);
+        t->tail_io = nullptr;
+        EGN_CUDA_CHECK(cudaMalloc(&t->tail_io, (size_t)3 * batch * ct.Cout * sizeof(float)));
+        t->tail_io_batch = batch;
+      }
+      pack_tail_kernel<<<grid_for((int64_t)ct.Cout * ct.Cin * ct.taps), 256, 0, st>>>(flat_params + ct.w_off, ct.Cout, ct.Cin,
+                                                                                     ct.taps, ct.Cin_p, t->w_tail);
+      HeadTailArgs a{};
+      a.in = act(op.in);
+      a.w = t->w_tail;
+      a.bias = flat_params + ct.bias_off;
+      a.coords = t->tail_io;                                   // [B, Cout] sigmoid outputs (kept for the backward pass)
+      a.logits = t->tail_io + (size_t)batch * ct.Cout;
+      a.B = batch;
+      a.L = ct.taps * ct.Cin_p;
+      a.Cout = ct.Cout;
+      a.Cp = ct.Cin_p;
+      if (int rc = launch_head_tail(Dtype::F32, a, st)) return rc;
+      if (coords_out)
+        EGN_CUDA_CHECK(cudaMemcpyAsync(coords_out, t->tail_io, (size_t)batch * ct.Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     if (op.kind != Op::CONV && op.kind != Op::STEM) continue;
     egn_hrnet_train::ConvT& ct = t->convs[i];
     const TensorInfo& to = g->tensors[op.out];
@@ -746,6 +854,11 @@ int egn_hrnet_forward_train(egn_hrnet_train* t, float* flat_params, const float*
     a.bias = ct.bias_p;
     a.B = batch; a.H = H; a.W = W; a.Cin_p = ct.Cin_p; a.OH = to.H; a.OW = to.W; a.Cout_p = ct.Cout_p; a.Cout = ct.Cout;
     a.ksize = ct.ksize; a.stride = stride; a.pad = pad; a.relu = 0;
+    if (op.coord_maps) {                      // head1: channels Cout, Cout + 1 carry the coordinate maps (hrnet.py:602-606)
+      a.coord_maps = 1;
+      a.xs = t->d_xs;
+      a.ys = t->d_ys;
+    }
     if (int rc = launch_conv_simt(Dtype::F32, a, ct.w_fwd, st)) return rc;
     if (!bn) continue;
     const int64_t npix = (int64_t)batch * to.H * to.W;
@@ -762,18 +875,20 @@ int egn_hrnet_forward_train(egn_hrnet_train* t, float* flat_params, const float*
         npix, ct.Cout, ct.Cout_p, relu, act(op.out));
     EGN_LAUNCH_CHECK("train forward conv + bn");
   }
-  // heat-maps: the last conv's NHWC output -> fp32 NCHW
-  const Op& last = g->ops.back();
-  const TensorInfo& th = g->tensors[last.out];
-  if (int rc = launch_nhwc_to_nchw(Dtype::F32, act(last.out), heatmap_out, batch, th.H, th.W, th.Cp, th.C, st)) return rc;
+  // heat-maps: the heat-map conv's NHWC output (its first num_joints channels) -> fp32 NCHW
+  const Op& hop = g->ops[t->head1_op];
+  const TensorInfo& th = g->tensors[hop.out];
+  if (int rc = launch_nhwc_to_nchw(Dtype::F32, act(hop.out), heatmap_out, batch, th.H, th.W, th.Cp, t->convs[t->head1_op].Cout, st))
+    return rc;
   t->last_batch = batch;
   return EGN_OK;
 }
 
-int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float* grad_heatmap, int batch,
-                       float* flat_grads, void* workspace, size_t workspace_bytes, void* stream) {
+int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float* grad_heatmap, const float* grad_coords,
+                       int batch, float* flat_grads, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace egn;
-  EGN_REQUIRE(t && flat_params && grad_heatmap && flat_grads, "egn_hrnet_backward: null argument");
+  EGN_REQUIRE(t && flat_params && flat_grads && (grad_heatmap || grad_coords), "egn_hrnet_backward: null argument");
+  EGN_REQUIRE(!grad_coords || t->tail_op >= 0, "egn_hrnet_backward: grad_coords needs the coordinate head");
   if (t->last_batch != batch || batch <= 0) {
     set_error("egn_hrnet_backward: call egn_hrnet_forward_train with the same batch (%d) and workspace first", batch);
     return EGN_ERR_STATE;
@@ -793,16 +908,36 @@ int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float
   const egn_hrnet_cfg& c = g->cfg;
   EGN_CUDA_CHECK(cudaMemsetAsync(flat_grads, 0, (size_t)t->flat_size * sizeof(float), st));
   std::vector<char> written(g->tensors.size(), 0);     // first writer of a gradient buffer overwrites, later ones add
-  // d loss / d heat-maps arrives as fp32 NCHW
-  const Op& last = g->ops.back();
+  // d loss / d heat-maps arrives as fp32 NCHW; it seeds the gradient of the heat-map conv's output (the coordinate
+  // head's consumers add to it; its coordinate-map channels are constants and stay zero here)
   {
-    const TensorInfo& th = g->tensors[last.out];
-    nchw_to_nhwc_pad_kernel<<<grid_for((int64_t)batch * th.H * th.W * th.Cp), 256, 0, st>>>(
-        grad_heatmap, grad(last.out), batch, th.C, th.H, th.W, th.Cp);
-    written[last.out] = 1;
+    const Op& hop = g->ops[t->head1_op];
+    const TensorInfo& th = g->tensors[hop.out];
+    if (grad_heatmap) {
+      nchw_to_nhwc_pad_kernel<<<grid_for((int64_t)batch * th.H * th.W * th.Cp), 256, 0, st>>>(
+          grad_heatmap, grad(hop.out), batch, t->convs[t->head1_op].Cout, th.H, th.W, th.Cp);
+    } else {
+      EGN_CUDA_CHECK(cudaMemsetAsync(grad(hop.out), 0, (size_t)batch * th.H * th.W * th.Cp * sizeof(float), st));
+    }
+    written[hop.out] = 1;
   }
   for (int i = (int)g->ops.size() - 1; i >= 0; --i) {
     const Op& op = g->ops[i];
+    if (op.kind == Op::TAIL) {
+      if (!grad_coords) continue;
+      egn_hrnet_train::ConvT& ct = t->convs[i];
+      const int n = batch * ct.Cout, L = ct.taps * ct.Cin_p;
+      float* coords = t->tail_io;
+      float* dlogit = t->tail_io + (size_t)2 * batch * ct.Cout;
+      tail_dlogit_kernel<<<ceil_div(n, 256), 256, 0, st>>>(grad_coords, coords, n, dlogit);
+      tail_wgrad_kernel<<<grid_for((int64_t)ct.Cout * ct.Cin * ct.taps), 256, 0, st>>>(
+          dlogit, act(op.in), batch, ct.Cout, ct.Cin, ct.taps, ct.Cin_p, flat_grads + ct.w_off, flat_grads + ct.bias_off);
+      tail_dgrad_kernel<<<grid_for((int64_t)batch * L), 256, 0, st>>>(dlogit, t->w_tail, batch, ct.Cout, L, grad(op.in),
+                                                                      written[op.in]);
+      written[op.in] = 1;
+      EGN_LAUNCH_CHECK("coordinate head tail backward");
+      continue;
+    }
     if (op.out < 0 || !written[op.out]) continue;      // nothing downstream depends on this op
     const TensorInfo& to = g->tensors[op.out];
     if (op.kind == Op::FUSE) {

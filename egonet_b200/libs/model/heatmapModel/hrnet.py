@@ -73,15 +73,17 @@ class _TrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, *params):
-        maps = module._train_forward(x)
+        maps, coords = module._train_forward(x)
         ctx.module = module
         ctx.batch = x.shape[0]
         ctx.needs = [p.requires_grad for p in params]
-        return maps
+        if coords is None:
+            return maps
+        return maps, coords
 
     @staticmethod
-    def backward(ctx, grad_maps):
-        grads = ctx.module._train_backward(grad_maps, ctx.batch)
+    def backward(ctx, grad_maps, grad_coords=None):
+        grads = ctx.module._train_backward(grad_maps, grad_coords, ctx.batch)
         return (None, None) + tuple(g if need else None for g, need in zip(grads, ctx.needs))
 
 
@@ -201,26 +203,29 @@ class PoseHighResolutionNet(nn.Module):
             B = x.shape[0]
             maps = torch.empty((B, self.num_joints, hm['heatmap_size'][1], hm['heatmap_size'][0]), device=x.device,
                                dtype=torch.float32)
+            coords = torch.empty((B, self.num_joints, 2), device=x.device, dtype=torch.float32) \
+                if self.head_type == 'coordinates' else None
             need = L.egn_hrnet_train_workspace_bytes(tr['handle'], B)
             ws = tr['workspace']
             if ws is None or ws.numel() < need or ws.device != x.device:
                 tr['workspace'] = None                      # release before the larger allocation
                 ws = tr['workspace'] = torch.empty(need, device=x.device, dtype=torch.uint8)
-            N.check(L.egn_hrnet_forward_train(tr['handle'], N.ptr(tr['flat']), N.ptr(x), B, N.ptr(maps), 0.1, 1,
-                                              N.ptr(ws), ws.numel(), N.current_stream()))
+            N.check(L.egn_hrnet_forward_train(tr['handle'], N.ptr(tr['flat']), N.ptr(x), B, N.ptr(maps), N.ptr(coords),
+                                              0.1, 1, N.ptr(ws), ws.numel(), N.current_stream()))
             with torch.no_grad():                           # nn.BatchNorm2d bookkeeping
                 torch._foreach_add_([b for n, b in self.named_buffers() if n.endswith('num_batches_tracked')], 1)
         self._dirty = True                                  # the folded inference weights are stale now
-        return maps
+        return maps, coords
 
-    def _train_backward(self, grad_maps, batch):
+    def _train_backward(self, grad_maps, grad_coords, batch):
         L = N.lib()
         tr = self._train
-        with torch.cuda.device(grad_maps.device):
-            g = grad_maps.detach().float().contiguous()
+        with torch.cuda.device(tr['flat'].device):
+            g = grad_maps.detach().float().contiguous() if grad_maps is not None else None
+            gc = grad_coords.detach().float().contiguous() if grad_coords is not None else None
             flat_grads = torch.empty_like(tr['flat'])
             ws = tr['workspace']
-            N.check(L.egn_hrnet_backward(tr['handle'], N.ptr(tr['flat']), N.ptr(g), batch, N.ptr(flat_grads),
+            N.check(L.egn_hrnet_backward(tr['handle'], N.ptr(tr['flat']), N.ptr(g), N.ptr(gc), batch, N.ptr(flat_grads),
                                          N.ptr(ws), ws.numel(), N.current_stream()))
         tr['last_grads'] = flat_grads                        # FlatOptimizer consumes it without a gather
         views = {k: flat_grads[off:off + n].view(shape) for k, off, n, shape in tr['entries']}
@@ -261,9 +266,6 @@ class PoseHighResolutionNet(nn.Module):
         if self.training:
             if not x.is_cuda:
                 raise RuntimeError('the native HC engine has no CPU path: input must be a CUDA tensor')
-            if self.head_type != 'heatmap':
-                raise NotImplementedError('the native training engine implements the heat-map head (BASELINE '
-                                          'configs[3]); head_type=%r trains with the composite loss' % self.head_type)
             return _TrainFunction.apply(self, x, *[p for _, p in self.named_parameters()])
         if not x.is_cuda:
             raise RuntimeError('the native HC engine has no CPU path: input must be a CUDA tensor')

@@ -363,7 +363,7 @@ EGN_API int egn_mse_hm_fwd_bwd(const float* pred, const float* target, const flo
 /* ------------------------------------------------------------------------- */
 typedef struct egn_hrnet_train egn_hrnet_train;
 
-/* cfg as for egn_hrnet_create (precision / conv_impl / keep_taps ignored); head_type must be EGN_HEAD_HEATMAP. */
+/* cfg as for egn_hrnet_create (precision / conv_impl / keep_taps ignored); both head types. */
 EGN_API int egn_hrnet_train_create(const egn_hrnet_cfg* cfg, egn_hrnet_train** out);
 EGN_API void egn_hrnet_train_destroy(egn_hrnet_train* t);
 EGN_API int64_t egn_hrnet_train_flat_size(const egn_hrnet_train* t);            /* floats in the flat buffer */
@@ -374,14 +374,17 @@ EGN_API int64_t egn_hrnet_train_flops_per_sample(const egn_hrnet_train* t);    /
 
 /* Train-mode forward.  flat_params: device fp32 (running statistics inside it are updated in place with
  * `momentum` when update_running_stats != 0, as nn.BatchNorm2d does); x: device fp32 NCHW [B,C,H,W];
- * heatmap_out: device fp32 [B,K,hh,hw].  The workspace keeps every activation for the backward pass. */
+ * heatmap_out: device fp32 [B,K,hh,hw]; coords_out: device fp32 [B,K,2] (coordinate head) or NULL.
+ * The workspace keeps every activation for the backward pass. */
 EGN_API int egn_hrnet_forward_train(egn_hrnet_train* t, float* flat_params, const float* x, int batch,
-                            float* heatmap_out, float momentum, int update_running_stats, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            float* heatmap_out, float* coords_out, float momentum, int update_running_stats,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* Backward of the last forward (same batch, same workspace).  grad_heatmap: device fp32 [B,K,hh,hw] =
- * d loss / d heatmap_out; flat_grads: device fp32, overwritten with d loss / d parameter (flat layout). */
-EGN_API int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float* grad_heatmap, int batch,
-                       float* flat_grads, void* workspace, size_t workspace_bytes, void* stream);
+ * d loss / d heatmap_out or NULL; grad_coords: device fp32 [B,K,2] = d loss / d coords_out or NULL (at least one);
+ * flat_grads: device fp32, overwritten with d loss / d parameter (flat layout). */
+EGN_API int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float* grad_heatmap,
+                       const float* grad_coords, int batch, float* flat_grads, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* Optimiser updates over flat device buffers with torch.optim semantics (optimizer.py:19-27): step counts from 1;
  * trainable_mask (device uint8 [n], NULL = all) skips frozen entries / buffers. */
@@ -390,6 +393,20 @@ EGN_API int egn_adam_step(float* params, const float* grads, float* exp_avg, flo
                   float weight_decay, void* stream);
 EGN_API int egn_sgd_step(float* params, const float* grads, float* momentum_buf, const uint8_t* trainable_mask,
                  int64_t n, int step, float lr, float momentum, float weight_decay, int nesterov, void* stream);
+
+/* Coordinate (L_2d) and cross-ratio (L_cr) terms of JointsCompositeLoss, forward + gradient in one launch.
+ * replaces calc_coor_loss libs/loss/function.py:159-168, calc_cross_ratio_loss :113-138 (appro_cr
+ * libs/common/img_proc.py:709-720) and get_cr_mask :140-153.
+ * coords_pred device fp32 [B,K,2] in (0,1); coords_gt_px device fp32 [B,K,2] in crop pixels (divided by img_w /
+ * img_h inside, as upstream); criterion kinds 0 = mse, 1 = smooth L1, 2 = L1 (loss_dict :16-19), mean reduction;
+ * cr_indices device int32 [L,4] point indices of each line (cr_indices_dict['bbox12'], car_instance.py:83-97) or
+ * NULL; lines whose smallest non-zero pairwise distance is <= cr_threshold are masked out.
+ * loss_out device fp32 [3] = {coor_weight * coor + cr_weight * cr, coor, cr}; grad_out device fp32 [B,K,2] =
+ * d loss_out[0] / d coords_pred, or NULL. */
+EGN_API int egn_coord_loss_fwd_bwd(const float* coords_pred, const float* coords_gt_px, int B, int K, float img_w,
+                           float img_h, int coor_kind, float coor_weight, const int32_t* cr_indices, int L,
+                           int cr_kind, float cr_weight, float target_cr, float cr_threshold, float* loss_out,
+                           float* grad_out, void* stream);
 
 /* Gaussian heat-map targets of the training configuration (BASELINE configs[3]).
  * replaces generate_target libs/common/img_proc.py:347-409 (target_type 'gaussian'), one launch for N samples.

@@ -71,8 +71,11 @@ def joints_mse_loss(pred, target, target_weight=None):
     return loss / K
 
 
-def train_forward_backward(sd, cfgs, x, target, target_weight=None):
+def train_forward_backward(sd, cfgs, x, target, target_weight=None, coords_gt=None, coor_weight=0.1):
     """One forward + backward in training mode.  sd: state dict (not modified).
+    ``coords_gt`` ([B,K,2] in (0,1), coordinate head only) adds the shipped composite loss' second term,
+    ``coor_weight * mean |coords - coords_gt|`` (``JointsCompositeLoss`` ``function.py:170-202`` with
+    ``loss_spec_list: ['mse', 'l1', ...]``, ``loss_weight_list: [1.0, 0.1, ...]``, KITTI_train_IGRs.yml:88-89).
     Returns (loss float, grads {name: tensor}, new_sd with the updated BN running statistics)."""
     work = OrderedDict()
     for k, v in sd.items():
@@ -84,6 +87,8 @@ def train_forward_backward(sd, cfgs, x, target, target_weight=None):
         out = hrnet_ref.hrnet_forward.__wrapped__(work, cfgs, x, ctx=Train)
         maps = out[0] if isinstance(out, tuple) else out
         loss = joints_mse_loss(maps, target, target_weight)
+        if coords_gt is not None:
+            loss = loss + coor_weight * torch.mean(torch.abs(out[1] - coords_gt))
         loss.backward()
     grads = OrderedDict((k, v.grad) for k, v in work.items() if v.requires_grad and v.grad is not None)
     new_sd = OrderedDict()

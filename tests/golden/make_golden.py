@@ -451,6 +451,95 @@ def golden_train(ref):
     save('train_tiny.npz', **arrays)
 
 
+CR_BBOX12 = np.array([[1, 9, 21, 2], [3, 10, 22, 4], [5, 11, 23, 6], [7, 12, 24, 8], [1, 13, 25, 5], [2, 14, 26, 6],
+                      [3, 15, 27, 7], [4, 16, 28, 8], [1, 17, 29, 3], [2, 18, 30, 4], [5, 19, 31, 7], [6, 20, 32, 8]])
+
+
+class _cpu_cuda:
+    """JointsCompositeLoss.forward moves its targets with ``.cuda()`` (function.py:187); point it at the CPU while
+    the goldens are produced (the arithmetic is device independent)."""
+
+    def __enter__(self):
+        self.saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self.saved
+
+
+def golden_composite(ref):
+    """JointsCompositeLoss of the reference (function.py:61-202) with the shipped specification
+    (['mse', 'l1', 'sl1'], weights [1.0, 0.1, 'None'], KITTI_train_IGRs.yml:88-90) and with every term on
+    (cross-ratio weight 0.01, apply_cr_loss): loss and autograd gradients w.r.t. heat-maps and coordinates."""
+    import libs.loss.function as LF
+    import libs.dataset.KITTI.car_instance as CI
+    assert np.array_equal(CI.cr_indices_dict['bbox12'], CR_BBOX12)
+    g = rng(101)
+    B, K = 5, 33
+    arrays = {'cr_indices': CR_BBOX12}
+    hm_pred = g.standard_normal((B, K, 16, 16)).astype(np.float32)
+    hm_gt = g.uniform(0, 1, (B, K, 16, 16)).astype(np.float32)
+    # a plausible projected cuboid per sample + noise, in (0, 1)
+    base = g.uniform(0.2, 0.8, (B, 1, 2)) + 0.15 * g.standard_normal((B, K, 2))
+    coords = np.clip(base, 0.02, 0.98).astype(np.float32)
+    coords[0, 9] = coords[0, 1] + 0.01          # a fore-shortened edge: masked out of the cross-ratio term
+    joints = np.concatenate([(coords + 0.03 * g.standard_normal((B, K, 2))) * 256, np.ones((B, K, 1))], 2)
+    arrays.update(hm_pred=hm_pred, hm_gt=hm_gt, coords=coords, joints=joints)
+    for tag, specs, weights, apply_cr in (('shipped', ['mse', 'l1', 'sl1'], [1.0, 0.1, 'None'], True),
+                                          ('all', ['mse', 'l1', 'sl1'], [1.0, 0.1, 0.01], True),
+                                          ('sl1_mse', ['mse', 'sl1', 'mse'], [0.5, 2.0, 0.05], True),
+                                          ('coor_only', ['None', 'mse', 'None'], [1, 1, 1], False)):
+        f = LF.JointsCompositeLoss(spec_list=specs, img_size=[256, 256], hm_size=[16, 16], loss_weights=weights,
+                                   cr_loss_thres=0.15)
+        f.cr_indices, f.target_cr, f.apply_cr_loss = CR_BBOX12, 4 / 3, apply_cr
+        hp = torch.from_numpy(hm_pred).requires_grad_(True)
+        cp = torch.from_numpy(coords).requires_grad_(True)
+        with _cpu_cuda():
+            loss = f((hp, cp), torch.from_numpy(hm_gt), None, {'transformed_joints': joints.copy()})
+        loss.backward()
+        arrays[tag + '_loss'] = loss.detach().numpy()
+        arrays[tag + '_dcoords'] = cp.grad.numpy()
+        arrays[tag + '_dhm'] = hp.grad.numpy() if hp.grad is not None else np.zeros_like(hm_pred)
+        if 'cr' in f.comp_dict and f.comp_dict['cr'][1] != 'None' and apply_cr:
+            arrays[tag + '_mask'] = f.get_cr_mask(coords, 0.15).numpy()
+    save('loss_composite.npz', **arrays)
+
+
+def golden_train_coord(ref):
+    """One training-mode forward + backward of the reference HC module with the COORDINATE head and the shipped
+    composite loss (heat-map MSE + 0.1 * L1 on coordinates): loss, every gradient norm, a few gradients in full."""
+    import libs.loss.function as LF
+    cfgs = configs.tiny_cfgs()
+    hm = cfgs['heatmapModel']
+    model = ref['hrnet'].get_pose_net(cfgs, is_train=True)
+    model.load_state_dict(hrnet_ref.make_weights(cfgs, 6))
+    model.train()
+    B, K = 3, hm['num_joints']
+    x = egonet_ref.synth_crops(B, cfgs, 8)
+    g = rng(72)
+    joints = np.concatenate([g.uniform(5, hm['input_size'][0] - 5, (B, K, 2)), np.ones((B, K, 1))], 2)
+    vis = np.ones((B, K), dtype=np.float32)
+    params = {'num_joints': K, 'target_type': 'gaussian', 'input_size': np.array(hm['input_size']),
+              'heatmap_size': np.array(hm['heatmap_size']), 'sigma': 2, 'use_different_joints_weight': False}
+    tgts, wts = zip(*[ref['img_proc'].generate_target(joints[b], vis[b], params) for b in range(B)])
+    target = torch.from_numpy(np.stack(tgts))
+    f = LF.JointsCompositeLoss(spec_list=['mse', 'l1', 'sl1'], img_size=hm['input_size'], hm_size=hm['heatmap_size'],
+                               loss_weights=[1.0, 0.1, 'None'], cr_loss_thres=0.15)
+    f.cr_indices, f.target_cr = CR_BBOX12, 4 / 3
+    out = model(x)
+    with _cpu_cuda():
+        loss = f(out, target, None, {'transformed_joints': joints.copy()})
+    loss.backward()
+    named = dict(model.named_parameters())
+    arrays = {'joints': joints, 'target': target.numpy(), 'loss': loss.detach().numpy(), 'seed_w': 6, 'seed_x': 8,
+              'coords': out[1].detach().numpy(), 'maps_sum': np.array(out[0].detach().double().sum().item()),
+              'grad_names': np.array(list(named.keys())),
+              'grad_norms': np.array([named[k].grad.double().norm().item() for k in named])}
+    for k in ('head2.4.weight', 'head2.4.bias', 'head1.0.weight', 'head2.0.conv1.weight', 'head2.3.bn2.weight'):
+        arrays['grad__' + k] = named[k].grad.numpy()
+    save('train_tiny_coord.npz', **arrays)
+
+
 def main():
     ref = import_reference()
     torch.set_num_threads(os.cpu_count())
@@ -470,6 +559,8 @@ def main():
     golden_format(ref)
     golden_train(ref)
     golden_align(ref)
+    golden_composite(ref)
+    golden_train_coord(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,

@@ -155,3 +155,91 @@ def test_training_reduces_the_loss_and_eval_mode_sees_the_new_weights():
     assert not torch.equal(before, after)
     ref = hrnet_ref.hrnet_forward({k: v.cpu() for k, v in m.state_dict().items()}, cfgs, x.cpu())
     assert (after.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+COMPOSITE = {'shipped': (['mse', 'l1', 'sl1'], [1.0, 0.1, 'None'], True), 'all': (['mse', 'l1', 'sl1'], [1.0, 0.1, 0.01], True),
+             'sl1_mse': (['mse', 'sl1', 'mse'], [0.5, 2.0, 0.05], True), 'coor_only': (['None', 'mse', 'None'], [1, 1, 1], False)}
+
+
+@pytest.mark.parametrize('tag', list(COMPOSITE))
+def test_composite_loss_vs_reference_golden(golden, tag):
+    """JointsCompositeLoss (function.py:61-202) -- heat-map MSE + coordinate term + cross-ratio term with its
+    fore-shortening mask -- against the reference class and its autograd gradients: 2e-6 relative on the loss,
+    1e-5 of the gradient scale on d/d coordinates and d/d heat-maps."""
+    from egonet_b200.libs.loss.function import JointsCompositeLoss
+    g = golden('loss_composite.npz')
+    specs, weights, apply_cr = COMPOSITE[tag]
+    f = JointsCompositeLoss(spec_list=specs, img_size=[256, 256], hm_size=[16, 16], loss_weights=weights, cr_loss_thres=0.15)
+    f.cr_indices, f.target_cr, f.apply_cr_loss = g['cr_indices'], 4 / 3, apply_cr
+    hp = torch.from_numpy(g['hm_pred']).to(DEV).requires_grad_(True)
+    cp = torch.from_numpy(g['coords']).to(DEV).requires_grad_(True)
+    loss = f((hp, cp), torch.from_numpy(g['hm_gt']).to(DEV), None, {'transformed_joints': g['joints'].copy()})
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(float(g[tag + '_loss']), rel=2e-6)
+    ref = g[tag + '_dcoords']
+    np.testing.assert_allclose(cp.grad.cpu().numpy(), ref, rtol=0, atol=1e-5 * max(1e-3, np.abs(ref).max()))
+    if hp.grad is not None:
+        np.testing.assert_allclose(hp.grad.cpu().numpy(), g[tag + '_dhm'], rtol=1e-5, atol=1e-10)
+    else:
+        assert not g[tag + '_dhm'].any()
+
+
+def test_train_step_coordinate_head_vs_reference_golden(golden):
+    """The shipped training configuration (KITTI_train_IGRs.yml: coordinate head, heat-map MSE + 0.1 * L1 on the
+    coordinates): forward (coords 1e-5, heat-map sum, loss 1e-5) and every gradient norm against the reference
+    module + JointsCompositeLoss; full gradients of the coordinate head at 2e-3 of their max (see the heat-map test
+    for the conditioning of these numbers)."""
+    from egonet_b200.libs.loss.function import JointsCompositeLoss
+    g = golden('train_tiny_coord.npz')
+    cfgs = configs.tiny_cfgs()
+    hm = cfgs['heatmapModel']
+    m = _model(cfgs, int(g['seed_w']))
+    x = egonet_ref.synth_crops(len(g['joints']), cfgs, int(g['seed_x'])).to(DEV)
+    f = JointsCompositeLoss(spec_list=['mse', 'l1', 'sl1'], img_size=hm['input_size'], hm_size=hm['heatmap_size'],
+                            loss_weights=[1.0, 0.1, 'None'], cr_loss_thres=0.15)
+    maps, coords = m(x)
+    np.testing.assert_allclose(coords.detach().cpu().numpy(), g['coords'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(float(maps.detach().double().sum()), float(g['maps_sum']), rtol=1e-5)
+    loss = f((maps, coords), torch.from_numpy(g['target']).to(DEV), None, {'transformed_joints': g['joints'].copy()})
+    loss.backward()
+    np.testing.assert_allclose(float(loss.detach()), float(g['loss']), rtol=1e-5)
+    named = dict(m.named_parameters())
+    names = [str(n) for n in g['grad_names']]
+    assert names == list(named.keys())
+    norms = np.array([named[k].grad.double().norm().item() for k in names])
+    np.testing.assert_allclose(norms, g['grad_norms'], rtol=5e-3, atol=1e-10)
+    assert (np.abs(norms - g['grad_norms']) <= 5e-4 * g['grad_norms'] + 1e-10).mean() > 0.9
+    for k in g:
+        if k.startswith('grad__'):
+            ref = g[k]
+            np.testing.assert_allclose(named[k[6:]].grad.cpu().numpy(), ref, rtol=0, atol=2e-3 * np.abs(ref).max(), err_msg=k)
+
+
+def test_train_step_coordinate_head_vs_fp64_oracle():
+    """Coordinate head on the benchmarked HRNet-W48 against the fp64 oracle, as for the heat-map head."""
+    cfgs = configs.demo_cfgs()
+    hm = cfgs['heatmapModel']
+    batch = 2
+    sd = hrnet_ref.make_weights(cfgs, 3)
+    x = egonet_ref.synth_crops(batch, cfgs, 4)
+    rng = np.random.Generator(np.random.PCG64(9))
+    target = torch.from_numpy(rng.uniform(0, 1, (batch, hm['num_joints'], 64, 64)).astype(np.float32))
+    cgt = torch.from_numpy(rng.uniform(0.1, 0.9, (batch, hm['num_joints'], 2)).astype(np.float32))
+    torch.set_num_threads(16)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    loss64, truth, _ = train_ref.train_forward_backward(sd64, cfgs, x.double(), target.double(), None, cgt.double())
+    _, grads32, _ = train_ref.train_forward_backward(sd, cfgs, x, target, None, cgt)
+    from egonet_b200.libs.loss.function import JointsCompositeLoss
+    m = _model(cfgs, 3)
+    f = JointsCompositeLoss(spec_list=['mse', 'l1', 'None'], img_size=[1, 1], hm_size=hm['heatmap_size'], loss_weights=[1.0, 0.1, 0.])
+    out = m(x.to(DEV))
+    joints = np.concatenate([cgt.numpy(), np.ones((batch, hm['num_joints'], 1), np.float32)], 2)   # img_size 1: already normalised
+    loss = f(out, target.to(DEV), None, {'transformed_joints': joints})
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(loss64, rel=2e-5)
+    ours = _rel_errors({k: p.grad for k, p in m.named_parameters()}, truth)
+    ref32 = _rel_errors(grads32, truth)
+    eo, er = np.array([ours[k] for k in truth]), np.array([ref32[k] for k in truth])
+    print('coordinate head demo B=2: engine vs fp64 worst %.3g median %.3g | reference fp32 vs fp64 worst %.3g median %.3g' % (
+        eo.max(), np.median(eo), er.max(), np.median(er)))
+    assert eo.max() <= 3 * er.max() + 1e-4 and np.median(eo) <= 3 * np.median(er) + 1e-6

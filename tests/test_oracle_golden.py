@@ -156,3 +156,26 @@ def test_loss_oracle_matches_reference(golden):
         assert loss == pytest.approx(float(g['loss_w%d' % use_w]), rel=1e-6)
         np.testing.assert_allclose(grad, g['grad_w%d' % use_w], rtol=1e-5, atol=1e-10)
     assert float(g['calc_hm_loss']) == pytest.approx(float(g['loss_w0']), rel=1e-7)
+
+
+COMPOSITE_CASES = {'shipped': dict(coor_kind='l1', coor_weight=0.1, hm_w=1.0), 'all': dict(coor_kind='l1', coor_weight=0.1, cr_kind='sl1', cr_weight=0.01, hm_w=1.0),
+                   'sl1_mse': dict(coor_kind='sl1', coor_weight=2.0, cr_kind='mse', cr_weight=0.05, hm_w=0.5),
+                   'coor_only': dict(coor_kind='mse', coor_weight=1.0, hm_w=0.0)}
+
+
+@pytest.mark.parametrize('tag', list(COMPOSITE_CASES))
+def test_composite_loss_oracle_matches_reference(golden, tag):
+    """Coordinate + cross-ratio terms (function.py:113-202) and the heat-map term against the reference's
+    JointsCompositeLoss and its autograd gradients (make_golden.golden_composite)."""
+    g = golden('loss_composite.npz')
+    kw = dict(COMPOSITE_CASES[tag])
+    hm_w = kw.pop('hm_w')
+    total, coor, cr, grad = loss_ref.composite_coord_terms(g['coords'], g['joints'], [256, 256], cr_indices=g['cr_indices'], **kw)
+    hm_loss, hm_grad = loss_ref.joints_mse_loss(g['hm_pred'], g['hm_gt'])
+    assert total + hm_w * hm_loss == pytest.approx(float(g[tag + '_loss']), rel=2e-6)
+    np.testing.assert_allclose(grad, g[tag + '_dcoords'], rtol=0, atol=2e-6 * max(1e-3, np.abs(g[tag + '_dcoords']).max()))
+    np.testing.assert_allclose(hm_w * hm_grad, g[tag + '_dhm'], rtol=1e-5, atol=1e-10)
+    if tag + '_mask' in g:
+        m = loss_ref.cr_mask(g['coords'], g['cr_indices'], 0.15)
+        np.testing.assert_array_equal(m, g[tag + '_mask'][:, :, 0])
+        assert 0 < m.sum() < m.size                     # both masked and unmasked lines are present
