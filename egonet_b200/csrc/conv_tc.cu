@@ -1804,7 +1804,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   // ---- v2 window-run configuration (stride-1 convs) ----
   {
     const char* env = getenv("EGN_TC_V2");
-    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks;
+    // fp16x2: measured slower than the per-tap kernel (96ch@32x32, batch 256: 545 us vs 345 us -- one CTA per SM and
+    // the in-order weight ring expose the L2 latency of every tile); kept behind EGN_TC_V2_SPLIT=1 and tested
+    const bool allow = !(env && atoi(env) == 0) && a.stride == 1 && p->sw == 128 && p->kchunks <= kMaxChunks &&
+                       (!split || (getenv("EGN_TC_V2_SPLIT") && atoi(getenv("EGN_TC_V2_SPLIT"))));
+    const int force_T2 = getenv("EGN_TC_V2_T") ? atoi(getenv("EGN_TC_V2_T")) : 0;
     if (allow) {
       const int halo = a.ksize == 3 ? 1 : 0;
       const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
@@ -1815,6 +1819,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const int nacc2 = split ? 2 : 1;                 // fp16x2: accumulators H and L per M tile
       const int Tmax = std::min(8, 512 / nacc2 / p->n_tile);
       for (int T = 1; T <= Tmax; ++T) {
+        if (force_T2 && T != force_T2) continue;
         for (int multi = 0; multi < 2; ++multi) {
           int THW, TBW;
           if (!multi) {
@@ -1924,7 +1929,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             if (rows_win - 2 * lead > 128 * T) continue;
             const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
             // fp16x2 windows are twice the bytes: also try a single window slot (the measured fp16 plans keep two)
+            const int force_slots = getenv("EGN_TC_ASLOTS") ? atoi(getenv("EGN_TC_ASLOTS")) : 0;
             for (int a_slots = 2; a_slots >= (split ? 1 : 2); --a_slots) {
+            if (force_slots && a_slots != force_slots) continue;
             const size_t a_bytes = (size_t)a_slots * p->kchunks * rows_alloc * 128;
             const size_t fixed = 1024 + 256 + (size_t)n_tile * 4 +
                                  (size_t)a.ksize * a.ksize * groups * T * 16;   // barriers, bias, issue table

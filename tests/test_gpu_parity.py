@@ -472,6 +472,8 @@ def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
         monkeypatch.setenv('EGN_TC_PAIR', '0')
     if variant in ('no_v3', 'v1_only'):
         monkeypatch.setenv('EGN_TC_V3', '0')
+    if variant == 'no_v3':
+        monkeypatch.setenv('EGN_TC_V2_SPLIT', '1')         # the window-run kernel in split storage (off by default: slower)
     if variant == 'v1_only':
         monkeypatch.setenv('EGN_TC_V2', '0')
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)

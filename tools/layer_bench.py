@@ -20,14 +20,15 @@ def run_child(args):
     for (Cin, Cout, H, W, k, st, has_res) in SHAPES[:args.shapes]:
         g = torch.Generator().manual_seed(1)
         Cip, Cop = (Cin + 15) // 16 * 16, (Cout + 15) // 16 * 16
-        x = torch.randn((B, H, W, Cip), generator=g).to(torch.float16).cuda()
+        mul = 2 if args.dtype == 2 else 1          # fp16x2: [hi | lo] planes (random lo planes are fine for timing)
+        x = torch.randn((B, H, W, mul * Cip), generator=g).to(torch.float16).cuda()
         pad = 1 if k == 3 else 0
         OH, OW = (H + 2 * pad - k) // st + 1, (W + 2 * pad - k) // st + 1
-        res = torch.randn((B, OH, OW, Cop), generator=g).to(torch.float16).cuda() if has_res else None
-        out = torch.empty((B, OH, OW, Cop), dtype=torch.float16, device='cuda')
+        res = torch.randn((B, OH, OW, mul * Cop), generator=g).to(torch.float16).cuda() if has_res else None
+        out = torch.empty((B, OH, OW, mul * Cop), dtype=torch.float16, device='cuda')
         w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5).contiguous()
         ms = ctypes.c_float(0)
-        N.check(N.lib().egn_conv2d_bench(1, 1, N.ptr(x), N.ptr(w), None, N.ptr(res), N.ptr(out), B, H, W, Cin, Cout,
+        N.check(N.lib().egn_conv2d_bench(1, args.dtype, N.ptr(x), N.ptr(w), None, N.ptr(res), N.ptr(out), B, H, W, Cin, Cout,
                                          k, st, 1, None, args.iters, ctypes.byref(ms)))
         flops = 2.0 * B * OH * OW * Cout * Cin * k * k
         byts = 2.0 * (x.numel() + out.numel() + (res.numel() if has_res else 0)) + 2.0 * Cop * Cip * k * k
@@ -42,15 +43,22 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--iters', type=int, default=30)
     ap.add_argument('--child', action='store_true')
+    ap.add_argument('--dtype', type=int, default=1, help='1 = fp16, 2 = fp16x2 split storage')
+    ap.add_argument('--variants', default='', help='extra variants: name:ENV=V,ENV=V;name2:...')
     ap.add_argument('--shapes', type=int, default=len(SHAPES), help='only the first N shapes')
     args = ap.parse_args()
     if args.child:
         return run_child(args)
     table = {}
-    for label, env in (('v3_pers', {}), ('v3_nopair', {'EGN_TC_PAIR': '0'}), ('v2_run', {'EGN_TC_V3': '0'}),
-                       ('v1_tap', {'EGN_TC_V3': '0', 'EGN_TC_V2': '0'})):
+    variants = [('v3_pers', {}), ('v3_nopair', {'EGN_TC_PAIR': '0'}), ('v2_run', {'EGN_TC_V3': '0', 'EGN_TC_V2_SPLIT': '1'}),
+                ('v1_tap', {'EGN_TC_V3': '0', 'EGN_TC_V2': '0'})]
+    for item in filter(None, args.variants.split(';')):
+        name, envs = item.split(':')
+        variants.append((name, dict(kv.split('=') for kv in envs.split(','))))
+    for label, env in variants:
         e = dict(os.environ, EGN_TC_VERBOSE='1', **env)
-        r = subprocess.run([sys.executable, __file__, '--child', '--batch', str(args.batch), '--iters', str(args.iters)],
+        r = subprocess.run([sys.executable, __file__, '--child', '--batch', str(args.batch), '--iters', str(args.iters),
+                            '--dtype', str(args.dtype), '--shapes', str(args.shapes)],
                            capture_output=True, text=True, env=e)
         cfg = {}
         for l in r.stderr.splitlines():

@@ -21,13 +21,13 @@ from oracle import configs, egonet_ref, hrnet_ref  # noqa: E402
 
 CASES = [(48, 48, 32, 32, 3, 1, 2), (96, 96, 32, 32, 3, 1, 3), (64, 64, 16, 16, 3, 2, 2), (64, 256, 32, 32, 1, 1, 1),
          (192, 192, 16, 16, 3, 1, 1), (35, 66, 32, 32, 3, 2, 1)]
-VARIANTS = {'auto': {}, 'no_pair': {'EGN_TC_PAIR': '0'}, 'no_v3': {'EGN_TC_V3': '0'},
+VARIANTS = {'auto': {}, 'no_pair': {'EGN_TC_PAIR': '0'}, 'no_v3': {'EGN_TC_V3': '0', 'EGN_TC_V2_SPLIT': '1'},
             'v1_only': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0'}}
 
 
 def convs():
     for vname, env in VARIANTS.items():
-        for k in ('EGN_TC_PAIR', 'EGN_TC_V3', 'EGN_TC_V2'):
+        for k in ('EGN_TC_PAIR', 'EGN_TC_V3', 'EGN_TC_V2', 'EGN_TC_V2_SPLIT'):
             os.environ.pop(k, None)
         os.environ.update(env)
         for dtype, pack in ((1, T._nhwc16), (2, T._split16)):
