@@ -1795,7 +1795,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   const size_t a_stage = 128 * (size_t)p->sw;
   const size_t b_stage = ((size_t)p->n_tile * p->sw + 1023) & ~(size_t)1023;
   const size_t stage = a_stage + b_stage;
-  const size_t budget = stage > 24 * 1024 ? 176 * 1024 : 80 * 1024;
+  // stage ring budget: small stages -> ~80 KB so that two CTAs share an SM; EGN_TC_V1_BUDGET_KB overrides (tuning)
+  const size_t budget = getenv("EGN_TC_V1_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V1_BUDGET_KB")) * 1024
+                                                       : (stage > 24 * 1024 ? 176 * 1024 : 80 * 1024);
   const int n_iters = a.ksize * a.ksize * (p->kchunks + p->kchunks_h);
   size_t st_count = std::min<size_t>((size_t)kMaxStages, budget / stage);
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
@@ -2547,8 +2549,11 @@ umma_rate_kernel(int n, int nacc, int iters, int a_rows_shift, long long* __rest
   uint8_t* sa = smem;                 // 1024 rows x 128 B
   uint8_t* sb = smem + 1024 * 128;    // 256 rows x 128 B
   uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 256 * 128);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
-  // a_rows_shift >= 1000: fill the operands with pseudo-random finite fp16 values instead of zeros
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  // a_rows_shift >= 1000: fill the operands with pseudo-random finite fp16 values instead of zeros;
+  // a_rows_shift >= 2000: additionally TWO issuing threads (warps 1 and 2), each driving nacc / 2 accumulators
+  const bool two = a_rows_shift >= 2000;
+  if (two) a_rows_shift -= 1000;
   const bool random_fill = a_rows_shift >= 1000;
   if (random_fill) a_rows_shift -= 1000;
   for (int i = threadIdx.x; i < (1024 + 256) * 128 / 4; i += 128) {
@@ -2558,7 +2563,8 @@ umma_rate_kernel(int n, int nacc, int iters, int a_rows_shift, long long* __rest
   }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(slot, 512);
@@ -2567,26 +2573,31 @@ umma_rate_kernel(int n, int nacc, int iters, int a_rows_shift, long long* __rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
-  if (warp == 1) {
+  if (warp == 1 || (two && warp == 2)) {
+    const int who = warp - 1;
+    const int my_acc = two ? nacc / 2 : nacc;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t desc_hi = make_smem_desc(0, 128);
-    const uint64_t ad0 = desc_hi | (uint64_t)(((smem_u32(sa) + (uint32_t)a_rows_shift * 128u) & 0x3FFFFu) >> 4);
+    const uint64_t ad0 = desc_hi | (uint64_t)(((smem_u32(sa) + (uint32_t)a_rows_shift * 128u + (uint32_t)who * my_acc * 16384u) & 0x3FFFFu) >> 4);
     const uint64_t bd0 = desc_hi | (uint64_t)((smem_u32(sb) & 0x3FFFFu) >> 4);
     long long t0 = clock64();
     if (elect_one()) {
       for (int it = 0; it < iters; ++it) {
         for (int k = 0; k < 4; ++k) {
           uint64_t ad = ad0 + (uint64_t)(2 * k);
-          uint32_t d = tmem;
-          for (int t = 0; t < nacc; ++t, ad += 1024, d += (uint32_t)n) umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, 1u);
+          uint32_t d = tmem + (uint32_t)(who * my_acc * n);
+          for (int t = 0; t < my_acc; ++t, ad += 1024, d += (uint32_t)n) umma_f16(d, ad, bd0 + (uint64_t)(2 * k), idesc, 1u);
         }
       }
-      umma_commit(bar);
+      umma_commit(&bar[who]);
     }
     __syncwarp();
-    mbar_wait(bar, 0);
+    mbar_wait(&bar[who], 0);
     long long t1 = clock64();
-    if (threadIdx.x == 32) out_cycles[blockIdx.x] = t1 - t0;
+    if ((threadIdx.x & 31) == 0) {
+      if (!two) out_cycles[blockIdx.x] = t1 - t0;
+      else atomicMax((unsigned long long*)&out_cycles[blockIdx.x], (unsigned long long)(t1 - t0));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -2601,6 +2612,7 @@ extern "C" int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift,
   if (int rc = require_device()) return rc;
   long long* d = nullptr;
   EGN_CUDA_CHECK(cudaMalloc(&d, ctas * sizeof(long long)));
+  EGN_CUDA_CHECK(cudaMemset(d, 0, ctas * sizeof(long long)));
   const size_t smem = 1024 + (1024 + 256) * 128 + 64;
   EGN_CUDA_CHECK(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_rate_kernel<<<ctas, 128, smem>>>(n, nacc, iters, a_rows_shift, d);
