@@ -1796,8 +1796,12 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   const size_t b_stage = ((size_t)p->n_tile * p->sw + 1023) & ~(size_t)1023;
   const size_t stage = a_stage + b_stage;
   // stage ring budget: small stages -> ~80 KB so that two CTAs share an SM; EGN_TC_V1_BUDGET_KB overrides (tuning)
+  // fp16x2 with <= 256 TMEM columns per CTA (96-channel layers: 28 KB stages): three stages and TWO CTAs per SM
+  // beat six stages and one (96ch@32x32+res, batch 256: 217 us vs 344 us -- one CTA cannot hide the L2 latency of
+  // its own ring); layers that need all 512 columns keep the deep ring (192ch: 183 us vs 217 us).
+  const bool two_ctas = split && pow2_cols(2 * p->n_tile) <= 256;
   const size_t budget = getenv("EGN_TC_V1_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V1_BUDGET_KB")) * 1024
-                                                       : (stage > 24 * 1024 ? 176 * 1024 : 80 * 1024);
+                        : (stage > 24 * 1024 ? (two_ctas ? 100 * 1024 : 176 * 1024) : 80 * 1024);
   const int n_iters = a.ksize * a.ksize * (p->kchunks + p->kchunks_h);
   size_t st_count = std::min<size_t>((size_t)kMaxStages, budget / stage);
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
