@@ -9,6 +9,7 @@
 // chains :63-133, fuse :282-300, heads :427-467,601-608).
 #include "common.h"
 #include "kernels.h"
+#include "simt_gemm.cuh"
 
 namespace egn {
 
@@ -91,120 +92,154 @@ struct Split16 {
   } while (0)
 
 // ---------------------------------------------------------------------------
-// generic conv: 64 pixels x 64 output channels per CTA, K chunks of 16
+// generic conv (implicit GEMM on CUDA cores): M = output pixels, N = output channels, K = taps x input channels.
+// 128 pixels x BN (64 / 128) channels per CTA, 8 x 4 / 8 x 8 outputs per thread (simt_gemm.cuh), the next K slab
+// prefetched into registers while the current one is multiplied.
 // ---------------------------------------------------------------------------
-constexpr int CBM = 64, CBN = 64, CBK = 16, CTHREADS = 256;
-
-template <typename S>
-__global__ void __launch_bounds__(CTHREADS)
+template <typename S, int GROUPS>
+__global__ void __launch_bounds__(SG_THREADS, 2)
 conv_simt_kernel(ConvArgs p, const float* __restrict__ wp) {
-  __shared__ __align__(16) float As[CBK][CBM + 4];
-  __shared__ __align__(16) float Bs[CBK][CBN];
+  constexpr int BN = 64 * GROUPS;
+  __shared__ __align__(16) float As[SG_BK][SG_APITCH];
+  __shared__ __align__(16) float Bs[SG_BK][BN];
   const int t = threadIdx.x;
   if (t == 0) pdl_trigger();
   pdl_wait();
   const int64_t M = (int64_t)p.B * p.OH * p.OW;
-  const int64_t m0 = (int64_t)blockIdx.x * CBM;
-  const int n0 = blockIdx.y * CBN;
-  // A-load role: pixel lp = t/4, channel quad lq = t%4
+  const int64_t m0 = (int64_t)blockIdx.x * SG_BM;
+  const int n0 = blockIdx.y * BN;
+  // A-load role: pixels lp and lp + 64, channel quad lq
   const int lp = t >> 2, lq = t & 3;
-  const int64_t lm = m0 + lp;
-  const bool lvalid = lm < M;
-  int lb = 0, loh = 0, low = 0;
-  if (lvalid) {
-    lb = (int)(lm / ((int64_t)p.OH * p.OW));
-    const int r = (int)(lm - (int64_t)lb * p.OH * p.OW);
-    loh = r / p.OW;
-    low = r - loh * p.OW;
+  int lb[2], loh[2], low[2];
+  bool lvalid[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t lm = m0 + lp + 64 * h;
+    lvalid[h] = lm < M;
+    lb[h] = loh[h] = low[h] = 0;
+    if (lvalid[h]) {
+      lb[h] = (int)(lm / ((int64_t)p.OH * p.OW));
+      const int r = (int)(lm - (int64_t)lb[h] * p.OH * p.OW);
+      loh[h] = r / p.OW;
+      low[h] = r - loh[h] * p.OW;
+    }
   }
-  // B-load role: row t/16, float4 column t%16
-  const int bk = t >> 4, bc = (t & 15) * 4;
-  // compute role
   const int tx = t & 15, ty = t >> 4;
-  float acc[4][4];
+  float acc[8][4 * GROUPS];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4 * GROUPS; ++j) acc[i][j] = 0.f;
 
   const int taps = p.ksize * p.ksize;
-  for (int tap = 0; tap < taps; ++tap) {
-    const int r = tap / p.ksize, s = tap - r * p.ksize;
-    const int ih = loh * p.stride + r - p.pad, iw = low * p.stride + s - p.pad;
-    const bool pv = lvalid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-    const int64_t spix = ((int64_t)lb * p.H + ih) * p.W + iw;
-    const float* wt = wp + (size_t)tap * p.Cin_p * p.Cout_p;
-    for (int c0 = 0; c0 < p.Cin_p; c0 += CBK) {
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      if (pv) S::load4(p.in, spix, p.Cin_p, c0 + lq * 4, a);
+  const int kslabs = p.Cin_p / SG_BK;                  // Cin_p is a multiple of 16
+  const int nslab = taps * kslabs;
+  float a_reg[2][4];
+  float4 b_reg[GROUPS];
+  auto fetch = [&](int slab) {
+    const int tap = slab / kslabs, c0 = (slab - tap * kslabs) * SG_BK;
+    const int r = tap / p.ksize, q = tap - r * p.ksize;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) As[lq * 4 + c][lp] = a[c];
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + bc < p.Cout_p) b = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(c0 + bk) * p.Cout_p + n0 + bc));
-      *reinterpret_cast<float4*>(&Bs[bk][bc]) = b;
-      __syncthreads();
+    for (int h = 0; h < 2; ++h) {
+      const int ih = loh[h] * p.stride + r - p.pad, iw = low[h] * p.stride + q - p.pad;
+      const bool pv = lvalid[h] && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+      a_reg[h][0] = a_reg[h][1] = a_reg[h][2] = a_reg[h][3] = 0.f;
+      if (pv) S::load4(p.in, ((int64_t)lb[h] * p.H + ih) * p.W + iw, p.Cin_p, c0 + lq * 4, a_reg[h]);
+    }
+    const float* wt = wp + ((size_t)tap * p.Cin_p + c0) * p.Cout_p;
 #pragma unroll
-      for (int k = 0; k < CBK; ++k) {
-        const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float aa[4] = {av.x, av.y, av.z, av.w};
-        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    for (int g = 0; g < GROUPS; ++g) {
+      const int idx = t + g * SG_THREADS;              // float4 index inside the 16 x BN slab
+      const int row = idx / (BN / 4), col = (idx - row * (BN / 4)) * 4;
+      b_reg[g] = n0 + col < p.Cout_p ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)row * p.Cout_p + n0 + col))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&]() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
-      }
+      for (int c = 0; c < 4; ++c) As[lq * 4 + c][lp + 64 * h] = a_reg[h][c];
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      const int idx = t + g * SG_THREADS;
+      const int row = idx / (BN / 4), col = (idx - row * (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[row][col]) = b_reg[g];
+    }
+  };
+  fetch(0);
+  stage();
+  __syncthreads();
+  for (int slab = 0; slab < nslab; ++slab) {
+    if (slab + 1 < nslab) fetch(slab + 1);
+    sg_slab_fma<GROUPS, 4>(As, Bs, tx, ty, acc);
+    __syncthreads();
+    if (slab + 1 < nslab) {
+      stage();
       __syncthreads();
     }
   }
 
   // epilogue: bias (+ residual) (+ ReLU), 4 consecutive channels per store
-  const int n = n0 + tx * 4;
-  if (n >= p.Cout_p) return;
-  const float4 bias = *reinterpret_cast<const float4*>(p.bias + n);
-  const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    float v[4];
+  for (int g = 0; g < GROUPS; ++g) {
+    const int n = n0 + sg_col<4>(tx, g, 0);
+    if (n >= p.Cout_p) continue;
+    const float4 bias = *reinterpret_cast<const float4*>(p.bias + n);
+    const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
-    if (p.res) {
-      float rv[4];
-      S::load4(p.res, m, p.Cout_p, n, rv);
+    for (int i = 0; i < 8; ++i) {
+      const int64_t m = m0 + sg_row(ty, i);
+      if (m >= M) continue;
+      float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] += rv[j];
-    }
-    if (p.relu) {
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][g * 4 + j] + bv[j];
+      if (p.res) {
+        float rv[4];
+        S::load4(p.res, m, p.Cout_p, n, rv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (p.heatmap || p.coord_maps) {
-      const int b = (int)(m / ((int64_t)p.OH * p.OW));
-      const int rr = (int)(m - (int64_t)b * p.OH * p.OW);
-      const int oh = rr / p.OW, ow = rr - oh * p.OW;
-      if (p.heatmap) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (n + j < p.Cout) p.heatmap[(((int64_t)b * p.Cout + n + j) * p.OH + oh) * p.OW + ow] = v[j];
+        for (int j = 0; j < 4; ++j) v[j] += rv[j];
       }
-      if (p.coord_maps) {
+      if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (n + j == p.Cout) v[j] = p.xs[ow];
-          if (n + j == p.Cout + 1) v[j] = p.ys[oh];
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.heatmap || p.coord_maps) {
+        const int b = (int)(m / ((int64_t)p.OH * p.OW));
+        const int rr = (int)(m - (int64_t)b * p.OH * p.OW);
+        const int oh = rr / p.OW, ow = rr - oh * p.OW;
+        if (p.heatmap) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.Cout) p.heatmap[(((int64_t)b * p.Cout + n + j) * p.OH + oh) * p.OW + ow] = v[j];
+        }
+        if (p.coord_maps) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n + j == p.Cout) v[j] = p.xs[ow];
+            if (n + j == p.Cout + 1) v[j] = p.ys[oh];
+          }
         }
       }
+      S::store4(p.out, m, p.Cout_p, n, v);
     }
-    S::store4(p.out, m, p.Cout_p, n, v);
   }
+}
+
+// N tile of the FFMA kernels: 128-wide tiles (8 x 8 per thread) unless 64-wide ones waste fewer columns
+int simt_groups_for(int Cout_p) {
+  const int c128 = ceil_div(Cout_p, 128) * 128, c64 = ceil_div(Cout_p, 64) * 64;
+  return (double)c128 <= 1.25 * (double)c64 ? 2 : 1;
 }
 
 int launch_conv_simt(Dtype dt, const ConvArgs& a, const float* w_packed, cudaStream_t st) {
   const int64_t M = (int64_t)a.B * a.OH * a.OW;
-  dim3 grid((unsigned)ceil_div64(M, CBM), (unsigned)ceil_div(a.Cout_p, CBN));
-  EGN_DISPATCH_STORAGE(dt, S, EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<S>, grid, dim3(CTHREADS), 0, st, a, w_packed)));
+  const int groups = simt_groups_for(a.Cout_p);
+  dim3 grid((unsigned)ceil_div64(M, SG_BM), (unsigned)ceil_div(a.Cout_p, 64 * groups));
+  if (groups == 2)
+    EGN_DISPATCH_STORAGE(dt, S, EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<S, 2>, grid, dim3(SG_THREADS), 0, st, a, w_packed)));
+  else
+    EGN_DISPATCH_STORAGE(dt, S, EGN_CUDA_CHECK(launch_pdl(conv_simt_kernel<S, 1>, grid, dim3(SG_THREADS), 0, st, a, w_packed)));
   EGN_LAUNCH_CHECK("conv_simt_kernel");
   return EGN_OK;
 }

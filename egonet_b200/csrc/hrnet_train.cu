@@ -21,6 +21,7 @@
 #include "common.h"
 #include "hrnet_graph.h"
 #include "kernels.h"
+#include "simt_gemm.cuh"
 
 namespace egn {
 
@@ -223,11 +224,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------
 // convolution data gradient: dx[b,ih,iw,ci] (+)= sum_{r,s,co} dy[b,oh,ow,co] * w[co,ci,r,s] with
-// oh * stride + r - pad = ih (same for columns).  Implicit GEMM, M = input pixels, N = Cin, K = taps x Cout;
-// weights in the "dgrad" layout [tap][Cout_p][Cin_p].
+// oh * stride + r - pad = ih (same for columns).  Implicit GEMM on the register-tiled FFMA core (simt_gemm.cuh):
+// M = input pixels (128 per CTA), N = Cin (64 / 128 per CTA), K = taps x Cout; weights in the "dgrad" layout
+// [tap][Cout_p][Cin_p].
 // ---------------------------------------------------------------------------
-constexpr int GBM = 64, GBN = 64, GBK = 16, GTHREADS = 256;
-
 struct DgradArgs {
   const float* dy;    // [B, OH, OW, Cout_p]
   const float* w;     // [taps][Cout_p][Cin_p]
@@ -235,147 +235,204 @@ struct DgradArgs {
   int B, H, W, Cin_p, OH, OW, Cout_p, ksize, stride, pad, accumulate;
 };
 
-__global__ void __launch_bounds__(GTHREADS) conv_dgrad_kernel(DgradArgs p) {
-  __shared__ __align__(16) float As[GBK][GBM + 4];
-  __shared__ __align__(16) float Bs[GBK][GBN];
+template <int GROUPS>
+__global__ void __launch_bounds__(SG_THREADS, 2) conv_dgrad_kernel(DgradArgs p) {
+  constexpr int BN = 64 * GROUPS;
+  __shared__ __align__(16) float As[SG_BK][SG_APITCH];
+  __shared__ __align__(16) float Bs[SG_BK][BN];
   const int t = threadIdx.x;
   const int64_t M = (int64_t)p.B * p.H * p.W;
-  const int64_t m0 = (int64_t)blockIdx.x * GBM;
-  const int n0 = blockIdx.y * GBN;
+  const int64_t m0 = (int64_t)blockIdx.x * SG_BM;
+  const int n0 = blockIdx.y * BN;
   const int lp = t >> 2, lq = t & 3;
-  const int64_t lm = m0 + lp;
-  const bool lvalid = lm < M;
-  int lb = 0, lih = 0, liw = 0;
-  if (lvalid) {
-    lb = (int)(lm / ((int64_t)p.H * p.W));
-    const int r = (int)(lm - (int64_t)lb * p.H * p.W);
-    lih = r / p.W;
-    liw = r - lih * p.W;
+  int lb[2], lih[2], liw[2];
+  bool lvalid[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t lm = m0 + lp + 64 * h;
+    lvalid[h] = lm < M;
+    lb[h] = lih[h] = liw[h] = 0;
+    if (lvalid[h]) {
+      lb[h] = (int)(lm / ((int64_t)p.H * p.W));
+      const int r = (int)(lm - (int64_t)lb[h] * p.H * p.W);
+      lih[h] = r / p.W;
+      liw[h] = r - lih[h] * p.W;
+    }
   }
-  const int bk = t >> 4, bc = (t & 15) * 4;
   const int tx = t & 15, ty = t >> 4;
-  float acc[4][4];
+  float acc[8][4 * GROUPS];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4 * GROUPS; ++j) acc[i][j] = 0.f;
   const int taps = p.ksize * p.ksize;
-  for (int tap = 0; tap < taps; ++tap) {
-    const int r = tap / p.ksize, s = tap - r * p.ksize;
-    const int nh = lih + p.pad - r, nw = liw + p.pad - s;
-    const int oh = nh / p.stride, ow = nw / p.stride;
-    const bool pv = lvalid && nh >= 0 && nw >= 0 && oh * p.stride == nh && ow * p.stride == nw && oh < p.OH && ow < p.OW;
-    const float* src = p.dy + (((int64_t)lb * p.OH + oh) * p.OW + ow) * p.Cout_p;
-    const float* wt = p.w + (size_t)tap * p.Cout_p * p.Cin_p;
-    for (int c0 = 0; c0 < p.Cout_p; c0 += GBK) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pv) a = *reinterpret_cast<const float4*>(src + c0 + lq * 4);
-      As[lq * 4 + 0][lp] = a.x;
-      As[lq * 4 + 1][lp] = a.y;
-      As[lq * 4 + 2][lp] = a.z;
-      As[lq * 4 + 3][lp] = a.w;
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + bc < p.Cin_p) b = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(c0 + bk) * p.Cin_p + n0 + bc));
-      *reinterpret_cast<float4*>(&Bs[bk][bc]) = b;
-      __syncthreads();
+  const int kslabs = p.Cout_p / SG_BK;
+  const int nslab = taps * kslabs;
+  float4 a_reg[2], b_reg[GROUPS];
+  auto fetch = [&](int slab) {
+    const int tap = slab / kslabs, c0 = (slab - tap * kslabs) * SG_BK;
+    const int r = tap / p.ksize, q = tap - r * p.ksize;
 #pragma unroll
-      for (int k = 0; k < GBK; ++k) {
-        const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float aa[4] = {av.x, av.y, av.z, av.w};
-        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    for (int h = 0; h < 2; ++h) {
+      const int nh = lih[h] + p.pad - r, nw = liw[h] + p.pad - q;
+      const int oh = nh / p.stride, ow = nw / p.stride;
+      const bool pv = lvalid[h] && nh >= 0 && nw >= 0 && oh * p.stride == nh && ow * p.stride == nw && oh < p.OH && ow < p.OW;
+      a_reg[h] = pv ? *reinterpret_cast<const float4*>(p.dy + (((int64_t)lb[h] * p.OH + oh) * p.OW + ow) * p.Cout_p + c0 + lq * 4)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* wt = p.w + ((size_t)tap * p.Cout_p + c0) * p.Cin_p;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int g = 0; g < GROUPS; ++g) {
+      const int idx = t + g * SG_THREADS;
+      const int row = idx / (BN / 4), col = (idx - row * (BN / 4)) * 4;
+      b_reg[g] = n0 + col < p.Cin_p ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)row * p.Cin_p + n0 + col))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&]() {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
-      }
+    for (int h = 0; h < 2; ++h) {
+      As[lq * 4 + 0][lp + 64 * h] = a_reg[h].x;
+      As[lq * 4 + 1][lp + 64 * h] = a_reg[h].y;
+      As[lq * 4 + 2][lp + 64 * h] = a_reg[h].z;
+      As[lq * 4 + 3][lp + 64 * h] = a_reg[h].w;
+    }
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      const int idx = t + g * SG_THREADS;
+      const int row = idx / (BN / 4), col = (idx - row * (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[row][col]) = b_reg[g];
+    }
+  };
+  fetch(0);
+  stage();
+  __syncthreads();
+  for (int slab = 0; slab < nslab; ++slab) {
+    if (slab + 1 < nslab) fetch(slab + 1);
+    sg_slab_fma<GROUPS, 4>(As, Bs, tx, ty, acc);
+    __syncthreads();
+    if (slab + 1 < nslab) {
+      stage();
       __syncthreads();
     }
   }
-  const int n = n0 + tx * 4;
-  if (n >= p.Cin_p) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    float* dst = p.dx + m * p.Cin_p + n;
-    if (p.accumulate) {
-      const float4 old = *reinterpret_cast<const float4*>(dst);
-      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+  for (int g = 0; g < GROUPS; ++g) {
+    const int n = n0 + sg_col<4>(tx, g, 0);
+    if (n >= p.Cin_p) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t m = m0 + sg_row(ty, i);
+      if (m >= M) continue;
+      float4 v = make_float4(acc[i][g * 4], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
+      float* dst = p.dx + m * p.Cin_p + n;
+      if (p.accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(dst);
+        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+      }
+      *reinterpret_cast<float4*>(dst) = v;
     }
-    *reinterpret_cast<float4*>(dst) = v;
   }
 }
 
 // ---------------------------------------------------------------------------
 // convolution weight gradient: dw[tap][ci][co] += sum_{b,oh,ow} x[b, oh*stride + r - pad, ow*stride + s - pad, ci] * dy[b,oh,ow,co]
-// GEMM with K = output pixels: a CTA owns a 64 (ci) x 64 (co) tile of one tap and a slice of the pixels
-// (split-K over blockIdx.z); partial tiles are combined with fp32 atomics into a zeroed buffer.
+// GEMM with K = output pixels on the same FFMA core.  The taps are folded into M (row m' = tap * Cin_p + ci: the
+// A operand of a row is the input pixel shifted by its tap), so 48-channel layers fill 432 of 512 tile rows
+// instead of 48 of 128 per tap; N = Cout (64 / 128 per CTA); split-K over blockIdx.z, partial tiles combined with
+// fp32 atomics into a zeroed [taps * Cin_p][Cout_p] buffer.
 // ---------------------------------------------------------------------------
 struct WgradArgs {
   const float* x;     // [B, H, W, Cin_p]
   const float* dy;    // [B, OH, OW, Cout_p]
   float* dw;          // [taps][Cin_p][Cout_p], zeroed
   int B, H, W, Cin_p, OH, OW, Cout_p, ksize, stride, pad;
-  int co_tiles, pix_per_split;
+  int pix_per_split;
 };
 
-__global__ void __launch_bounds__(GTHREADS) conv_wgrad_kernel(WgradArgs p) {
-  __shared__ __align__(16) float As[GBK][GBM];   // [pixel][ci]
-  __shared__ __align__(16) float Bs[GBK][GBN];   // [pixel][co]
+template <int GROUPS>
+__global__ void __launch_bounds__(SG_THREADS, 2) conv_wgrad_kernel(WgradArgs p) {
+  constexpr int BN = 64 * GROUPS;
+  __shared__ __align__(16) float As[SG_BK][SG_APITCH];   // [pixel][tap * Cin_p + ci]
+  __shared__ __align__(16) float Bs[SG_BK][BN];          // [pixel][co]
   const int t = threadIdx.x;
-  const int ci0 = (blockIdx.x / p.co_tiles) * GBM, co0 = (blockIdx.x % p.co_tiles) * GBN;
-  const int tap = blockIdx.y;
-  const int r = tap / p.ksize, s = tap - r * p.ksize;
-  const int64_t M = (int64_t)p.B * p.OH * p.OW;
+  const int taps = p.ksize * p.ksize;
+  const int Mrows = taps * p.Cin_p;
+  const int m0 = blockIdx.x * SG_BM, n0 = blockIdx.y * BN;
+  const int64_t Mpix = (int64_t)p.B * p.OH * p.OW;
   const int64_t k_begin = (int64_t)blockIdx.z * p.pix_per_split;
-  const int64_t k_end = min(M, k_begin + p.pix_per_split);
-  const int lp = t >> 4, lc = (t & 15) * 4;       // load role: pixel lp of the 16-pixel step, 4 channels at lc
+  const int64_t k_end = min(Mpix, k_begin + p.pix_per_split);
+  // A-load role: slab pixel t / 32 (+ 8), 4 consecutive rows at (t % 32) * 4; the rows' tap / channel are fixed
+  const int apx = t >> 5, am = m0 + (t & 31) * 4;
+  const bool arow = am < Mrows;
+  const int atap = arow ? am / p.Cin_p : 0, aci = arow ? am - atap * p.Cin_p : 0;
+  const int ar = atap / p.ksize, as_ = atap - ar * p.ksize;
   const int tx = t & 15, ty = t >> 4;
-  float acc[4][4];
+  float acc[8][4 * GROUPS];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int64_t k0 = k_begin; k0 < k_end; k0 += GBK) {
-    const int64_t m = k0 + lp;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (m < k_end) {
-      const int bi = (int)(m / ((int64_t)p.OH * p.OW));
-      const int rem = (int)(m - (int64_t)bi * p.OH * p.OW);
-      const int oh = rem / p.OW, ow = rem - oh * p.OW;
-      const int ih = oh * p.stride + r - p.pad, iw = ow * p.stride + s - p.pad;
-      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && ci0 + lc < p.Cin_p)
-        a = *reinterpret_cast<const float4*>(p.x + (((int64_t)bi * p.H + ih) * p.W + iw) * p.Cin_p + ci0 + lc);
-      if (co0 + lc < p.Cout_p) b = *reinterpret_cast<const float4*>(p.dy + m * p.Cout_p + co0 + lc);
+    for (int j = 0; j < 4 * GROUPS; ++j) acc[i][j] = 0.f;
+  float4 a_reg[2], b_reg[GROUPS];
+  auto fetch = [&](int64_t k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t m = k0 + apx + 8 * h;
+      a_reg[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (arow && m < k_end) {
+        const int bi = (int)(m / ((int64_t)p.OH * p.OW));
+        const int rem = (int)(m - (int64_t)bi * p.OH * p.OW);
+        const int oh = rem / p.OW, ow = rem - oh * p.OW;
+        const int ih = oh * p.stride + ar - p.pad, iw = ow * p.stride + as_ - p.pad;
+        if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+          a_reg[h] = *reinterpret_cast<const float4*>(p.x + (((int64_t)bi * p.H + ih) * p.W + iw) * p.Cin_p + aci);
+      }
     }
-    *reinterpret_cast<float4*>(&As[lp][lc]) = a;
-    *reinterpret_cast<float4*>(&Bs[lp][lc]) = b;
-    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < GBK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float aa[4] = {av.x, av.y, av.z, av.w};
-      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    for (int g = 0; g < GROUPS; ++g) {
+      const int idx = t + g * SG_THREADS;
+      const int row = idx / (BN / 4), col = (idx - row * (BN / 4)) * 4;
+      const int64_t m = k0 + row;
+      b_reg[g] = (m < k_end && n0 + col < p.Cout_p) ? *reinterpret_cast<const float4*>(p.dy + m * p.Cout_p + n0 + col)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) *reinterpret_cast<float4*>(&As[apx + 8 * h][(t & 31) * 4]) = a_reg[h];
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g) {
+      const int idx = t + g * SG_THREADS;
+      const int row = idx / (BN / 4), col = (idx - row * (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[row][col]) = b_reg[g];
+    }
+  };
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stage();
     __syncthreads();
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += SG_BK) {
+      const bool more = k0 + SG_BK < k_end;
+      if (more) fetch(k0 + SG_BK);
+      sg_slab_fma<GROUPS, 4>(As, Bs, tx, ty, acc);
+      __syncthreads();
+      if (more) {
+        stage();
+        __syncthreads();
+      }
+    }
   }
-  float* dst = p.dw + (size_t)tap * p.Cin_p * p.Cout_p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + ty * 4 + i;
-    if (ci >= p.Cin_p) continue;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + sg_row(ty, i);
+    if (m >= Mrows) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + tx * 4 + j;
-      if (co < p.Cout_p) atomicAdd(dst + (size_t)ci * p.Cout_p + co, acc[i][j]);
-    }
+    for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = n0 + sg_col<4>(tx, g, j);
+        if (co < p.Cout_p) atomicAdd(p.dw + (size_t)m * p.Cout_p + co, acc[i][g * 4 + j]);
+      }
   }
 }
 
@@ -993,14 +1050,14 @@ int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float
       a.dw = t->dw_scratch;
       a.B = batch; a.H = H; a.W = W; a.Cin_p = ct.Cin_p; a.OH = to.H; a.OW = to.W; a.Cout_p = ct.Cout_p;
       a.ksize = ct.ksize; a.stride = stride; a.pad = pad;
-      const int ci_tiles = ceil_div(ct.Cin_p, GBM);
-      a.co_tiles = ceil_div(ct.Cout_p, GBN);
-      const int tiles = ci_tiles * a.co_tiles * ct.taps;
-      int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div64(148 * 6, tiles), ceil_div64(npix, 256)));
-      a.pix_per_split = (int)(ceil_div64(ceil_div64(npix, splits), GBK) * GBK);
+      const int groups = simt_groups_for(ct.Cout_p);
+      const int m_tiles = ceil_div(ct.taps * ct.Cin_p, SG_BM), n_tiles = ceil_div(ct.Cout_p, 64 * groups);
+      int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div64(148 * 4, m_tiles * n_tiles), ceil_div64(npix, 512)));
+      a.pix_per_split = (int)(ceil_div64(ceil_div64(npix, splits), SG_BK) * SG_BK);
       splits = ceil_div64(npix, a.pix_per_split);
-      dim3 grid((unsigned)(ci_tiles * a.co_tiles), (unsigned)ct.taps, (unsigned)splits);
-      conv_wgrad_kernel<<<grid, GTHREADS, 0, st>>>(a);
+      dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+      if (groups == 2) conv_wgrad_kernel<2><<<grid, SG_THREADS, 0, st>>>(a);
+      else conv_wgrad_kernel<1><<<grid, SG_THREADS, 0, st>>>(a);
       unpack_wgrad_kernel<<<grid_for((int64_t)ct.Cout * ct.Cin * ct.taps), 256, 0, st>>>(
           t->dw_scratch, ct.Cout, ct.Cin, ct.taps, ct.Cin_p, ct.Cout_p, flat_grads + ct.w_off);
     }
@@ -1012,8 +1069,10 @@ int egn_hrnet_backward(egn_hrnet_train* t, const float* flat_params, const float
       a.dx = grad(op.in);
       a.B = batch; a.H = H; a.W = W; a.Cin_p = ct.Cin_p; a.OH = to.H; a.OW = to.W; a.Cout_p = ct.Cout_p;
       a.ksize = ct.ksize; a.stride = stride; a.pad = pad; a.accumulate = written[op.in];
-      dim3 grid((unsigned)ceil_div64((int64_t)batch * H * W, GBM), (unsigned)ceil_div(ct.Cin_p, GBN));
-      conv_dgrad_kernel<<<grid, GTHREADS, 0, st>>>(a);
+      const int groups = simt_groups_for(ct.Cin_p);
+      dim3 grid((unsigned)ceil_div64((int64_t)batch * H * W, SG_BM), (unsigned)ceil_div(ct.Cin_p, 64 * groups));
+      if (groups == 2) conv_dgrad_kernel<2><<<grid, SG_THREADS, 0, st>>>(a);
+      else conv_dgrad_kernel<1><<<grid, SG_THREADS, 0, st>>>(a);
       written[op.in] = 1;
     }
     EGN_LAUNCH_CHECK("train backward conv");

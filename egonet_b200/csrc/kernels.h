@@ -37,6 +37,8 @@ struct ConvArgs {
 
 // CUDA-core implicit GEMM (exact fp32 accumulation, fp32 weights [tap][Cin_p][Cout_p]).
 int launch_conv_simt(Dtype dt, const ConvArgs& a, const float* w_packed, cudaStream_t st);
+// 64-channel column groups per CTA (1 or 2) the FFMA kernels use for this output width
+int simt_groups_for(int Cout_p);
 
 // Stem conv1: fp32 NCHW network input -> NHWC, 3x3 stride 2 pad 1, Cin in {3,5}, Cout 64.
 struct StemArgs {
