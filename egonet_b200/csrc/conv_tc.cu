@@ -1257,6 +1257,11 @@ struct PersistParams {
   int split, nh, nblk_plane;
   int a_slots;          // input-window slots in smem: 2 (window j+1 loads while j is multiplied) or 1 (load and MMA
                         // phases of consecutive windows serialise; the epilogue still overlaps -- TMEM stays double buffered)
+  // chunk phasing (one window slot of TWO 64-channel chunks, fp16x2): the issue table is ordered phase A = every MMA
+  // whose activation slice lies in chunk 0, then phase B = those in chunk 1, and each chunk has its own full / empty
+  // barrier (a_full[c] / a_empty[c]).  Chunk 0 of the next window reloads while phase B runs, chunk 1 while the next
+  // phase A runs: the single slot behaves like a double buffer for most of the load.  n_phase_a = MMAs of phase A.
+  int chunk_phase, n_phase_a;
 };
 
 // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps).
@@ -1317,9 +1322,36 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int n_mma = p.taps * groups * p.T;
     const int ntap_w = p.halo ? 3 : 1;
     const uint32_t b_stage_t = ((uint32_t)pp.b_rows * 128u + 1023u) & ~1023u;
+    // activation slice of group g of a tap (split storage; see PersistParams)
+    auto slice_of = [&](int g) { return g < 2 * pp.nh ? (g >> 1) + (g & 1) * pp.nh : g - 2 * pp.nh; };
+    // chunk phasing: groups of a tap that read chunk 0 (phase A) / chunk 1 (phase B), and the first group in ISSUE
+    // order that writes each accumulator (it must not accumulate)
+    int n_a = groups, first_h = 0, first_l = 1;
+    if (pp.chunk_phase) {
+      n_a = 0;
+      first_h = first_l = -1;
+      for (int ph = 0; ph < 2; ++ph)
+        for (int g = 0; g < groups; ++g) {
+          if ((slice_of(g) >> 2) != ph) continue;
+          if (ph == 0) ++n_a;
+          const int lo_g = g < 2 * pp.nh ? (g & 1) : 1;
+          if (lo_g && first_l < 0) first_l = g;
+          if (!lo_g && first_h < 0) first_h = g;
+        }
+    }
     for (int i = threadIdx.x; i < n_mma; i += (int)blockDim.x) {
-      const int t = i % p.T, kk = i / p.T;
-      const int tap = kk / groups, g = kk - tap * groups;
+      int t = i % p.T, kk = i / p.T;
+      int tap = kk / groups, g = kk - tap * groups;
+      if (pp.chunk_phase) {
+        // issue position i -> (phase, tap, rank inside the phase) -> group g
+        const int n_b = groups - n_a;
+        const int in_a = kk < p.taps * n_a;
+        const int kq = in_a ? kk : kk - p.taps * n_a, per = in_a ? n_a : n_b;
+        tap = kq / per;
+        int rank = kq - tap * per;
+        for (g = 0; g < groups; ++g)
+          if ((slice_of(g) >> 2) == (in_a ? 0 : 1) && rank-- == 0) break;
+      }
       // A slice sa, weight slice sb, accumulator, position of this group among the groups using weight slice sb
       int sa = g, sb = g, lo = 0, first_of_sb = 1, last_of_sb = 1;
       if (pp.split) {
@@ -1356,8 +1388,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       e.y = (pp.b_resident ? (wt * b_stage_t) >> 4 : 0u) + 2u * ks;
       if (pp.split) {
         e.z = (uint32_t)((lo * p.T + t) * p.n_tile);
-        // first MMA into H is group 0 of tap 0, first into L is group 1 of tap 0
-        e.w = (tap == 0 && g == lo) ? 0u : 1u;
+        // first MMA into H is group 0 of tap 0, first into L is group 1 of tap 0 (in issue order: first_h / first_l)
+        e.w = (tap == 0 && g == (lo ? first_l : first_h)) ? 0u : 1u;
       } else {
         e.z = (uint32_t)(((kk % pp.ksplit) * p.T + t) * p.n_tile);
         e.w = kk >= pp.ksplit ? 1u : 0u;
@@ -1411,8 +1443,25 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int wb = w0; wb < pp.n_windows; wb += gridDim.x, ++j) {
       const int w = wb + w_off;
       const int slot = pp.a_slots == 2 ? (j & 1) : 0;
-      mbar_wait(&a_empty[slot], (uint32_t)(((pp.a_slots == 2 ? j >> 1 : j) & 1) ^ 1));
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
+      if (pp.chunk_phase) {
+        // one slot, two chunks, each released by its own phase of the MMA loop
+        for (int c = 0; c < 2; ++c) {
+          mbar_wait(&a_empty[c], (uint32_t)((j & 1) ^ 1));
+          if (!(p.dbg & 8) && elect_one()) {
+            mbar_expect_tx(&a_full[c], p.a_bytes);
+            tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, -p.halo, win * p.THW - p.halo, bg * p.TBW);
+          }
+        }
+        if (p.res && !pp.n_stage && !(p.dbg & 128) && w < pp.n_windows && elect_one()) {
+          const int b0 = bg * p.TBW, h0 = win * p.THW;
+          const int rows = p.TBW > 1 ? min(p.TBW, p.B - b0) * p.H : min(p.THW, p.H - h0);
+          const int cpitch = pp.split ? 2 * p.Cout_p : p.Cout_p;
+          l2_prefetch_bulk(p.res + ((size_t)b0 * p.H + h0) * p.W * cpitch, (uint32_t)(rows * p.W * cpitch * 2));
+        }
+        continue;
+      }
+      mbar_wait(&a_empty[slot], (uint32_t)(((pp.a_slots == 2 ? j >> 1 : j) & 1) ^ 1));
       if (!(p.dbg & 8) && elect_one()) {
         if constexpr (kPair) {
           // both windows of the iteration are accounted for on the leader's barrier
@@ -1506,6 +1555,25 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           umma_commit_pair(&a_empty[aslot]);    // both CTAs' window slots may be refilled
           umma_commit_pair(&acc_full[slot]);    // both CTAs' accumulator halves complete
+          continue;
+        }
+        if (pp.chunk_phase) {
+          // phase A (chunk 0, already waited for above), release chunk 0, phase B (chunk 1), release chunk 1
+#pragma unroll 4
+          for (int i = 0; i < pp.n_phase_a; ++i) {
+            const uint4 e = s_issue[i];
+            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+          }
+          umma_commit(&a_empty[0]);
+          if (!(p.dbg & 8)) mbar_wait(&a_full[1], aph);
+          tc_fence_after();
+#pragma unroll 4
+          for (int i = pp.n_phase_a; i < n_mma; ++i) {
+            const uint4 e = s_issue[i];
+            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+          }
+          umma_commit(&a_empty[1]);
+          umma_commit(&acc_full[slot]);
           continue;
         }
         if (pp.b_resident) {
@@ -1981,7 +2049,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const double t_mma = (double)a.ksize * a.ksize * groups * T * mma_cyc;
             const double t_w = resident ? 0.0 : (double)w_tiles * 2400.0;
             const double t_a = (double)p->kchunks * rows_win * 128 / 48.0;      // window load, ~48 B/cycle/SM
-            for (int S = max_stage; S >= 0; --S) {
+            const int min_stage = getenv("EGN_TC_STAGE_MIN") ? atoi(getenv("EGN_TC_STAGE_MIN")) : 0;   // tuning
+            for (int S = max_stage; S >= min_stage; --S) {
               if (S && !cb) continue;
               const size_t smem_s = smem + (size_t)S * nblk * blk_bytes * nacc;     // split: hi and lo planes staged
               if (smem_s > smem_cap) continue;
@@ -2293,6 +2362,18 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       if (p->split) ks = 2;          // fp16x2: accumulator H (hi*hi) and L (cross terms), summed by the epilogue
       pp.ksplit = ks;
       rp.tmem_cols = pow2_cols(2 * ks * p->T * rp.n_tile);
+    }
+    // chunk phasing of the single window slot (see PersistParams)
+    pp.chunk_phase = (p->split && p->a_slots == 1 && p->kchunks == 2 && p->b_resident && !pair &&
+                      !(getenv("EGN_TC_NO_CHUNK_PHASE"))) ? 1 : 0;
+    if (pp.chunk_phase) {
+      const int groups = 3 * pp.nh;
+      int n_a = 0;
+      for (int g = 0; g < groups; ++g) {
+        const int sa = g < 2 * pp.nh ? (g >> 1) + (g & 1) * pp.nh : g - 2 * pp.nh;
+        if ((sa >> 2) == 0) ++n_a;
+      }
+      pp.n_phase_a = rp.taps * n_a * p->T;
     }
     CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
     if (p->n_stage && !head) {
