@@ -108,6 +108,8 @@ SIGNATURES = {
     'egn_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int] + [c_float] * 5 + [c_void_p]),
     'egn_sgd_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_int, c_void_p]),
     'egn_coord_loss_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_float, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    'egn_box_overlaps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'egn_image_box_overlaps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'egn_generate_target': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_double, c_void_p, c_void_p, c_void_p]),
     'egn_observation_angle': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p]),
 }

@@ -19,7 +19,7 @@ SRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'lib', 'libegonet_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-SOURCES = ['common.cu', 'decode.cu', 'pose.cu', 'lifter.cu', 'conv_simt.cu', 'conv_tc.cu', 'hrnet_engine.cu', 'hrnet_train.cu', 'loss.cu', 'crop.cu', 'pnp.cu']
+SOURCES = ['common.cu', 'decode.cu', 'pose.cu', 'lifter.cu', 'conv_simt.cu', 'conv_tc.cu', 'hrnet_engine.cu', 'hrnet_train.cu', 'loss.cu', 'crop.cu', 'pnp.cu', 'eval.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr',
          '-I', os.path.join(ROOT, 'include'), '-I', SRC]

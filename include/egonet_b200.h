@@ -408,6 +408,21 @@ EGN_API int egn_coord_loss_fwd_bwd(const float* coords_pred, const float* coords
                            int cr_kind, float cr_weight, float target_cr, float cr_threshold, float* loss_out,
                            float* grad_out, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* KITTI object-evaluation overlaps, all pairs of a frame */
+/* replaces groundBoxOverlap / box3DOverlap / imageBoxOverlap of               */
+/* tools/kitti-eval/evaluate_object_3d_offline.cpp:224-344 (Boost.Geometry     */
+/* polygon intersection of the oriented ground-plane rectangles).              */
+/* det device fp64 [D,7], gt device fp64 [G,7], rows = ry, h, w, l, t1 (x),    */
+/* t2 (y of the box bottom), t3 (z); criterion -1 union, 0 / detection area,   */
+/* 1 / ground-truth area.  ground_out / box3d_out device fp64 [D,G] or NULL.   */
+/* ------------------------------------------------------------------------- */
+EGN_API int egn_box_overlaps(const double* det, const double* gt, int D, int G, int criterion, double* ground_out,
+                     double* box3d_out, void* stream);
+/* det / gt device fp64 [D,4] / [G,4] = x1, y1, x2, y2 -> out [D,G] */
+EGN_API int egn_image_box_overlaps(const double* det, const double* gt, int D, int G, int criterion, double* out,
+                           void* stream);
+
 /* Gaussian heat-map targets of the training configuration (BASELINE configs[3]).
  * replaces generate_target libs/common/img_proc.py:347-409 (target_type 'gaussian'), one launch for N samples.
  * joints device fp64 [N,K,3] (crop pixels; column 2 = visibility when joints_vis is NULL), joints_vis device

@@ -540,6 +540,43 @@ def golden_train_coord(ref):
     save('train_tiny_coord.npz', **arrays)
 
 
+KITTI_LABEL = """Car 0.00 0 -1.58 587.01 173.33 614.12 200.12 1.65 1.67 3.64 -0.65 1.71 46.70 -1.59 0.91
+Pedestrian 0.00 1 0.21 423.17 173.67 433.17 224.03 1.60 0.38 0.30 -5.87 1.63 23.11 -0.03 0.55
+Car 0.88 3 1.88 0.00 192.37 402.31 374.00 1.48 1.60 3.69 -2.84 1.65 4.11 1.33 0.99
+Cyclist 0.00 0 -1.40 676.60 163.95 688.98 193.93 1.86 0.60 2.02 4.59 1.32 45.84 -1.30 0.30
+Car 0.00 2 -1.69 657.39 190.13 700.07 223.39 1.41 1.58 4.36 3.18 2.27 34.38 -1.60 0.42
+DontCare -1 -1 -10 503.89 169.71 590.61 190.13 -1 -1 -1 -1000 -1000 -1000 -10 0.10
+"""
+KITTI_CALIB = """P0: 7.215377e+02 0.0 6.095593e+02 0.0 0.0 7.215377e+02 1.728540e+02 0.0 0.0 0.0 1.0 0.0
+P1: 7.215377e+02 0.0 6.095593e+02 -3.875744e+02 0.0 7.215377e+02 1.728540e+02 0.0 0.0 0.0 1.0 0.0
+P2: 7.215377e+02 0.000000e+00 6.095593e+02 4.485728e+01 0.000000e+00 7.215377e+02 1.728540e+02 2.163791e-01 0.000000e+00 0.000000e+00 1.000000e+00 2.745884e-03
+P3: 7.215377e+02 0.0 6.095593e+02 -3.395242e+02 0.0 7.215377e+02 1.728540e+02 2.199936e+00 0.0 0.0 1.0 2.729905e-03
+R0_rect: 9.999239e-01 9.837760e-03 -7.445048e-03 -9.869795e-03 9.999421e-01 -4.278459e-03 7.402527e-03 4.351614e-03 9.999631e-01
+"""
+
+
+def golden_kitti_io(ref):
+    """csv_read_annot / csv_read_calib of the reference's KITTI class (car_instance.py:792-842) on a label file with
+    scores and a calibration file written here (KITTI text format)."""
+    import tempfile
+    import types
+    import libs.dataset.KITTI.car_instance as CI
+    with tempfile.TemporaryDirectory() as d:
+        lp, cp = os.path.join(d, '000001.txt'), os.path.join(d, 'calib.txt')
+        open(lp, 'w').write(KITTI_LABEL)
+        open(cp, 'w').write(KITTI_CALIB)
+        out = {}
+        for tag, classes in (('car', ['Car']), ('all', ['Car', 'Pedestrian', 'Cyclist'])):
+            fake = types.SimpleNamespace(_classes=classes)
+            out[tag] = CI.KITTI.csv_read_annot(fake, lp, CI.FIELDNAMES_P)
+        out['car_no_score'] = CI.KITTI.csv_read_annot(types.SimpleNamespace(_classes=['Car']), lp, CI.FIELDNAMES)
+        P = CI.KITTI.csv_read_calib(types.SimpleNamespace(), cp)
+    with open(os.path.join(HERE, 'kitti_io.json'), 'w') as f:
+        json.dump({'label': KITTI_LABEL, 'calib': KITTI_CALIB, 'annots': out, 'P': P.tolist(),
+                   'fieldnames': CI.FIELDNAMES, 'fieldnames_p': CI.FIELDNAMES_P, 'type_id': CI.TYPE_ID_CONVERSION}, f, indent=1)
+    print('kitti_io.json')
+
+
 def main():
     ref = import_reference()
     torch.set_num_threads(os.cpu_count())
@@ -561,6 +598,7 @@ def main():
     golden_align(ref)
     golden_composite(ref)
     golden_train_coord(ref)
+    golden_kitti_io(ref)
     import cv2, scipy
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'torch': torch.__version__, 'numpy': np.__version__, 'scipy': scipy.__version__,
