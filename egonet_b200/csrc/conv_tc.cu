@@ -384,7 +384,7 @@ __device__ __forceinline__ void epi_process(const EpiArgs& e, const EpiRow& r, u
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[c][j] = 0;
   }
-  if (e.split && !(e.dbg & 32)) {
+  if (e.split && e.acc_stride && !(e.dbg & 32)) {
     // second accumulator (cross terms) of the same columns
 #pragma unroll
     for (int c = 0; c < kEpiGroup; ++c) {
@@ -838,6 +838,8 @@ struct TcParams {
   // kchunks_h chunks of x_hi against w_lo (weights stored in exactly that stage order); nh = Cin_p / 16 K16
   // slices per plane.  hi*hi products accumulate in TMEM columns [0, n_tile), the cross terms in [n_tile, 2 n_tile).
   int split, cin_a, kchunks_h, nh;
+  int one_acc;   // split storage with ONE accumulator (cross terms added to the hi*hi sum): half the TMEM columns, so two
+                 // CTAs fit per SM for N = 192; costs ~3x the accumulation-truncation bias on that layer
 };
 
 template <int SW>
@@ -943,7 +945,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool g2 = kcx >= p.kchunks;
           const int sg = (g2 ? kcx - p.kchunks : kcx) * (SW / 32) + k;
           if (sg >= (g2 ? p.nh : 2 * p.nh)) continue;        // padding slice
-          const bool lo = g2 || sg >= p.nh;
+          const bool lo = (g2 || sg >= p.nh) && !p.one_acc;
           m_valid |= 1u << k;
           if (lo) m_lo |= 1u << k;
           if (lo ? acc_l : acc_h) m_acc |= 1u << k;
@@ -955,7 +957,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int k = 0; k < SW / 32; ++k) {
           // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
           if (m_valid >> k & 1u)
-            umma_f16(tmem_base + ((m_lo >> k & 1u) ? (uint32_t)p.n_tile : 0u), adesc + (uint64_t)(2 * k),
+            umma_f16(tmem_base + ((m_lo >> k & 1u) && !p.one_acc ? (uint32_t)p.n_tile : 0u), adesc + (uint64_t)(2 * k),
                      bdesc + (uint64_t)(2 * k), idesc, m_acc >> k & 1u);
         }
         umma_commit(&empty_bar[stage]);  // frees this stage once the MMAs above have read it
@@ -981,7 +983,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     er.valid = row < p.TW * p.TH * p.TB && er.b < p.B && er.oh < p.OH && er.ow < p.OW;
     er.pix = ((size_t)er.b * p.OH + er.oh) * p.OW + er.ow;
     EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr,
-              p.split, (uint32_t)p.n_tile};
+              p.split, p.one_acc ? 0u : (uint32_t)p.n_tile};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
             [&](int) { return er; });
   }
@@ -1776,6 +1778,7 @@ static EncodeTiledFn get_encode_fn() {
 struct TcConvPlan {
   // shape (batch independent)
   int H, W, Cin_p, OH, OW, Cout_p, Cout, ksize, stride, pad;
+  bool one_acc = false; // per-tap kernel, fp16x2: single accumulator (TcParams::one_acc)
   bool split = false;   // fp16x2 storage: cin_a = 2 * Cin_p physical input channels, 2 * Cout_p physical output channels
   int cin_a = 0;        // physical channels of the activation tensor
   int kchunks_h = 0;    // v1, split: chunks of the x_hi * w_lo stage group
@@ -2107,7 +2110,13 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   }
   if (!p->use_persist && !p->use_run) {
     // v1 after a rejected window-run / persistent plan: its own TMEM and shared-memory footprint
-    p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
+    p->one_acc = split && getenv("EGN_TC_SPLIT_1ACC") && atoi(getenv("EGN_TC_SPLIT_1ACC")) && pow2_cols(2 * p->n_tile) > 256;
+    p->tmem_cols = pow2_cols((split && !p->one_acc ? 2 : 1) * p->n_tile);
+    if (p->one_acc && !getenv("EGN_TC_V1_BUDGET_KB")) {
+      // two CTAs per SM become possible: size the ring for that
+      size_t st2 = std::min<size_t>((size_t)kMaxStages, (100 * 1024) / stage);
+      p->stages = (int)std::max<size_t>(2, std::min<size_t>(st2, (size_t)std::max(2, n_iters)));
+    }
     p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
   }
   if (getenv("EGN_TC_VERBOSE") && !p->use_persist && !p->use_run)
@@ -2477,6 +2486,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   TcParams tp{};
   tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
   tp.split = p->split ? 1 : 0; tp.cin_a = p->cin_a; tp.kchunks_h = p->kchunks_h; tp.nh = p->Cin_p / 16;
+  tp.one_acc = p->one_acc ? 1 : 0;
   tp.taps = p->ksize * p->ksize; tp.ksize = p->ksize; tp.stride = p->stride; tp.pad = p->pad; tp.relu = a.relu;
   tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
   tp.tiles_w = ceil_div(p->OW, p->TW);
