@@ -181,8 +181,11 @@ def roofline_block(classes, total_ms, pk, batch, precision='fp16'):
             blk['traffic_source'] = 'ncu --set full capture of this kernel class at this batch size (profiles/)'
     except (OSError, ValueError):
         pass
-    top = sorted(classes.items(), key=lambda kv: -kv[1]['ms'])[:6]
-    blk['top_classes'] = [{'kernel': k, 'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in top]
+    top = sorted(classes.items(), key=lambda kv: -kv[1]['ms'])
+    blk['top_classes'] = [{'kernel': k, 'ms': round(v['ms'], 3), 'launches': v['launches']} for k, v in top[:6]]
+    # every class: ms per batch, launches, algorithmic TFLOP/s and GB/s (activation + weight bytes)
+    blk['all_classes'] = [[k, round(v['ms'], 3), v['launches'], round(2.0 * v['macs'] / max(v['ms'], 1e-9) / 1e9, 1),
+                           round((v['act_bytes'] + v['weight_bytes']) / max(v['ms'], 1e-9) / 1e6, 1)] for k, v in top]
     return blk
 
 

@@ -2110,6 +2110,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   }
   if (!p->use_persist && !p->use_run) {
     // v1 after a rejected window-run / persistent plan: its own TMEM and shared-memory footprint
+    // N = 192 tiles (192 / 384-channel layers): two accumulators need all 512 TMEM columns, i.e. one CTA per SM.  With
+    // the cross terms added to the hi*hi accumulator instead (EGN_TC_SPLIT_1ACC=1), two CTAs fit: 195 -> 160 us
+    // (192ch@16x16) and 164 -> 131 us (384ch@8x8) at batch 256, +2 % end to end -- but the truncating accumulation then
+    // sees 3x the steps on those layers and the demo-config errors grow 2.5x (coords 4.8e-6 -> 1.25e-5, 3-D key-points
+    // 7e-5 -> 1.45e-4 m, past the 1e-4 bound).  OFF by default: parity first.
     p->one_acc = split && getenv("EGN_TC_SPLIT_1ACC") && atoi(getenv("EGN_TC_SPLIT_1ACC")) && pow2_cols(2 * p->n_tile) > 256;
     p->tmem_cols = pow2_cols((split && !p->one_acc ? 2 : 1) * p->n_tile);
     if (p->one_acc && !getenv("EGN_TC_V1_BUDGET_KB")) {
