@@ -1264,6 +1264,14 @@ struct PersistParams {
   // barrier (a_full[c] / a_empty[c]).  Chunk 0 of the next window reloads while phase B runs, chunk 1 while the next
   // phase A runs: the single slot behaves like a double buffer for most of the load.  n_phase_a = MMAs of phase A.
   int chunk_phase, n_phase_a;
+  // Block-shaped windows (3x3 convs): a window is BW x BH output pixels (BW = 8 * TX, BH = 16 * TY) plus the halo,
+  // loaded as ONE TMA box of r.Wp = BW + 2 columns x r.Hw = BH + 2 rows.  An M tile is 8 columns x 16 rows: its 16
+  // 8-row operand groups are one WINDOW ROW (r.Wp pixels) apart, which a K-major UMMA descriptor expresses directly
+  // as its stride byte offset (r.Wp * 128 B; any multiple of 16 B is legal, verified by tools/probes/
+  // umma_group_stride.py).  Every accumulator row is a real output pixel: no junk rows at the image borders (the
+  // flattened full-width run wastes 2 of every W + 2 rows plus the tail of the last tile: 73 % useful rows for
+  // 64 x 64 maps at T = 2), and the halo is loaded for 324 instead of 330 pixels per 256 (192) outputs.
+  int blk, BW, BH, TX, wins_x;
 };
 
 // kHead: generic epilogue with the head1 extras (fp32 heat-map copy, coordinate maps).
@@ -1374,8 +1382,11 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int r = tap / ntap_w, q = tap - r * ntap_w;
       const int ksteps_c = (c == p.kchunks - 1) ? ktot - 4 * c : 4;
       uint4 e;
-      e.x = (((uint32_t)ca * (uint32_t)p.rows_alloc * 128u + (uint32_t)(r * p.Wp + q) * 128u + (uint32_t)t * 16384u) >> 4) +
-            2u * (uint32_t)ka;
+      // first operand row of (tap, tile): flattened run -> tap shift + 128 rows per tile; block windows -> tile
+      // (tx, ty) starts 8 * tx columns / 16 * ty rows into the window
+      const uint32_t row0 = pp.blk ? (uint32_t)((r + 16 * (t / pp.TX)) * p.Wp + q + 8 * (t % pp.TX))
+                                   : (uint32_t)(r * p.Wp + q + t * 128);
+      e.x = (((uint32_t)ca * (uint32_t)p.rows_alloc * 128u + row0 * 128u) >> 4) + 2u * (uint32_t)ka;
       // weight tile and K16 slot inside it: (tap, chunk) tiles in order, or -- packed -- the full chunks first and
       // then one tile per pair of taps holding both 32-channel tails (slots 0-1: even tap, 2-3: odd tap)
       uint32_t wt = (uint32_t)(tap * p.kchunks + c), ks = (uint32_t)k;
@@ -1446,21 +1457,36 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int w = wb + w_off;
       const int slot = pp.a_slots == 2 ? (j & 1) : 0;
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
+      // TMA coordinates of the window's first (halo) pixel
+      const int wy = pp.blk ? win / pp.wins_x : win, wx = pp.blk ? win - wy * pp.wins_x : 0;
+      const int cx = wx * pp.BW - p.halo, cy = (pp.blk ? wy * pp.BH : win * p.THW) - p.halo, cb0 = bg * p.TBW;
+      // direct epilogue: pull the residual pixels of this window towards L2 now, ~2 windows before they are read
+      auto res_prefetch = [&]() {
+        if (!p.res || pp.n_stage || (p.dbg & 128) || w >= pp.n_windows) return;
+        const int cpitch = pp.split ? 2 * p.Cout_p : p.Cout_p;
+        if (pp.blk) {
+          // one piece per block row (lane = row)
+          const int y = wy * pp.BH + lane, x0 = wx * pp.BW;
+          if (lane < pp.BH && y < p.H && x0 < p.W)
+            l2_prefetch_bulk(p.res + (((size_t)cb0 * p.H + y) * p.W + x0) * cpitch, (uint32_t)(min(pp.BW, p.W - x0) * cpitch * 2));
+        } else if (elect_one()) {
+          // the rows of a full-width window are one contiguous NHWC range
+          const int h0 = win * p.THW;
+          const int rows = p.TBW > 1 ? min(p.TBW, p.B - cb0) * p.H : min(p.THW, p.H - h0);
+          l2_prefetch_bulk(p.res + ((size_t)cb0 * p.H + h0) * p.W * cpitch, (uint32_t)(rows * p.W * cpitch * 2));
+        }
+      };
       if (pp.chunk_phase) {
         // one slot, two chunks, each released by its own phase of the MMA loop
         for (int c = 0; c < 2; ++c) {
           mbar_wait(&a_empty[c], (uint32_t)((j & 1) ^ 1));
+          if (p.ts && j < 8 && lane == 0) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 10 + c] = gtime();
           if (!(p.dbg & 8) && elect_one()) {
             mbar_expect_tx(&a_full[c], p.a_bytes);
-            tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, -p.halo, win * p.THW - p.halo, bg * p.TBW);
+            tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, cx, cy, cb0);
           }
         }
-        if (p.res && !pp.n_stage && !(p.dbg & 128) && w < pp.n_windows && elect_one()) {
-          const int b0 = bg * p.TBW, h0 = win * p.THW;
-          const int rows = p.TBW > 1 ? min(p.TBW, p.B - b0) * p.H : min(p.THW, p.H - h0);
-          const int cpitch = pp.split ? 2 * p.Cout_p : p.Cout_p;
-          l2_prefetch_bulk(p.res + ((size_t)b0 * p.H + h0) * p.W * cpitch, (uint32_t)(rows * p.W * cpitch * 2));
-        }
+        res_prefetch();
         continue;
       }
       mbar_wait(&a_empty[slot], (uint32_t)(((pp.a_slots == 2 ? j >> 1 : j) & 1) ^ 1));
@@ -1470,23 +1496,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (crank == 0) mbar_expect_tx(&a_full[slot], 2u * p.a_bytes * (uint32_t)p.kchunks);
           const uint32_t bar = mapa_rank(&a_full[slot], 0);
           for (int c = 0; c < p.kchunks; ++c)
-            tma_load_4d_pair(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, bar, c * 64, -p.halo,
-                             win * p.THW - p.halo, bg * p.TBW);
+            tma_load_4d_pair(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, bar, c * 64, cx, cy, cb0);
         } else {
           mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
           for (int c = 0; c < p.kchunks; ++c)
-            tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, -p.halo,
-                        win * p.THW - p.halo, bg * p.TBW);
-        }
-        if (p.res && !pp.n_stage && !(p.dbg & 128) && w < pp.n_windows) {
-          // the residual rows of this window are one contiguous NHWC range: pull them towards L2 now,
-          // ~2 windows before the epilogue reads them
-          const int b0 = bg * p.TBW, h0 = win * p.THW;
-          const int rows = p.TBW > 1 ? min(p.TBW, p.B - b0) * p.H : min(p.THW, p.H - h0);
-          const int cpitch = pp.split ? 2 * p.Cout_p : p.Cout_p;
-          l2_prefetch_bulk(p.res + ((size_t)b0 * p.H + h0) * p.W * cpitch, (uint32_t)(rows * p.W * cpitch * 2));
+            tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, cx, cy, cb0);
         }
       }
+      if (!(p.dbg & 8)) res_prefetch();
     }
   } else if (warp == 2) {
     // ===================== B producer =====================
@@ -1528,6 +1545,9 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if ((!kPair || crank == 0) && elect_one()) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
       const uint64_t desc_hi = make_smem_desc(0, 128);
+      // block windows: the 8-row groups of an A tile are one window row apart
+      const uint64_t desc_hi_a = pp.blk ? (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((uint32_t)p.Wp * 128u >> 4) << 32)
+                                        : desc_hi;
       const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
       const int n_mma = p.taps * (pp.split ? 3 * pp.nh : ((p.Cin_p + 15) >> 4)) * p.T;
       if (pp.b_resident) mbar_wait(w_full, 0);
@@ -1538,14 +1558,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
         const int aslot = pp.a_slots == 2 ? slot : 0;                   // input-window slot (accumulator sets always alternate)
         const uint32_t aph = pp.a_slots == 2 ? ph : (uint32_t)(j & 1);
-        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 0] = gtime();
+        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 0] = gtime();
         mbar_wait(&acc_empty[slot], ph ^ 1u);        // epilogue has drained this accumulator set
-        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 1] = gtime();
+        if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 1] = gtime();
         if (!(p.dbg & 8)) mbar_wait(&a_full[aslot], aph);               // window landed
         tc_fence_after();
         if (p.ts && j < 8) {
-          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 2] = gtime();
-          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 6] = (unsigned long long)clock64();
+          p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 2] = gtime();
+          p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 6] = (unsigned long long)clock64();
         }
         const uint32_t a_lo = a_lo0 + (((uint32_t)aslot * a_slot) >> 4);
         const uint32_t d0 = tmem_base + (uint32_t)(slot * acc_cols);
@@ -1553,7 +1573,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll 4
           for (int i = 0; i < n_mma; ++i) {
             const uint4 e = s_issue[i];
-            umma_f16_pair(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+            umma_f16_pair(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
           }
           umma_commit_pair(&a_empty[aslot]);    // both CTAs' window slots may be refilled
           umma_commit_pair(&acc_full[slot]);    // both CTAs' accumulator halves complete
@@ -1564,25 +1584,31 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll 4
           for (int i = 0; i < pp.n_phase_a; ++i) {
             const uint4 e = s_issue[i];
-            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
           }
           umma_commit(&a_empty[0]);
+          if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 8] = gtime();
           if (!(p.dbg & 8)) mbar_wait(&a_full[1], aph);
           tc_fence_after();
+          if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 9] = gtime();
 #pragma unroll 4
           for (int i = pp.n_phase_a; i < n_mma; ++i) {
             const uint4 e = s_issue[i];
-            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
           }
           umma_commit(&a_empty[1]);
           umma_commit(&acc_full[slot]);
+          if (p.ts && j < 8) {
+            p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 3] = gtime();
+            p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 7] = (unsigned long long)clock64();
+          }
           continue;
         }
         if (pp.b_resident) {
 #pragma unroll 4
           for (int i = 0; i < n_mma; ++i) {
             const uint4 e = s_issue[i];
-            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
           }
         } else {
           uint32_t b_lo = b_lo0;
@@ -1593,7 +1619,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               tc_fence_after();
               b_lo = b_lo0 + ((stage * b_stage) >> 4);
             }
-            umma_f16(d0 + e.z, desc_hi | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo + e.y), idesc, e.w & 1u);
+            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo + e.y), idesc, e.w & 1u);
             if (e.w & 4u) {
               umma_commit(&b_empty[stage]);
               if (++stage == (uint32_t)p.b_stages) {
@@ -1606,8 +1632,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         umma_commit(&a_empty[aslot]);     // window slot may be refilled
         umma_commit(&acc_full[slot]);     // accumulators complete
         if (p.ts && j < 8) {
-          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 3] = gtime();
-          p.ts[((size_t)blockIdx.x * 8 + j) * 8 + 7] = (unsigned long long)clock64();
+          p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 3] = gtime();
+          p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 7] = (unsigned long long)clock64();
         }
       }
     }
@@ -1618,10 +1644,12 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int S = pp.n_stage;
       const bool has_res = p.res != nullptr && !(p.dbg & 2);
       const int my_windows = ((int)pp.n_windows - w0 + (int)gridDim.x - 1) / (int)gridDim.x;   // iterations of this CTA (pair)
-      auto coords = [&](int jj, int& h0, int& b0) {
+      auto coords = [&](int jj, int& x0, int& h0, int& b0) {
         const int w = w0 + jj * (int)gridDim.x + w_off;    // past-the-end window of a pair: loads zero-filled, stores clipped
         const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
-        h0 = win * p.THW;
+        const int wy = pp.blk ? win / pp.wins_x : win;
+        x0 = pp.blk ? (win - wy * pp.wins_x) * pp.BW : 0;
+        h0 = pp.blk ? wy * pp.BH : win * p.THW;
         b0 = bg * p.TBW;
       };
       // first physical channel of staging block k: hi-plane blocks, then (split storage) the lo-plane blocks
@@ -1631,12 +1659,12 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       auto fill = [&](int jj) {                 // buffer jj % S is free: fetch window jj's residual (or just release it)
         const int sb = jj % S;
         if (has_res) {
-          int h0, b0;
-          coords(jj, h0, b0);
+          int x0, h0, b0;
+          coords(jj, x0, h0, b0);
           mbar_expect_tx(&stage_full[sb], (uint32_t)pp.nblk * (uint32_t)(pp.rows_stage * pp.cb * 2));
           for (int k = 0; k < pp.nblk; ++k)
             tma_load_4d(smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, &map_res, &stage_full[sb],
-                        blk_chan(k), 0, h0, b0);
+                        blk_chan(k), x0, h0, b0);
         } else {
           mbar_arrive(&stage_full[sb]);
         }
@@ -1645,15 +1673,17 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int jj = 0; jj < my_windows; ++jj) {
         const int sb = jj % S;
         mbar_wait(&staged[sb], (uint32_t)((jj / S) & 1));
+        if (p.ts && jj < 8) p.ts[((size_t)blockIdx.x * 8 + jj) * 16 + 14] = gtime();
         if (!(p.dbg & 1)) {
-          int h0, b0;
-          coords(jj, h0, b0);
+          int x0, h0, b0;
+          coords(jj, x0, h0, b0);
           for (int k = 0; k < pp.nblk; ++k)
-            tma_store_4d(&map_out, smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, blk_chan(k), 0, h0,
+            tma_store_4d(&map_out, smem_stage + (size_t)sb * stage_bytes + (size_t)k * pp.blk_bytes, blk_chan(k), x0, h0,
                          b0);
           bulk_commit();
           bulk_wait_read0();                      // smem of this buffer has been read: it may be refilled
         }
+        if (p.ts && jj < 8) p.ts[((size_t)blockIdx.x * 8 + jj) * 16 + 15] = gtime();
         if (jj + S < my_windows) fill(jj + S);
       }
       bulk_wait0();                               // all output writes complete before the CTA exits
@@ -1677,7 +1707,9 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int slot = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       const int bg = w / p.win_per_img, win = w - bg * p.win_per_img;
-      const int h0 = win * p.THW, b0 = bg * p.TBW;
+      const int wy = pp.blk ? win / pp.wins_x : win;
+      const int x0 = pp.blk ? (win - wy * pp.wins_x) * pp.BW : 0;
+      const int h0 = pp.blk ? wy * pp.BH : win * p.THW, b0 = bg * p.TBW;
       if (p.dbg & 64) {
         mbar_wait(&acc_full[slot], ph);
         tc_fence_after();
@@ -1687,6 +1719,16 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         continue;
       }
       auto row_of = [&](int t) {
+        if (pp.blk) {
+          // block windows: lane -> (row & 7, row >> 3) inside tile (t % TX, t / TX); every lane is an output pixel
+          EpiRow rr;
+          rr.b = b0;
+          rr.oh = h0 + 16 * (t / pp.TX) + (row >> 3);
+          rr.ow = x0 + 8 * (t % pp.TX) + (row & 7);
+          rr.valid = rr.b < p.B && rr.oh < p.H && rr.ow < p.W;
+          rr.pix = ((size_t)rr.b * p.H + rr.oh) * p.W + rr.ow;
+          return rr;
+        }
         // run position -> window position -> (image, row, column); float reciprocals are exact here
         const int pos = t * 128 + row + p.lead;
         const int bi = p.TBW == 1 ? 0 : (int)(((float)pos + 0.5f) * p.inv_img);
@@ -1702,7 +1744,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         rr.pix = ((size_t)rr.b * p.H + rr.oh) * p.W + rr.ow;
         return rr;
       };
-      unsigned long long* ts = (p.ts && j < 8 && half == 0) ? p.ts + ((size_t)blockIdx.x * 8 + j) * 8 : nullptr;
+      unsigned long long* ts = (p.ts && j < 8 && half == 0) ? p.ts + ((size_t)blockIdx.x * 8 + j) * 16 : nullptr;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * acc_cols);
       if constexpr (kHead) {
         e.ts = ts;
@@ -1714,10 +1756,18 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             p.res != nullptr && !(p.dbg & 2), p.relu, p.dbg,
                             pp.split ? (uint32_t)pp.nblk_plane * pp.blk_bytes : 0u};
           mbar_wait(&stage_full[sb], (uint32_t)((j / pp.n_stage) & 1));
+          if (ts && (threadIdx.x & 127) == 64) ts[12] = gtime();
           mbar_wait(&acc_full[slot], ph);
           tc_fence_after();
           if (ts && (threadIdx.x & 127) == 64) ts[4] = gtime();
           epi_window_staged<kParts>(es, tbase, p.T, p.n_tile, half, [&](int t) {
+            if (pp.blk) {
+              // staging buffer = the BW x BH block, row-major; pixels past the image are clipped by the TMA store
+              StageRow sr;
+              sr.valid = true;
+              sr.srow = (uint32_t)((16 * (t / pp.TX) + (row >> 3)) * pp.BW + 8 * (t % pp.TX) + (row & 7));
+              return sr;
+            }
             const int pos = t * 128 + row + p.lead;
             const int bi = p.TBW == 1 ? 0 : (int)(((float)pos + 0.5f) * p.inv_img);
             const int rem = pos - bi * p.img_rows;
@@ -1729,6 +1779,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             sr.srow = (uint32_t)(((bi * p.THW) + (hp - p.halo)) * p.W + (wp - p.halo));
             return sr;
           }, pp.ksplit);
+          if (ts && (threadIdx.x & 127) == 64) ts[13] = gtime();
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&staged[sb]);
@@ -1736,7 +1787,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts, pp.ksplit);
         }
       }
-      if (p.ts && j < 8 && lane == 0) atomicMax(p.ts + ((size_t)blockIdx.x * 8 + j) * 8 + 5, gtime());   // last warp done
+      if (p.ts && j < 8 && lane == 0) atomicMax(p.ts + ((size_t)blockIdx.x * 8 + j) * 16 + 5, gtime());   // last warp done
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                                   // one arrival per warp releases the accumulator set
@@ -1799,6 +1850,7 @@ struct TcConvPlan {
   int n_stage = 0, cb = 0, nblk = 0, rows_stage = 0;   // staged (TMA) epilogue of the persistent kernel
   uint32_t blk_bytes = 0;
   int halo = 0, Wp = 0, Hw = 0, THW = 0, TBW = 1, T = 1, rows_alloc = 0, b_stages = 2;
+  int blk = 0, BW = 0, BH = 0, TX = 1;                 // block-shaped windows of the persistent kernel (PersistParams)
   float run_eff = 0.f;
   __half* d_w = nullptr;      // [Cout_p][taps*Cin_p]
   size_t w_bytes = 0;
@@ -1987,10 +2039,23 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         if (n_tile > 256 / nacc || n_tile < 16) continue;
         const size_t b_stage_bytes = ((size_t)n_tile * 128 + 1023) & ~(size_t)1023;
         const int Tmax = std::min(8, 256 / nacc / n_tile);
+        // window shapes: full-width rows of one image (mode 0), whole images (mode 1), or -- 3x3 convs -- blocks of
+        // 8 * TX x 16 * TY pixels whose M tiles are 8 columns x 16 rows (mode 2 + TY: PersistParams::blk; every
+        // accumulator row is an output pixel)
+        const bool allow_blk = a.ksize == 3 && !(getenv("EGN_TC_BLK") && atoi(getenv("EGN_TC_BLK")) == 0);
         for (int T = 1; T <= Tmax; ++T) {
-          for (int multi = 0; multi < 2; ++multi) {
+          for (int mode = 0; mode < 2 + (allow_blk ? T : 0); ++mode) {
+            const int multi = mode == 1;
+            const int TY = mode >= 2 ? mode - 1 : 0;          // block mode: tiles down (TX = T / TY across)
+            if (TY && T % TY) continue;
+            const int blk = TY ? 1 : 0, TX = TY ? T / TY : 1, BW = 8 * TX, BH = 16 * TY;
+            if (blk && (BW >= a.W + 8 || BH >= a.H + 16)) continue;          // a block larger than the map
+            if (getenv("EGN_TC_BLK") && atoi(getenv("EGN_TC_BLK")) == 2 && allow_blk && !blk) continue;   // tuning: blocks only
             int THW, TBW;
-            if (!multi) {
+            if (blk) {
+              THW = BH;
+              TBW = 1;
+            } else if (!multi) {
               THW = std::min(a.H, (128 * T + 2 * halo) / Wp);
               TBW = 1;
               if (THW < 1) continue;
@@ -2001,10 +2066,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
               TBW = std::min(TBW, 64);
             }
             const int Hw = THW + 2 * halo;
-            if (Wp > 256 || Hw > 256) continue;
-            const int rows_win = TBW * Hw * Wp;
-            if (rows_win - 2 * lead > 128 * T) continue;
-            const int rows_alloc = (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
+            const int Wpw = blk ? BW + 2 * halo : Wp;          // window pitch in pixels
+            if (Wpw > 256 || Hw > 256) continue;
+            const int rows_win = TBW * Hw * Wpw;
+            if (!blk && rows_win - 2 * lead > 128 * T) continue;
+            const int rows_alloc = blk ? (rows_win + 7) & ~7 : (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
             // fp16x2 windows are twice the bytes: also try a single window slot (the measured fp16 plans keep two)
             const int force_slots = getenv("EGN_TC_ASLOTS") ? atoi(getenv("EGN_TC_ASLOTS")) : 0;
             for (int a_slots = 2; a_slots >= (split ? 1 : 2); --a_slots) {
@@ -2030,13 +2096,13 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
               }
               if (smem > smem_cap) continue;
             }
-            const int windows = multi ? 1 : ceil_div(a.H, THW);
+            const int windows = blk ? ceil_div(a.W, BW) * ceil_div(a.H, BH) : (multi ? 1 : ceil_div(a.H, THW));
             const double eff = multi ? (double)TBW * a.H * a.W / ((double)T * 128)
                                      : (double)a.H * a.W / ((double)windows * T * 128);
             if (force_T && T != force_T) continue;
             // staging buffers of the TMA epilogue: [block][TBW*THW*W pixels][cb channels]
             const int cb = n_tile % 64 == 0 ? 64 : (n_tile % 48 == 0 ? 48 : 0);
-            const int rows_stage = TBW * THW * a.W;
+            const int rows_stage = blk ? BW * BH : TBW * THW * a.W;
             const size_t blk_bytes = cb ? (((size_t)rows_stage * cb * 2 + 1023) & ~(size_t)1023) : 0;
             const int nblk = cb ? n_tile / cb : 0;
             // cost model in SM cycles at the nominal batch 256 (measured constants, profiles/r01_*):
@@ -2068,7 +2134,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->b_resident = resident;
                 p->n_tiles = n_tiles;
                 p->n_tile = n_tile;
-                p->halo = halo; p->Wp = Wp; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
+                p->halo = halo; p->Wp = Wpw; p->Hw = Hw; p->THW = THW; p->TBW = TBW; p->T = T;
+                p->blk = blk; p->BW = BW; p->BH = BH; p->TX = TX;
                 p->rows_alloc = rows_alloc; p->b_stages = bst; p->run_eff = (float)eff;
                 p->smem_bytes = smem_s;
                 p->tmem_cols = pow2_cols(2 * nacc * T * n_tile);
@@ -2084,6 +2151,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
       if (p->use_persist && p->run_eff < 0.6f) {
         p->use_persist = false;
+        if (p->blk) p->use_run = false;          // the window-run plan's geometry was overwritten by the block candidate
+        p->blk = 0;
         p->pack_tail = false;
         p->n_tiles = base_tiles;
         p->n_tile = a.Cout_p / base_tiles;
@@ -2102,8 +2171,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       }
       if (getenv("EGN_TC_VERBOSE") && p->use_persist && p->use_pair) fprintf(stderr, "[egn] (next line) CTA-pair mode\n");
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
-        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v3-persist a_slots=%d T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
-                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->a_slots, p->T, p->THW, p->TBW, p->run_eff,
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v3-persist blk=%dx%d a_slots=%d T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
+                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->blk ? p->BW : 0, p->blk ? p->BH : 0, p->a_slots, p->T, p->THW, p->TBW, p->run_eff,
                 p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->b_resident, p->b_stages, p->tmem_cols, p->n_stage, p->nblk,
                 p->blk_bytes, p->cb);
     }
@@ -2202,7 +2271,8 @@ static int make_io_map(TcConvPlan* p, const void* ptr, int B, CUtensorMap* m) {
   const cuuint64_t C = (p->split ? 2 : 1) * p->Cout_p, W = p->OW, H = p->OH;     // fp16x2: [hi | lo] planes
   const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
   const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)p->cb, (cuuint32_t)p->OW, (cuuint32_t)p->THW, (cuuint32_t)p->TBW};
+  const cuuint32_t box[4] = {(cuuint32_t)p->cb, (cuuint32_t)(p->blk ? p->BW : p->OW), (cuuint32_t)(p->blk ? p->BH : p->THW),
+                             (cuuint32_t)p->TBW};
   const cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, p->cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -2321,7 +2391,9 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.B = a.B; rp.H = p->H; rp.W = p->W; rp.Cout_p = p->Cout_p; rp.Cout = p->Cout; rp.Cin_p = p->cin_a;
     rp.taps = p->ksize * p->ksize; rp.relu = a.relu;
     rp.halo = p->halo; rp.Wp = p->Wp; rp.Hw = p->Hw; rp.THW = p->THW; rp.TBW = p->TBW;
-    rp.win_per_img = ceil_div(p->H, p->THW);
+    pp.blk = p->blk; pp.BW = p->BW; pp.BH = p->BH; pp.TX = p->TX;
+    pp.wins_x = p->blk ? ceil_div(p->W, p->BW) : 1;
+    rp.win_per_img = p->blk ? pp.wins_x * ceil_div(p->H, p->BH) : ceil_div(p->H, p->THW);
     rp.lead = p->halo * (p->Wp + 1);
     rp.m_run = p->TBW * p->Hw * p->Wp - 2 * rp.lead;
     rp.img_rows = p->Hw * p->Wp;
@@ -2349,8 +2421,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.ts = nullptr;
     static unsigned long long* d_ts3 = nullptr;
     if (getenv("EGN_TC_TS")) {
-      if (!d_ts3) cudaMalloc(&d_ts3, 256 * 64 * sizeof(unsigned long long));
-      cudaMemsetAsync(d_ts3, 0, 256 * 64 * sizeof(unsigned long long), st);
+      if (!d_ts3) cudaMalloc(&d_ts3, 256 * 128 * sizeof(unsigned long long));
+      cudaMemsetAsync(d_ts3, 0, 256 * 128 * sizeof(unsigned long long), st);
       rp.ts = d_ts3;
     }
     pp.n_windows = rp.win_per_img * ceil_div(a.B, p->TBW);
@@ -2424,16 +2496,22 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     EGN_LAUNCH_CHECK("conv_persist_kernel");
     if (rp.ts && getenv("EGN_TC_TS_DUMP")) {
       cudaStreamSynchronize(st);
-      std::vector<unsigned long long> h(256 * 64);
+      std::vector<unsigned long long> h(256 * 128);
       cudaMemcpy(h.data(), d_ts3, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       // CTA 0 and CTA 77, first windows: times relative to the CTA's first stamp
       for (int cta : {0, 77}) {
-        const unsigned long long t0 = h[(size_t)cta * 64];
+        const unsigned long long t0 = h[(size_t)cta * 128];
         for (int j = 0; j < 6; ++j) {
-          const unsigned long long* q = &h[((size_t)cta * 8 + j) * 8];
+          const unsigned long long* q = &h[((size_t)cta * 8 + j) * 16];
           if (!q[0]) continue;
           fprintf(stderr, "[egn-ts3] cta %d win %d: mma-loop-top %.2f acc-empty-ok %.2f a-full-ok %.2f mma-issued %.2f | epi acc-full-ok %.2f epi-done %.2f (us) | mma phase %llu SM cycles\n",
                   cta, j, (q[0] - t0) * 1e-3, (q[1] - t0) * 1e-3, (q[2] - t0) * 1e-3, (q[3] - t0) * 1e-3, (q[4] - t0) * 1e-3, (q[5] - t0) * 1e-3, q[7] - q[6]);
+          if (q[12])
+            fprintf(stderr, "[egn-ts3]            staged: residual landed %.2f items done (warp 6) %.2f | dma: all staged %.2f store read out %.2f (us)\n",
+                    (q[12] - t0) * 1e-3, (q[13] - t0) * 1e-3, (q[14] - t0) * 1e-3, (q[15] - t0) * 1e-3);
+          if (q[8])
+            fprintf(stderr, "[egn-ts3]            chunk phases: A-issued %.2f a-full[1]-ok %.2f | producer: chunk0 free %.2f chunk1 free %.2f (us)\n",
+                    (q[8] - t0) * 1e-3, (q[9] - t0) * 1e-3, (q[10] - t0) * 1e-3, (q[11] - t0) * 1e-3);
         }
       }
     }
@@ -2553,6 +2631,13 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_fence_after();
     const uint32_t start = smem_u32(sa) + (uint32_t)row_off * SW;
     uint64_t adesc = make_smem_desc(start, SW);
+    // bo_mode >= 16: the 8-row groups of the operand are (bo_mode >> 4) rows apart instead of 8 (stride byte offset
+    // = rows * SW): row i of the tile is operand row  off + (i / 8) * rows + i % 8  (block-shaped conv windows)
+    if (bo_mode >= 16) {
+      const uint64_t sbo = (uint64_t)(((uint32_t)(bo_mode >> 4) * SW) >> 4);
+      adesc = (adesc & ~((uint64_t)0x3FFF << 32)) | (sbo << 32);
+      bo_mode &= 15;
+    }
     uint32_t bo = 0;
     if (bo_mode == 1) bo = (uint32_t)row_off & 7u;          // row phase inside the 8-row atom
     if (bo_mode == 2) bo = (start >> 7) & 7u;               // literal (addr >> 7) & 7
@@ -2625,6 +2710,7 @@ extern "C" int egn_debug_umma_probe(int swizzle_bytes, int row_off, int bo_mode,
   using namespace egn;
   EGN_REQUIRE(a_f16 && b_f16 && out, "egn_debug_umma_probe: null pointer");
   EGN_REQUIRE(row_off >= 0 && row_off <= 128, "egn_debug_umma_probe: row_off out of range");
+  EGN_REQUIRE(bo_mode < 16 || row_off + 15 * (bo_mode >> 4) + 8 <= 256, "egn_debug_umma_probe: group stride out of range");
   if (int rc = require_device()) return rc;
   const __half* a = static_cast<const __half*>(a_f16);
   const __half* b = static_cast<const __half*>(b_f16);

@@ -385,7 +385,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize('variant', ['auto', 'no_pair', 'ksplit', 'no_v3', 'v1_only'])
+@pytest.mark.parametrize('variant', ['auto', 'no_blk', 'no_pair', 'ksplit', 'no_v3', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
 def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
     """One fused conv (bias + residual + ReLU) through the tcgen05 and the CUDA-core kernels against
@@ -397,6 +397,10 @@ def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
     import ctypes
     from egonet_b200 import _native as N
     Cin, Cout, H, W, k, stride, B = case
+    if variant == 'no_blk':
+        if not (k == 3 and stride == 1 and W >= 24):
+            pytest.skip('block-shaped windows only exist in the persistent kernel (3x3 stride 1)')
+        monkeypatch.setenv('EGN_TC_BLK', '0')            # full-width flattened-run windows
     if variant == 'no_pair':
         monkeypatch.setenv('EGN_TC_PAIR', '0')
     if variant == 'ksplit':
@@ -457,7 +461,7 @@ def _unsplit(t, C):
     return (t[..., :C].double() + t[..., Cp:Cp + C].double()).permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize('variant', ['auto', 'no_pair', 'no_v3', 'v1_only'])
+@pytest.mark.parametrize('variant', ['auto', 'no_blk', 'no_pair', 'no_v3', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
 def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
     """One fused conv in fp16x2 split storage (three error-compensated tcgen05 MMAs per product, two TMEM
@@ -466,6 +470,10 @@ def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
     K16 step, profiles/r02_acc_precision.md) -- 100x tighter than the plain fp16 path's rounding."""
     from egonet_b200 import _native as N
     Cin, Cout, H, W, k, stride, B = case
+    if variant == 'no_blk':
+        if not (k == 3 and stride == 1 and W >= 24):
+            pytest.skip('block-shaped windows only exist in the persistent kernel (3x3 stride 1)')
+        monkeypatch.setenv('EGN_TC_BLK', '0')
     if variant == 'no_pair':
         if not (k == 3 and stride == 1 and W >= 24):
             pytest.skip('CTA pairs only exist in the persistent kernel')
