@@ -325,6 +325,7 @@ struct EpiArgs {
   // summed here in round-to-nearest fp32
   int split;
   uint32_t acc_stride;
+  uint32_t tile_stride;   // TMEM columns between consecutive M tiles (0 = n_tile)
 };
 
 // v -> (hi, lo) fp16 planes of 8 values each: hi = rn16(v), lo = rn16(v - hi)
@@ -497,7 +498,8 @@ __device__ __forceinline__ void epi_run(const EpiArgs& e, uint32_t tmem_lane_bas
   };
   auto nch_of = [&](const EpiCursor& c) { return min(kEpiGroup, nch_total - c.gi * kEpiGroup); };
   auto n_of = [&](const EpiCursor& c) { return n0 + 16 * kEpiGroup * c.gi; };
-  auto ta_of = [&](const EpiCursor& c) { return tmem_lane_base + (uint32_t)(c.t * n_tile + 16 * kEpiGroup * c.gi); };
+  const int tstride = e.tile_stride ? (int)e.tile_stride : n_tile;
+  auto ta_of = [&](const EpiCursor& c) { return tmem_lane_base + (uint32_t)(c.t * tstride + 16 * kEpiGroup * c.gi); };
   EpiCursor ca{0, 0, row_of(0)};
   while (ca.t < T && !mine(ca)) step(ca);
   if (ca.t < T) epi_prefetch(e, ca.row, n_of(ca), nch_of(ca), bufA);
@@ -621,9 +623,11 @@ __device__ __forceinline__ void add_split_accumulators(uint32_t (&v)[16], uint32
 template <int kParts, typename RowFn>
 __device__ __forceinline__ void epi_window_lite(const EpiLite& e, uint32_t tmem_lane_base, int T, int n_tile, int n0,
                                                 uint64_t* full_bar, uint32_t parity, int half, RowFn row_of,
-                                                unsigned long long* ts, int ksplit = 1) {
+                                                unsigned long long* ts, int ksplit = 1, int stacked = 0) {
+  // stacked (fp16x2, persistent kernel): tile t keeps [H | L] in adjacent column ranges of n_tile each
   const int per_tile = n_tile >> 4;
-  const uint32_t acc_stride = (uint32_t)(T * n_tile);
+  const uint32_t acc_stride = (uint32_t)(stacked ? n_tile : T * n_tile);
+  const int tstride = stacked ? 2 * n_tile : n_tile;
   auto next = [&](const LiteItem& it) {              // item + kParts; refresh the row when the tile changes
     LiteItem n = it;
     n.g += kParts;
@@ -638,7 +642,7 @@ __device__ __forceinline__ void epi_window_lite(const EpiLite& e, uint32_t tmem_
     }
     return n;
   };
-  auto taddr = [&](const LiteItem& it) { return tmem_lane_base + (uint32_t)(it.t * n_tile + 16 * it.g); };
+  auto taddr = [&](const LiteItem& it) { return tmem_lane_base + (uint32_t)(it.t * tstride + 16 * it.g); };
 
   LiteItem cur{-1, half - kParts + per_tile, false, 0};   // one step before the first item of tile 0
   cur = next(cur);
@@ -695,9 +699,10 @@ struct StageRow {
 
 template <int kParts, typename RowFn>
 __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tmem_lane_base, int T, int n_tile,
-                                                  int part, RowFn row_of, int ksplit = 1) {
+                                                  int part, RowFn row_of, int ksplit = 1, int stacked = 0) {
   const int per_tile = n_tile >> 4;
-  const uint32_t acc_stride = (uint32_t)(T * n_tile);
+  const uint32_t acc_stride = (uint32_t)(stacked ? n_tile : T * n_tile);
+  const int tstride = stacked ? 2 * n_tile : n_tile;
   const uint32_t pitch = (uint32_t)e.cb * 2u;
   int t = -1, g = part - kParts + per_tile, t_row = -1;
   StageRow r{false, 0};
@@ -783,14 +788,14 @@ __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tm
   // software pipeline over this warp's items with two register buffers: the TMEM load of the next item
   // is in flight while the current one is converted
   uint32_t vA[16], vB[16];
-  if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vA);
+  if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * tstride + 16 * g), vA);
 #pragma unroll 1
   while (t < T) {
     int ct = t, cg = g;
     step();
     tmem_ld_wait_dep(vA);
-    if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vB);
-    if (ksplit > 1) add_split_accumulators(vA, tmem_lane_base + (uint32_t)(ct * n_tile + 16 * cg), ksplit, acc_stride);
+    if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * tstride + 16 * g), vB);
+    if (ksplit > 1) add_split_accumulators(vA, tmem_lane_base + (uint32_t)(ct * tstride + 16 * cg), ksplit, acc_stride);
     row_for(ct);
     item(vA, r, cg);
     if (t >= T) break;
@@ -798,8 +803,8 @@ __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tm
     cg = g;
     step();
     tmem_ld_wait_dep(vB);
-    if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * n_tile + 16 * g), vA);
-    if (ksplit > 1) add_split_accumulators(vB, tmem_lane_base + (uint32_t)(ct * n_tile + 16 * cg), ksplit, acc_stride);
+    if (t < T) tmem_ld(tmem_lane_base + (uint32_t)(t * tstride + 16 * g), vA);
+    if (ksplit > 1) add_split_accumulators(vB, tmem_lane_base + (uint32_t)(ct * tstride + 16 * cg), ksplit, acc_stride);
     row_for(ct);
     item(vB, r, cg);
   }
@@ -983,7 +988,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     er.valid = row < p.TW * p.TH * p.TB && er.b < p.B && er.oh < p.OH && er.ow < p.OW;
     er.pix = ((size_t)er.b * p.OH + er.oh) * p.OW + er.ow;
     EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr,
-              p.split, p.one_acc ? 0u : (uint32_t)p.n_tile};
+              p.split, p.one_acc ? 0u : (uint32_t)p.n_tile, 0u};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
             [&](int) { return er; });
   }
@@ -1191,7 +1196,7 @@ conv_run_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int row = quarter * 32 + lane;
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
               p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, p.run_split,
-              (uint32_t)(p.T * p.n_tile)};
+              (uint32_t)(p.T * p.n_tile), 0u};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), p.T, p.n_tile, n0, tmem_full_bar, [&](int t) {
       // run position -> window position -> (image, row, column); float reciprocals are exact here
       // (positions < 2^16, margins >= 0.5 / pitch)
@@ -1250,20 +1255,26 @@ struct PersistParams {
   int cb, nblk;         // channels per staging block (64 / 48), blocks per n_tile
   int rows_stage;       // TBW * THW * W pixels per window
   uint32_t blk_bytes;   // bytes of one block, 1024-aligned
-  // fp16x2 split storage (kernels.h): r.Cin_p = 2 * Cin physical channels ([x_hi | x_lo] planes, nh K16 slices each),
-  // the weight matrix holds [w_hi | w_lo] per tap in the same chunking, and a tap issues, per weight slice sb,
-  //   sb <  nh (w_hi):  A slice sb (x_hi) -> accumulator H,  A slice sb + nh (x_lo) -> accumulator L
-  //   sb >= nh (w_lo):  A slice sb - nh (x_hi) -> accumulator L
-  // (ksplit = 2: H and L are summed by the epilogue).  The staging buffer holds nblk_plane hi blocks followed by
-  // nblk_plane lo blocks (nblk = 2 * nblk_plane); out / res tensors have 2 * Cout_p physical channels.
+  // fp16x2 split storage (kernels.h): r.Cin_p = 2 * Cin physical channels ([x_hi | x_lo] planes, nh K16 slices each).
+  // STACKED weights: a weight tile holds 2 * n_tile rows, [w_hi rows | w_lo rows], over 64 K columns = four K16
+  // slices of ONE plane, the (tap, slice) pairs packed densely (slice tap * nh + s: no per-tap padding), and tile t's
+  // accumulators sit side by side in TMEM, [H_t | L_t].  Per (tap, slice s) the issuer runs
+  //   A = x_hi[s], B = all 2 * n_tile rows, N = 2 * n_tile  ->  H += x_hi w_hi,  L += x_hi w_lo   (one MMA)
+  //   A = x_lo[s], B = the first n_tile rows, N = n_tile    ->  L += x_lo w_hi
+  // two MMAs per slice instead of three and the x_hi operand is read from shared memory once (an N <= 128 MMA is bound
+  // by its operand reads: 32 + N / 4 cycles, so 56 + 44 = 100 cycles per slice at n_tile = 48 instead of 3 x 44).
+  // H and L are summed by the epilogue (ksplit = 2, accumulator stride n_tile).  The staging buffer holds nblk_plane
+  // hi blocks followed by nblk_plane lo blocks (nblk = 2 * nblk_plane); out / res tensors have 2 * Cout_p channels.
   int split, nh, nblk_plane;
+  int a_sw;             // bytes per window row and chunk: 128 (64 channels, SWIZZLE_128B) or 64 (32 channels, SWIZZLE_64B:
+                        // 96 physical channels = three exact chunks instead of two with a half-empty second one)
   int a_slots;          // input-window slots in smem: 2 (window j+1 loads while j is multiplied) or 1 (load and MMA
                         // phases of consecutive windows serialise; the epilogue still overlaps -- TMEM stays double buffered)
-  // chunk phasing (one window slot of TWO 64-channel chunks, fp16x2): the issue table is ordered phase A = every MMA
-  // whose activation slice lies in chunk 0, then phase B = those in chunk 1, and each chunk has its own full / empty
-  // barrier (a_full[c] / a_empty[c]).  Chunk 0 of the next window reloads while phase B runs, chunk 1 while the next
-  // phase A runs: the single slot behaves like a double buffer for most of the load.  n_phase_a = MMAs of phase A.
-  int chunk_phase, n_phase_a;
+  // chunk phasing (ONE window slot of 2..4 chunks, fp16x2): the issue table is ordered phase c = every MMA whose
+  // activation slice lies in chunk c, and each chunk has its own full / empty barrier (a_full[c] / a_empty[c]).
+  // Chunk c of the next window reloads while the other phases run: the single slot behaves like a ring of chunks.
+  // phase_end[c] = issue-table index one past phase c.
+  int chunk_phase, phase_end[4];
   // Block-shaped windows (3x3 convs): a window is BW x BH output pixels (BW = 8 * TX, BH = 16 * TY) plus the halo,
   // loaded as ONE TMA box of r.Wp = BW + 2 columns x r.Hw = BH + 2 rows.  An M tile is 8 columns x 16 rows: its 16
   // 8-row operand groups are one WINDOW ROW (r.Wp pixels) apart, which a K-major UMMA descriptor expresses directly
@@ -1289,9 +1300,9 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const RunParams& p = pp.r;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_chunk = (uint32_t)p.rows_alloc * 128u;
+  const uint32_t a_chunk = (uint32_t)p.rows_alloc * (uint32_t)pp.a_sw;
   const uint32_t a_slot = a_chunk * (uint32_t)p.kchunks;
-  const uint32_t b_stage = ((uint32_t)pp.b_rows * 128u + 1023u) & ~1023u;
+  const uint32_t b_stage = ((uint32_t)pp.b_rows * (pp.split ? 256u : 128u) + 1023u) & ~1023u;   // stacked: [w_hi | w_lo] rows
   const int w_tiles = pp.w_tiles;
   const int b_slots = pp.b_resident ? w_tiles : p.b_stages;
   const uint32_t crank = kPair ? cluster_ctarank() : 0u;          // 0 = leader of the pair
@@ -1304,8 +1315,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem_stage = smem_b + (size_t)b_slots * b_stage;                  // n_stage x nblk x blk_bytes (1024-aligned)
   const uint32_t stage_bytes = (uint32_t)pp.nblk * pp.blk_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_stage + (size_t)pp.n_stage * stage_bytes);
-  uint64_t* a_empty = a_full + 2;
-  uint64_t* acc_full = a_empty + 2;
+  uint64_t* a_empty = a_full + 4;                   // [4]: window slots, or the chunks of a chunk-phased slot
+  uint64_t* acc_full = a_empty + 4;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
   uint64_t* b_full = w_full + 1;
@@ -1313,7 +1324,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* stage_full = b_empty + kMaxBStages;     // [2] residual landed / buffer free for the epilogue
   uint64_t* staged = stage_full + 2;                // [2] epilogue finished writing the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // offset (9 + 12 + 4) * 8 + 8 = 208: 16-byte aligned
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);    // offset (13 + 12 + 4) * 8 + 8 = 240: 16-byte aligned
   uint4* s_issue = reinterpret_cast<uint4*>(s_bias + p.n_tile);   // [n_mma] issue table (n_tile % 16 == 0)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -1328,56 +1339,36 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   //   z: TMEM column offset of the M tile   w: bit0 accumulate, bit1 first / bit2 last MMA of a weight tile
   {
     const int ktot = (p.Cin_p + 15) >> 4;                      // K16 slices per tap (both planes in split mode)
-    const int groups = pp.split ? 3 * pp.nh : ktot;            // MMA groups (of T tiles) per tap
+    const int groups = pp.split ? 2 * pp.nh : ktot;            // MMA groups (of T tiles) per tap
     const int n_mma = p.taps * groups * p.T;
     const int ntap_w = p.halo ? 3 : 1;
-    const uint32_t b_stage_t = ((uint32_t)pp.b_rows * 128u + 1023u) & ~1023u;
-    // activation slice of group g of a tap (split storage; see PersistParams)
-    auto slice_of = [&](int g) { return g < 2 * pp.nh ? (g >> 1) + (g & 1) * pp.nh : g - 2 * pp.nh; };
-    // chunk phasing: groups of a tap that read chunk 0 (phase A) / chunk 1 (phase B), and the first group in ISSUE
-    // order that writes each accumulator (it must not accumulate)
-    int n_a = groups, first_h = 0, first_l = 1;
-    if (pp.chunk_phase) {
-      n_a = 0;
-      first_h = first_l = -1;
-      for (int ph = 0; ph < 2; ++ph)
-        for (int g = 0; g < groups; ++g) {
-          if ((slice_of(g) >> 2) != ph) continue;
-          if (ph == 0) ++n_a;
-          const int lo_g = g < 2 * pp.nh ? (g & 1) : 1;
-          if (lo_g && first_l < 0) first_l = g;
-          if (!lo_g && first_h < 0) first_h = g;
-        }
-    }
+    const int spc = pp.a_sw >> 5;                              // K16 slices per window chunk
+    const uint32_t b_stage_t = b_stage;
+    // activation slice of group g of a tap (split storage, stacked weights: g even = x_hi[g/2], odd = x_lo[g/2])
+    auto slice_of = [&](int g) { return pp.split ? (g >> 1) + (g & 1) * pp.nh : g; };
     for (int i = threadIdx.x; i < n_mma; i += (int)blockDim.x) {
       int t = i % p.T, kk = i / p.T;
       int tap = kk / groups, g = kk - tap * groups;
       if (pp.chunk_phase) {
-        // issue position i -> (phase, tap, rank inside the phase) -> group g
-        const int n_b = groups - n_a;
-        const int in_a = kk < p.taps * n_a;
-        const int kq = in_a ? kk : kk - p.taps * n_a, per = in_a ? n_a : n_b;
+        // issue position -> (phase = chunk, tap, rank inside the phase) -> group g
+        int ph = 0;
+        while (i >= pp.phase_end[ph]) ++ph;
+        const int base = ph ? pp.phase_end[ph - 1] : 0;
+        const int per = (pp.phase_end[ph] - base) / (p.taps * p.T);       // groups of a tap in this phase
+        const int kq = (i - base) / p.T;
         tap = kq / per;
         int rank = kq - tap * per;
         for (g = 0; g < groups; ++g)
-          if ((slice_of(g) >> 2) == (in_a ? 0 : 1) && rank-- == 0) break;
+          if (slice_of(g) / spc == ph && rank-- == 0) break;
       }
-      // A slice sa, weight slice sb, accumulator, position of this group among the groups using weight slice sb
-      int sa = g, sb = g, lo = 0, first_of_sb = 1, last_of_sb = 1;
+      // A slice sa, weight slice sb; lo = 1: the half-width MMA x_lo * w_hi into L
+      int sa = g, sb = g, lo = 0;
       if (pp.split) {
-        if (g < 2 * pp.nh) {
-          sb = g >> 1;
-          lo = g & 1;
-          sa = sb + lo * pp.nh;
-          first_of_sb = !lo;
-          last_of_sb = lo;
-        } else {
-          sa = g - 2 * pp.nh;
-          sb = pp.nh + sa;
-          lo = 1;
-        }
+        sb = g >> 1;
+        lo = g & 1;
+        sa = sb + lo * pp.nh;
       }
-      const int ca = sa >> 2, ka = sa & 3;
+      const int ca = sa / spc, ka = sa - ca * spc;
       const int c = sb >> 2, k = sb & 3;
       const int r = tap / ntap_w, q = tap - r * ntap_w;
       const int ksteps_c = (c == p.kchunks - 1) ? ktot - 4 * c : 4;
@@ -1386,11 +1377,16 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // (tx, ty) starts 8 * tx columns / 16 * ty rows into the window
       const uint32_t row0 = pp.blk ? (uint32_t)((r + 16 * (t / pp.TX)) * p.Wp + q + 8 * (t % pp.TX))
                                    : (uint32_t)(r * p.Wp + q + t * 128);
-      e.x = (((uint32_t)ca * (uint32_t)p.rows_alloc * 128u + row0 * 128u) >> 4) + 2u * (uint32_t)ka;
+      e.x = (((uint32_t)ca * a_chunk + row0 * (uint32_t)pp.a_sw) >> 4) + 2u * (uint32_t)ka;
       // weight tile and K16 slot inside it: (tap, chunk) tiles in order, or -- packed -- the full chunks first and
-      // then one tile per pair of taps holding both 32-channel tails (slots 0-1: even tap, 2-3: odd tap)
+      // then one tile per pair of taps holding both 32-channel tails (slots 0-1: even tap, 2-3: odd tap);
+      // stacked (split): the slices of all taps packed densely, four per tile
       uint32_t wt = (uint32_t)(tap * p.kchunks + c), ks = (uint32_t)k;
-      if (pp.pack_tail) {
+      if (pp.split) {
+        const int ws = tap * pp.nh + sb;
+        wt = (uint32_t)(ws >> 2);
+        ks = (uint32_t)(ws & 3);
+      } else if (pp.pack_tail) {
         if (c < p.kchunks - 1) {
           wt = (uint32_t)(tap * (p.kchunks - 1) + c);
         } else {
@@ -1400,14 +1396,15 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       e.y = (pp.b_resident ? (wt * b_stage_t) >> 4 : 0u) + 2u * ks;
       if (pp.split) {
-        e.z = (uint32_t)((lo * p.T + t) * p.n_tile);
-        // first MMA into H is group 0 of tap 0, first into L is group 1 of tap 0 (in issue order: first_h / first_l)
-        e.w = (tap == 0 && g == (lo ? first_l : first_h)) ? 0u : 1u;
+        // tile t: [H_t | L_t]; the full-width MMA starts at H_t, the half-width one at L_t.  The first MMA issued
+        // for a tile (a full-width one: every phase order starts with an x_hi slice) initialises both halves.
+        e.z = (uint32_t)(t * 2 * p.n_tile + lo * p.n_tile);
+        e.w = (i < p.T ? 0u : 1u) | (lo ? 16u : 0u);
       } else {
         e.z = (uint32_t)(((kk % pp.ksplit) * p.T + t) * p.n_tile);
         e.w = kk >= pp.ksplit ? 1u : 0u;
+        e.w |= ((k == 0 && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && t == p.T - 1) ? 4u : 0u);   // weight-ring tile boundaries
       }
-      e.w |= ((k == 0 && first_of_sb && t == 0) ? 2u : 0u) | ((k == ksteps_c - 1 && last_of_sb && t == p.T - 1) ? 4u : 0u);
       s_issue[i] = e;
     }
   }
@@ -1419,9 +1416,11 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tma_prefetch_desc(&map_res);
       tma_prefetch_desc(&map_out);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], (kPair ? 2 : 1) * 4 * kParts);        // one arrival per epilogue warp (of both CTAs)
       mbar_init(&stage_full[i], 1);
@@ -1460,6 +1459,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // TMA coordinates of the window's first (halo) pixel
       const int wy = pp.blk ? win / pp.wins_x : win, wx = pp.blk ? win - wy * pp.wins_x : 0;
       const int cx = wx * pp.BW - p.halo, cy = (pp.blk ? wy * pp.BH : win * p.THW) - p.halo, cb0 = bg * p.TBW;
+      const int cpc = pp.a_sw >> 1;                   // channels per chunk
       // direct epilogue: pull the residual pixels of this window towards L2 now, ~2 windows before they are read
       auto res_prefetch = [&]() {
         if (!p.res || pp.n_stage || (p.dbg & 128) || w >= pp.n_windows) return;
@@ -1477,13 +1477,13 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       };
       if (pp.chunk_phase) {
-        // one slot, two chunks, each released by its own phase of the MMA loop
-        for (int c = 0; c < 2; ++c) {
+        // one slot, kchunks chunks, each released by its own phase of the MMA loop
+        for (int c = 0; c < p.kchunks; ++c) {
           mbar_wait(&a_empty[c], (uint32_t)((j & 1) ^ 1));
-          if (p.ts && j < 8 && lane == 0) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 10 + c] = gtime();
+          if (p.ts && j < 8 && lane == 0 && c < 2) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 10 + c] = gtime();
           if (!(p.dbg & 8) && elect_one()) {
             mbar_expect_tx(&a_full[c], p.a_bytes);
-            tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * 64, cx, cy, cb0);
+            tma_load_4d(smem_a + (size_t)c * a_chunk, &map_a, &a_full[c], c * cpc, cx, cy, cb0);
           }
         }
         res_prefetch();
@@ -1496,11 +1496,11 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (crank == 0) mbar_expect_tx(&a_full[slot], 2u * p.a_bytes * (uint32_t)p.kchunks);
           const uint32_t bar = mapa_rank(&a_full[slot], 0);
           for (int c = 0; c < p.kchunks; ++c)
-            tma_load_4d_pair(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, bar, c * 64, cx, cy, cb0);
+            tma_load_4d_pair(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, bar, c * cpc, cx, cy, cb0);
         } else {
           mbar_expect_tx(&a_full[slot], p.a_bytes * (uint32_t)p.kchunks);
           for (int c = 0; c < p.kchunks; ++c)
-            tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * 64, cx, cy, cb0);
+            tma_load_4d(smem_a + (size_t)slot * a_slot + (size_t)c * a_chunk, &map_a, &a_full[slot], c * cpc, cx, cy, cb0);
         }
       }
       if (!(p.dbg & 8)) res_prefetch();
@@ -1516,6 +1516,13 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const uint32_t bar = mapa_rank(w_full, 0);
           for (int i = 0; i < w_tiles; ++i, kcoord += 64)
             tma_load_2d_pair(smem_b + (size_t)i * b_stage, &map_b, bar, kcoord, n0 + (int)crank * pp.b_rows);
+        } else if (pp.split) {
+          // stacked tiles: rows [0, n_tile) = w_hi, [n_tile, 2 n_tile) = w_lo (global rows n0.. and Cout_p + n0..)
+          mbar_expect_tx(w_full, 2u * p.b_bytes * (uint32_t)w_tiles);
+          for (int i = 0; i < w_tiles; ++i, kcoord += 64) {
+            tma_load_2d(smem_b + (size_t)i * b_stage, &map_b, w_full, kcoord, n0);
+            tma_load_2d(smem_b + (size_t)i * b_stage + p.b_bytes, &map_b, w_full, kcoord, p.Cout_p + n0);
+          }
         } else {
           mbar_expect_tx(w_full, p.b_bytes * (uint32_t)w_tiles);
           for (int i = 0; i < w_tiles; ++i, kcoord += 64)
@@ -1546,10 +1553,14 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
       const uint64_t desc_hi = make_smem_desc(0, 128);
       // block windows: the 8-row groups of an A tile are one window row apart
-      const uint64_t desc_hi_a = pp.blk ? (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((uint32_t)p.Wp * 128u >> 4) << 32)
-                                        : desc_hi;
+      // A operand: rows of a_sw bytes; block windows: the 8-row groups of an A tile are one window row apart
+      const uint64_t desc_hi_a = (make_smem_desc(0, (uint32_t)pp.a_sw) & ~((uint64_t)0x3FFF << 32)) |
+                                 ((uint64_t)(((uint32_t)(pp.blk ? p.Wp : 8) * (uint32_t)pp.a_sw) >> 4) << 32);
       const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
-      const int n_mma = p.taps * (pp.split ? 3 * pp.nh : ((p.Cin_p + 15) >> 4)) * p.T;
+      const int n_mma = p.taps * (pp.split ? 2 * pp.nh : ((p.Cin_p + 15) >> 4)) * p.T;
+      // stacked weights (split): full-width MMAs (N = 2 n_tile, [H | L]) and half-width ones (N = n_tile, into L)
+      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_w = (1u << 4) | ((uint32_t)(p.n_tile >> 2) << 17) | ((128u >> 4) << 24);
       if (pp.b_resident) mbar_wait(w_full, 0);
       uint32_t stage = 0, phase = 0;
       int j = 0;
@@ -1580,23 +1591,24 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           continue;
         }
         if (pp.chunk_phase) {
-          // phase A (chunk 0, already waited for above), release chunk 0, phase B (chunk 1), release chunk 1
+          // phase c = the MMAs that read chunk c (chunk 0 already waited for above); each phase releases its chunk
+          int i = 0;
+          for (int c = 0; c < p.kchunks; ++c) {
+            if (c) {
+              if (!(p.dbg & 8)) mbar_wait(&a_full[c], aph);
+              tc_fence_after();
+              if (p.ts && j < 8 && c == 1) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 9] = gtime();
+            }
+            const int end = pp.phase_end[c];
 #pragma unroll 4
-          for (int i = 0; i < pp.n_phase_a; ++i) {
-            const uint4 e = s_issue[i];
-            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+            for (; i < end; ++i) {
+              const uint4 e = s_issue[i];
+              umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y),
+                       pp.split ? ((e.w & 16u) ? idesc_n : idesc_w) : idesc, e.w & 1u);
+            }
+            umma_commit(&a_empty[c]);
+            if (p.ts && j < 8 && c == 0) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 8] = gtime();
           }
-          umma_commit(&a_empty[0]);
-          if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 8] = gtime();
-          if (!(p.dbg & 8)) mbar_wait(&a_full[1], aph);
-          tc_fence_after();
-          if (p.ts && j < 8) p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 9] = gtime();
-#pragma unroll 4
-          for (int i = pp.n_phase_a; i < n_mma; ++i) {
-            const uint4 e = s_issue[i];
-            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
-          }
-          umma_commit(&a_empty[1]);
           umma_commit(&acc_full[slot]);
           if (p.ts && j < 8) {
             p.ts[((size_t)blockIdx.x * 8 + j) * 16 + 3] = gtime();
@@ -1608,7 +1620,8 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll 4
           for (int i = 0; i < n_mma; ++i) {
             const uint4 e = s_issue[i];
-            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y), idesc, e.w & 1u);
+            umma_f16(d0 + e.z, desc_hi_a | (uint64_t)(a_lo + e.x), desc_hi | (uint64_t)(b_lo0 + e.y),
+                     pp.split ? ((e.w & 16u) ? idesc_n : idesc_w) : idesc, e.w & 1u);
           }
         } else {
           uint32_t b_lo = b_lo0;
@@ -1698,7 +1711,7 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     EpiArgs e{s_bias - n0, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, p.dbg,
-              nullptr, pp.split, (uint32_t)(p.T * p.n_tile)};
+              nullptr, pp.split, (uint32_t)(pp.split ? p.n_tile : p.T * p.n_tile), (uint32_t)(pp.split ? 2 * p.n_tile : 0)};
     const EpiLite el{p.res, p.out, smem_u32(s_bias), p.relu, p.Cout_p, p.dbg, pp.split};
     const uint32_t acc_empty_leader[2] = {kPair ? mapa_rank(&acc_empty[0], 0) : 0u, kPair ? mapa_rank(&acc_empty[1], 0) : 0u};
     int j = 0;
@@ -1778,13 +1791,13 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                        wp < p.Wp - p.halo;
             sr.srow = (uint32_t)(((bi * p.THW) + (hp - p.halo)) * p.W + (wp - p.halo));
             return sr;
-          }, pp.ksplit);
+          }, pp.ksplit, pp.split);
           if (ts && (threadIdx.x & 127) == 64) ts[13] = gtime();
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&staged[sb]);
         } else {
-          epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts, pp.ksplit);
+          epi_window_lite<kParts>(el, tbase, p.T, p.n_tile, n0, &acc_full[slot], ph, half, row_of, ts, pp.ksplit, pp.split);
         }
       }
       if (p.ts && j < 8 && lane == 0) atomicMax(p.ts + ((size_t)blockIdx.x * 8 + j) * 16 + 5, gtime());   // last warp done
@@ -1851,6 +1864,7 @@ struct TcConvPlan {
   uint32_t blk_bytes = 0;
   int halo = 0, Wp = 0, Hw = 0, THW = 0, TBW = 1, T = 1, rows_alloc = 0, b_stages = 2;
   int blk = 0, BW = 0, BH = 0, TX = 1;                 // block-shaped windows of the persistent kernel (PersistParams)
+  int a_sw = 128, a_kchunks = 0;                       // persistent kernel: window row bytes (128 / 64) and chunks per window
   float run_eff = 0.f;
   __half* d_w = nullptr;      // [Cout_p][taps*Cin_p]
   size_t w_bytes = 0;
@@ -2020,11 +2034,12 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                        (a.ksize == 1 ? a.W >= 32 : a.W >= 24);
     const int nacc = split ? 2 : 1;                  // accumulators per M tile
     const int kslices = (cin_a + 15) / 16;           // K16 slices of a tap's weight row
-    const int groups = split ? 3 * (a.Cin_p / 16) : kslices;   // MMA groups per tap
+    const int groups = split ? 2 * (a.Cin_p / 16) : kslices;   // MMA groups per tap (split: stacked weights, PersistParams)
     if (allow) {
       const int halo = a.ksize == 3 ? 1 : 0;
       const int Wp = a.W + 2 * halo, lead = halo * (Wp + 1);
-      const int w_tiles = a.ksize * a.ksize * p->kchunks;
+      // split: [w_hi | w_lo] row-stacked tiles over densely packed K16 slices (four per tile)
+      const int w_tiles = split ? ceil_div(a.ksize * a.ksize * (a.Cin_p / 16), 4) : a.ksize * a.ksize * p->kchunks;
       const size_t smem_cap = 225 * 1024;
       double best = 1e30;
       const int force_T = getenv("EGN_TC_V3_T") ? atoi(getenv("EGN_TC_V3_T")) : 0;
@@ -2037,7 +2052,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         if (a.Cout_p % (16 * n_tiles)) continue;
         const int n_tile = a.Cout_p / n_tiles;
         if (n_tile > 256 / nacc || n_tile < 16) continue;
-        const size_t b_stage_bytes = ((size_t)n_tile * 128 + 1023) & ~(size_t)1023;
+        const size_t b_stage_bytes = ((size_t)n_tile * (split ? 256 : 128) + 1023) & ~(size_t)1023;
         const int Tmax = std::min(8, 256 / nacc / n_tile);
         // window shapes: full-width rows of one image (mode 0), whole images (mode 1), or -- 3x3 convs -- blocks of
         // 8 * TX x 16 * TY pixels whose M tiles are 8 columns x 16 rows (mode 2 + TY: PersistParams::blk; every
@@ -2070,16 +2085,23 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             if (Wpw > 256 || Hw > 256) continue;
             const int rows_win = TBW * Hw * Wpw;
             if (!blk && rows_win - 2 * lead > 128 * T) continue;
-            const int rows_alloc = blk ? (rows_win + 7) & ~7 : (std::max(T * 128 + 2 * lead, rows_win) + 7) & ~7;
-            // fp16x2 windows are twice the bytes: also try a single window slot (the measured fp16 plans keep two)
+            const int rows_alloc = blk ? (rows_win + 15) & ~15 : (std::max(T * 128 + 2 * lead, rows_win) + 15) & ~15;
+            // fp16x2 windows are twice the bytes: also try a single window slot (the measured fp16 plans keep two),
+            // and 64-byte window rows when the physical channels are an odd number of 32-channel chunks (96 = 3 x 32)
             const int force_slots = getenv("EGN_TC_ASLOTS") ? atoi(getenv("EGN_TC_ASLOTS")) : 0;
+            const int force_asw = getenv("EGN_TC_ASW") ? atoi(getenv("EGN_TC_ASW")) : 0;
+            for (int a_sw = 128; a_sw >= (split && cin_a % 64 == 32 ? 64 : 128); a_sw -= 64) {
+            if (force_asw && a_sw != force_asw && (force_asw == 128 || (split && cin_a % 64 == 32))) continue;
+            const int a_kch = ceil_div(cin_a, a_sw / 2);
+            if (a_kch > kMaxChunksPersist) continue;
             for (int a_slots = 2; a_slots >= (split ? 1 : 2); --a_slots) {
             if (force_slots && a_slots != force_slots) continue;
-            const size_t a_bytes = (size_t)a_slots * p->kchunks * rows_alloc * 128;
-            const size_t fixed = 1024 + 256 + (size_t)n_tile * 4 +
+            if (a_slots == 1 && (a_kch < 2 || a_kch > 4)) continue;       // one slot = a chunk-phased ring of 2..4 chunks
+            const size_t a_bytes = (size_t)a_slots * a_kch * rows_alloc * a_sw;
+            const size_t fixed = 1024 + 320 + (size_t)n_tile * 4 +
                                  (size_t)a.ksize * a.ksize * groups * T * 16;   // barriers, bias, issue table
             // resident weights: the 32-channel tail chunks of a 3x3 conv are packed two taps per tile
-            const bool can_pack = a.ksize == 3 && p->kchunks >= 2 && cin_a % 64 == 32 && !getenv("EGN_TC_NOPACK");
+            const bool can_pack = !split && a.ksize == 3 && p->kchunks >= 2 && cin_a % 64 == 32 && !getenv("EGN_TC_NOPACK");
             const int w_tiles_res = can_pack ? a.ksize * a.ksize * (p->kchunks - 1) + (a.ksize * a.ksize + 1) / 2 : w_tiles;
             size_t smem = a_bytes + (size_t)w_tiles_res * b_stage_bytes + fixed;
             int resident = 1, bst = 0;
@@ -2115,16 +2137,18 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
             const int n_win = windows * ceil_div(256, TBW);
             const double mma_cyc = n_tile <= 32 ? 40.0 : n_tile <= 64 ? 40.0 + (n_tile - 32) * 0.25
                                  : n_tile <= 128 ? 48.0 + (n_tile - 64) * 0.25 : 64.0 + (n_tile - 128) * 0.68;
-            const double t_mma = (double)a.ksize * a.ksize * groups * T * mma_cyc;
+            // split: per slice one 2 n_tile-wide and one n_tile-wide MMA (operand-read bound: 32 + N / 4 cycles)
+            const double t_mma = split ? (double)a.ksize * a.ksize * (a.Cin_p / 16) * T * (64.0 + 0.75 * n_tile)
+                                       : (double)a.ksize * a.ksize * groups * T * mma_cyc;
             const double t_w = resident ? 0.0 : (double)w_tiles * 2400.0;
-            const double t_a = (double)p->kchunks * rows_win * 128 / 48.0;      // window load, ~48 B/cycle/SM
+            const double t_a = (double)a_kch * rows_win * a_sw / 48.0;      // window load, ~48 B/cycle/SM
             const int min_stage = getenv("EGN_TC_STAGE_MIN") ? atoi(getenv("EGN_TC_STAGE_MIN")) : 0;   // tuning
             for (int S = max_stage; S >= min_stage; --S) {
               if (S && !cb) continue;
               const size_t smem_s = smem + (size_t)S * nblk * blk_bytes * nacc;     // split: hi and lo planes staged
               if (smem_s > smem_cap) continue;
               const double t_epi = (double)T * (n_tile / 16) * (S ? 100.0 : 250.0) * nacc;
-              const double t_mm = (S ? t_mma : 1.5 * t_mma) + (a_slots == 1 ? t_a : 0.0);   // one slot: load, then multiply
+              const double t_mm = (S ? t_mma : 1.5 * t_mma) + (a_slots == 1 ? t_a / a_kch : 0.0);   // one slot: a chunk ring
               const double t_win = std::max(std::max(t_mm, t_epi), std::max(t_w, t_a)) +
                                    (S == 1 ? 4000.0 : 0.0) + 300.0;
               const double est = ceil_div(n_win * n_tiles, 148) * t_win;
@@ -2143,7 +2167,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->pack_tail = resident && can_pack;
                 p->w_tiles = resident ? w_tiles_res : w_tiles;
                 p->a_slots = a_slots;
+                p->a_sw = a_sw;
+                p->a_kchunks = a_kch;
               }
+            }
             }
             }
           }
@@ -2164,15 +2191,15 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         const char* pe = getenv("EGN_TC_PAIR");
         // per CTA the pair keeps the split's weights and windows but stages / biases the full N
         const size_t pair_smem = p->smem_bytes + (size_t)p->n_stage * p->nblk * p->blk_bytes * nacc + 4 * (size_t)p->n_tile;
-        p->use_pair = p->use_persist && !(pe && atoi(pe) == 0) && base_tiles == 1 && p->n_tiles == 2 && p->b_resident &&
+        p->use_pair = p->use_persist && !split && !(pe && atoi(pe) == 0) && base_tiles == 1 && p->n_tiles == 2 && p->b_resident &&
                       (2 * p->n_tile) % 16 == 0 && 2 * nacc * p->T * 2 * p->n_tile <= 512 && pair_smem <= 227 * 1024;
         if (p->use_pair) p->pair_smem = pair_smem;
         if (p->use_pair) p->tmem_cols = pow2_cols(2 * nacc * p->T * 2 * p->n_tile);
       }
       if (getenv("EGN_TC_VERBOSE") && p->use_persist && p->use_pair) fprintf(stderr, "[egn] (next line) CTA-pair mode\n");
       if (getenv("EGN_TC_VERBOSE") && p->use_persist)
-        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v3-persist blk=%dx%d a_slots=%d T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
-                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->blk ? p->BW : 0, p->blk ? p->BH : 0, p->a_slots, p->T, p->THW, p->TBW, p->run_eff,
+        fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v3-persist blk=%dx%d a_sw=%d a_slots=%d T=%d THW=%d TBW=%d eff=%.2f smem=%zuKB n_tiles=%d n_tile=%d resident=%d bst=%d tmem=%u stage=%dx%dx%uB cb=%d\n",
+                a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->blk ? p->BW : 0, p->blk ? p->BH : 0, p->a_sw, p->a_slots, p->T, p->THW, p->TBW, p->run_eff,
                 p->smem_bytes / 1024, p->n_tiles, p->n_tile, p->b_resident, p->b_stages, p->tmem_cols, p->n_stage, p->nblk,
                 p->blk_bytes, p->cb);
     }
@@ -2205,12 +2232,17 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   const int taps = a.ksize * a.ksize;
   const int cin_k = p->kchunks * p->kc;
   p->cin_k = cin_k;
+  //   fp16x2, v3           [2 * Cout_p][w_tiles * 64]: rows [0, Cout_p) = w_hi, [Cout_p, 2 Cout_p) = w_lo, K index
+  //                        tap * Cin_p + c (K16 slices packed densely, no per-tap padding; PersistParams "stacked")
   const bool pack = p->use_persist && p->pack_tail;
   const bool v1_split = split && !p->use_persist && !p->use_run;
+  const bool v3_split = split && p->use_persist;
   const int full_k = (p->kchunks - 1) * 64;              // channels of a tap that live in full 64-wide chunks
   const size_t tap_k = v1_split ? (size_t)(p->kchunks + p->kchunks_h) * p->kc : (size_t)cin_k;
-  const size_t K = pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * tap_k;
-  std::vector<__half> w((size_t)a.Cout_p * K, __float2half_rn(0.f));
+  const size_t K = v3_split ? (size_t)p->w_tiles * 64
+                            : (pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * tap_k);
+  const size_t w_rows = v3_split ? 2 * (size_t)a.Cout_p : (size_t)a.Cout_p;
+  std::vector<__half> w(w_rows * K, __float2half_rn(0.f));
   for (int o = 0; o < a.Cout_p; ++o)
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < a.Cin_p; ++c) {
@@ -2223,7 +2255,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                                      : (size_t)taps * full_k + (size_t)(t >> 1) * 64 + (size_t)(t & 1) * 32 + (pos - full_k);
           w[(size_t)o * K + k] = v;
         };
-        if (!split) {
+        if (v3_split) {
+          w[(size_t)o * K + (size_t)t * a.Cin_p + c] = hi;
+          w[((size_t)a.Cout_p + o) * K + (size_t)t * a.Cin_p + c] = lo;
+        } else if (!split) {
           put(c, hi);
         } else if (!v1_split) {
           put(c, hi);
@@ -2241,7 +2276,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
     tc_conv_plan_destroy(p);
     return EGN_ERR_CUDA;
   }
-  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)a.Cout_p};
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)w_rows};
   const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
   const cuuint32_t box[2] = {(cuuint32_t)p->kc, (cuuint32_t)p->n_tile};
   const cuuint32_t es[2] = {1, 1};
@@ -2290,12 +2325,13 @@ static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   const cuuint64_t C = p->cin_a, W = p->W, H = p->H;      // physical channels (fp16x2: [hi | lo] planes)
   CUresult r;
   if (p->use_run || p->use_persist) {
+    const int a_sw = p->use_persist ? p->a_sw : 128;          // window row bytes: 64 channels (SW128) or 32 (SW64)
     const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
     const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)p->Wp, (cuuint32_t)p->Hw, (cuuint32_t)p->TBW};
+    const cuuint32_t box[4] = {(cuuint32_t)(a_sw / 2), (cuuint32_t)p->Wp, (cuuint32_t)p->Hw, (cuuint32_t)p->TBW};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(a_sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (p->stride == 1) {
     const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
@@ -2400,8 +2436,8 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     rp.inv_wp = 1.0f / (float)p->Wp;
     rp.inv_img = 1.0f / (float)rp.img_rows;
     rp.T = p->T; rp.rows_alloc = p->rows_alloc;
-    rp.n_tile = p->n_tile; rp.kchunks = p->kchunks; rp.cin_k = p->cin_k; rp.b_stages = p->b_stages;
-    rp.a_bytes = (uint32_t)(p->TBW * p->Hw * p->Wp) * 128u;
+    rp.n_tile = p->n_tile; rp.kchunks = p->a_kchunks; rp.cin_k = p->cin_k; rp.b_stages = p->b_stages;
+    rp.a_bytes = (uint32_t)(p->TBW * p->Hw * p->Wp) * (uint32_t)p->a_sw;
     rp.b_bytes = (uint32_t)p->n_tile * 128u;
     rp.tmem_cols = p->tmem_cols;
     rp.bias = a.bias;
@@ -2412,6 +2448,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     pp.split = p->split ? 1 : 0;
     pp.nh = p->Cin_p / 16;
     pp.a_slots = p->a_slots;
+    pp.a_sw = p->a_sw;
     // L2 bulk prefetch of the residual rows by the A producer (direct, non-staged epilogue only):
     // EGN_TC_RES_PREFETCH = 2 (default) only when the output channels are not split over blockIdx.y, 1 always,
     // 0 never.  A split layer would prefetch the all-channel rows once per half -- 2x the residual DRAM traffic
@@ -2450,16 +2487,21 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       rp.tmem_cols = pow2_cols(2 * ks * p->T * rp.n_tile);
     }
     // chunk phasing of the single window slot (see PersistParams)
-    pp.chunk_phase = (p->split && p->a_slots == 1 && p->kchunks == 2 && p->b_resident && !pair &&
-                      !(getenv("EGN_TC_NO_CHUNK_PHASE"))) ? 1 : 0;
+    pp.chunk_phase = (p->split && p->a_slots == 1 && p->a_kchunks >= 2 && p->a_kchunks <= 4 && p->b_resident && !pair) ? 1 : 0;
+    if (p->a_slots == 1 && !pp.chunk_phase) {
+      set_error("launch_conv_tc: a single window slot needs the chunk-phased ring");
+      return EGN_ERR_STATE;
+    }
     if (pp.chunk_phase) {
-      const int groups = 3 * pp.nh;
-      int n_a = 0;
-      for (int g = 0; g < groups; ++g) {
-        const int sa = g < 2 * pp.nh ? (g >> 1) + (g & 1) * pp.nh : g - 2 * pp.nh;
-        if ((sa >> 2) == 0) ++n_a;
+      const int groups = 2 * pp.nh, spc = p->a_sw / 32;
+      int cum = 0;
+      for (int c = 0; c < 4; ++c) {
+        int n_c = 0;
+        for (int g = 0; g < groups && c < p->a_kchunks; ++g)
+          if (((g >> 1) + (g & 1) * pp.nh) / spc == c) ++n_c;
+        cum += rp.taps * n_c * p->T;
+        pp.phase_end[c] = cum;
       }
-      pp.n_phase_a = rp.taps * n_a * p->T;
     }
     CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
     if (p->n_stage && !head) {
