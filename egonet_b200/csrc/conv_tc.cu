@@ -838,13 +838,16 @@ struct TcParams {
   const float* xs;
   const float* ys;
   int coord_maps;
-  // fp16x2 split storage: the activation tensor has cin_a = 2 * Cin_p physical channels ([hi | lo] planes) and
-  // a tap's pipeline stages are the kchunks chunks of [x_hi | x_lo] against [w_hi | w_hi] followed by the
-  // kchunks_h chunks of x_hi against w_lo (weights stored in exactly that stage order); nh = Cin_p / 16 K16
-  // slices per plane.  hi*hi products accumulate in TMEM columns [0, n_tile), the cross terms in [n_tile, 2 n_tile).
-  int split, cin_a, kchunks_h, nh;
-  int one_acc;   // split storage with ONE accumulator (cross terms added to the hi*hi sum): half the TMEM columns, so two
-                 // CTAs fit per SM for N = 192; costs ~3x the accumulation-truncation bias on that layer
+  // fp16x2 split storage: the activation tensor has cin_a = 2 * Cin_p physical channels ([hi | lo] planes), nh =
+  // Cin_p / 16 K16 slices per plane.  A pipeline stage is "fat": for one (tap, kc-channel chunk of the LOGICAL input
+  // channels) it holds all four operands -- the x_hi box, the x_lo box and the row-stacked weight tile
+  // [w_hi (n_tile rows) | w_lo (n_tile rows)] (the dense stacked weight matrix of PersistParams) -- so every operand
+  // byte is fetched once per tap (the previous [x_hi | x_lo] x [w_hi | w_hi], then x_hi x w_lo staging fetched x_hi and
+  // w_hi twice: the per-tap kernel is bound by the bytes its shared-memory ring can keep in flight, so 1.5x the MMA
+  // work per byte is 1.5x the speed).  Per K16 slice: N = 2 n_tile <= 256: one MMA x_hi x [w_hi | w_lo] -> [H | L] and
+  // one x_lo x w_hi -> L; wider tiles: x_hi x w_hi -> H, x_hi x w_lo -> L, x_lo x w_hi -> L.  H (hi*hi) lives in
+  // TMEM columns [0, n_tile), L (cross terms) in [n_tile, 2 n_tile); the epilogue adds them.
+  int split, cin_a, nh;
 };
 
 template <int SW>
@@ -854,8 +857,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (swizzle atoms are address based)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_stage = 128u * SW;
-  const uint32_t b_stage = ((uint32_t)p.n_tile * SW + 1023u) & ~1023u;
+  const uint32_t a_plane = 128u * SW;                                  // one activation box
+  const uint32_t a_stage = p.split ? 2u * a_plane : a_plane;           // split: [x_hi box | x_lo box]
+  const uint32_t b_stage = ((uint32_t)p.n_tile * SW * (p.split ? 2u : 1u) + 1023u) & ~1023u;   // split: [w_hi | w_lo] rows
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * a_stage;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage);
@@ -898,23 +902,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
     int kcoord = 0;                                  // B coordinate of the stage: stages are stored back to back
-    const int kct = p.kchunks + (p.split ? p.kchunks_h : 0);      // stages per tap
+    int tap = 0;
     for (int r = 0; r < p.ksize; ++r) {
-      for (int q = 0; q < p.ksize; ++q) {
+      for (int q = 0; q < p.ksize; ++q, ++tap) {
         // stride 2: input row = 2*(oh + dh) + hp, input col = 2*(ow + dw) + wp
         const int er = r - p.pad, eq = q - p.pad;
         const int hp = er & 1, dh = (er - hp) / 2;
         const int wp = eq & 1, dw = (eq - wp) / 2;
-        for (int kcx = 0; kcx < kct; ++kcx, kcoord += p.kc) {
+        for (int kcx = 0; kcx < p.kchunks; ++kcx, kcoord += p.kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          const int c0 = (kcx < p.kchunks ? kcx : kcx - p.kchunks) * p.kc;
+          const int c0 = kcx * p.kc;
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+            uint8_t* sa = smem_a + stage * a_stage;
+            uint8_t* sb = smem_b + stage * b_stage;
+            mbar_expect_tx(&full_bar[stage], (p.split ? 2u : 1u) * (p.a_bytes + p.b_bytes));
             if (p.stride == 1)
-              tma_load_4d(smem_a + stage * a_stage, &map_a, &full_bar[stage], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
+              tma_load_4d(sa, &map_a, &full_bar[stage], c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
             else
-              tma_load_5d(smem_a + stage * a_stage, &map_a, &full_bar[stage], wp * p.cin_a + c0, ow0 + dw, hp, oh0 + dh, b0);
-            tma_load_2d(smem_b + stage * b_stage, &map_b, &full_bar[stage], kcoord, n0);
+              tma_load_5d(sa, &map_a, &full_bar[stage], wp * p.cin_a + c0, ow0 + dw, hp, oh0 + dh, b0);
+            if (p.split) {
+              // the lo-plane box of the same channels, and the stacked weight tile of (tap, chunk): dense K index
+              if (p.stride == 1)
+                tma_load_4d(sa + a_plane, &map_a, &full_bar[stage], p.Cin_p + c0, ow0 + q - p.pad, oh0 + r - p.pad, b0);
+              else
+                tma_load_5d(sa + a_plane, &map_a, &full_bar[stage], wp * p.cin_a + p.Cin_p + c0, ow0 + dw, hp, oh0 + dh, b0);
+              tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.Cin_p + c0, n0);
+              tma_load_2d(sb + p.b_bytes, &map_b, &full_bar[stage], tap * p.Cin_p + c0, p.Cout_p + n0);
+            } else {
+              tma_load_2d(sb, &map_b, &full_bar[stage], kcoord, n0);
+            }
           }
           if (++stage == (uint32_t)p.stages) {
             stage = 0;
@@ -927,47 +943,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_w = (1u << 4) | ((uint32_t)(p.n_tile >> 2) << 17) | ((128u >> 4) << 24);   // N = 2 n_tile
+    const bool wide = p.split && 2 * p.n_tile <= 256;
     const uint64_t desc_hi = make_smem_desc(0, SW);
     const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
-    const int kct = p.kchunks + (p.split ? p.kchunks_h : 0);
-    const int n_iters = p.taps * kct;
+    const int n_iters = p.taps * p.kchunks;
     uint32_t stage = 0, phase = 0;
-    bool acc_h = false, acc_l = false;               // accumulators already written (split mode)
     int kcx = 0;
     for (int it = 0; it < n_iters; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint64_t adesc = desc_hi | (uint64_t)(((a_addr0 + stage * a_stage) & 0x3FFFFu) >> 4);
       const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
-      // per K16 slice of this stage (warp-uniform): valid / which accumulator / accumulate flag
-      uint32_t m_valid = 0, m_lo = 0, m_acc = 0;
-#pragma unroll
-      for (int k = 0; k < SW / 32; ++k) {
-        if (!p.split) {
-          m_valid |= 1u << k;
-          if (it | k) m_acc |= 1u << k;
-        } else {
-          const bool g2 = kcx >= p.kchunks;
-          const int sg = (g2 ? kcx - p.kchunks : kcx) * (SW / 32) + k;
-          if (sg >= (g2 ? p.nh : 2 * p.nh)) continue;        // padding slice
-          const bool lo = (g2 || sg >= p.nh) && !p.one_acc;
-          m_valid |= 1u << k;
-          if (lo) m_lo |= 1u << k;
-          if (lo ? acc_l : acc_h) m_acc |= 1u << k;
-          if (lo) acc_l = true; else acc_h = true;
-        }
-      }
       if (elect_one()) {
+        if (!p.split) {
 #pragma unroll
-        for (int k = 0; k < SW / 32; ++k) {
-          // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
-          if (m_valid >> k & 1u)
-            umma_f16(tmem_base + ((m_lo >> k & 1u) && !p.one_acc ? (uint32_t)p.n_tile : 0u), adesc + (uint64_t)(2 * k),
-                     bdesc + (uint64_t)(2 * k), idesc, m_acc >> k & 1u);
+          for (int k = 0; k < SW / 32; ++k)      // +32 bytes (16 fp16) along K inside the swizzle span: start-address field += 2
+            umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        } else {
+          const uint64_t adesc_lo = adesc + (uint64_t)(a_plane >> 4);
+          const uint64_t bdesc_lo = bdesc + (uint64_t)(p.b_bytes >> 4);
+#pragma unroll
+          for (int k = 0; k < SW / 32; ++k) {
+            if (kcx * (SW / 32) + k >= p.nh) continue;             // padding slice of the last chunk
+            const uint32_t acc = (it | k) ? 1u : 0u;               // the first slice initialises H and L
+            const uint64_t ko = (uint64_t)(2 * k);
+            if (wide) {
+              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc_w, acc);                               // [H | L] += x_hi [w_hi | w_lo]
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
+            } else {
+              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                                 // H += x_hi w_hi
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);         // L += x_hi w_lo
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
+            }
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees this stage once the MMAs above have read it
       }
-      if (++kcx == kct) kcx = 0;
+      if (++kcx == p.kchunks) kcx = 0;
       if (++stage == (uint32_t)p.stages) {
         stage = 0;
         phase ^= 1u;
@@ -988,7 +1001,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     er.valid = row < p.TW * p.TH * p.TB && er.b < p.B && er.oh < p.OH && er.ow < p.OW;
     er.pix = ((size_t)er.b * p.OH + er.oh) * p.OW + er.ow;
     EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr,
-              p.split, p.one_acc ? 0u : (uint32_t)p.n_tile, 0u};
+              p.split, (uint32_t)p.n_tile, 0u};
     epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
             [&](int) { return er; });
   }
@@ -1842,10 +1855,8 @@ static EncodeTiledFn get_encode_fn() {
 struct TcConvPlan {
   // shape (batch independent)
   int H, W, Cin_p, OH, OW, Cout_p, Cout, ksize, stride, pad;
-  bool one_acc = false; // per-tap kernel, fp16x2: single accumulator (TcParams::one_acc)
   bool split = false;   // fp16x2 storage: cin_a = 2 * Cin_p physical input channels, 2 * Cout_p physical output channels
   int cin_a = 0;        // physical channels of the activation tensor
-  int kchunks_h = 0;    // v1, split: chunks of the x_hi * w_lo stage group
   int sw;          // swizzle bytes 32 / 64 / 128
   int kc, kchunks, cin_k, n_tile, n_tiles, stages;
   int TW, TH, TB;
@@ -1920,8 +1931,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   if (force_sw == 0 && cin_a <= 16) p->sw = 32;
   else if (force_sw == 0 && cin_a <= 32) p->sw = 64;
   p->kc = p->sw / 2;
-  p->kchunks = ceil_div(cin_a, p->kc);
-  p->kchunks_h = split ? ceil_div(a.Cin_p, p->kc) : 0;
+  p->kchunks = ceil_div(cin_a, p->kc);      // (the fp16x2 per-tap plan recomputes sw / kc / kchunks below)
   // split mode keeps two accumulators per tile (hi*hi | cross terms): at most 256 columns each in v1
   p->n_tiles = a.Cout_p > 256 ? 2 : 1;
   p->n_tile = a.Cout_p / p->n_tiles;
@@ -1938,8 +1948,8 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   // its own ring); layers that need all 512 columns keep the deep ring (192ch: 183 us vs 217 us).
   const bool two_ctas = split && pow2_cols(2 * p->n_tile) <= 256;
   const size_t budget = getenv("EGN_TC_V1_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V1_BUDGET_KB")) * 1024
-                        : (stage > 24 * 1024 ? (two_ctas ? 100 * 1024 : 176 * 1024) : 80 * 1024);
-  const int n_iters = a.ksize * a.ksize * (p->kchunks + p->kchunks_h);
+                        : (stage > 24 * 1024 ? 176 * 1024 : 80 * 1024);
+  const int n_iters = a.ksize * a.ksize * p->kchunks;
   size_t st_count = std::min<size_t>((size_t)kMaxStages, budget / stage);
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
   p->stages = (int)std::max<size_t>(2, st_count);
@@ -2206,19 +2216,27 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   }
   if (!p->use_persist && !p->use_run) {
     // v1 after a rejected window-run / persistent plan: its own TMEM and shared-memory footprint
-    // N = 192 tiles (192 / 384-channel layers): two accumulators need all 512 TMEM columns, i.e. one CTA per SM.  With
-    // the cross terms added to the hi*hi accumulator instead (EGN_TC_SPLIT_1ACC=1), two CTAs fit: 195 -> 160 us
-    // (192ch@16x16) and 164 -> 131 us (384ch@8x8) at batch 256, +2 % end to end -- but the truncating accumulation then
-    // sees 3x the steps on those layers and the demo-config errors grow 2.5x (coords 4.8e-6 -> 1.25e-5, 3-D key-points
-    // 7e-5 -> 1.45e-4 m, past the 1e-4 bound).  OFF by default: parity first.
-    p->one_acc = split && getenv("EGN_TC_SPLIT_1ACC") && atoi(getenv("EGN_TC_SPLIT_1ACC")) && pow2_cols(2 * p->n_tile) > 256;
-    p->tmem_cols = pow2_cols((split && !p->one_acc ? 2 : 1) * p->n_tile);
-    if (p->one_acc && !getenv("EGN_TC_V1_BUDGET_KB")) {
-      // two CTAs per SM become possible: size the ring for that
-      size_t st2 = std::min<size_t>((size_t)kMaxStages, (100 * 1024) / stage);
-      p->stages = (int)std::max<size_t>(2, std::min<size_t>(st2, (size_t)std::max(2, n_iters)));
+    // (A single accumulator for N = 192 tiles -- cross terms added to the hi*hi sum so that two CTAs fit per SM -- was
+    // measured at +2 % end to end but 2.5x the error, past the 1e-4 bound on 3-D key-points: removed.)
+    p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
+    if (split) {
+      // fat stages (TcParams): x_hi box + x_lo box + [w_hi | w_lo] rows per (tap, kc LOGICAL channels).  32-channel
+      // stages by default (EGN_TC_V1_SW overrides): more, smaller stages in flight for the same bytes.  Tiles of at most
+      // 256 TMEM columns: ~100 KB rings so that TWO CTAs share an SM (one CTA cannot hide the L2 latency of its own ring);
+      // wider tiles need all 512 columns: one CTA with the deepest ring that fits.
+      if (force_sw == 0) p->sw = getenv("EGN_TC_V1_SW") ? atoi(getenv("EGN_TC_V1_SW")) : 64;
+      p->kc = p->sw / 2;
+      p->kchunks = ceil_div(a.Cin_p, p->kc);
+      const size_t stage2 = 2 * 128 * (size_t)p->sw + (((size_t)2 * p->n_tile * p->sw + 1023) & ~(size_t)1023);
+      const size_t budget2 = getenv("EGN_TC_V1_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V1_BUDGET_KB")) * 1024
+                                                           : (two_ctas ? 104 * 1024 : 208 * 1024);
+      size_t st2 = std::min<size_t>((size_t)kMaxStages, budget2 / stage2);
+      st2 = std::min<size_t>(st2, (size_t)std::max(2, a.ksize * a.ksize * p->kchunks));
+      p->stages = (int)std::max<size_t>(2, st2);
+      p->smem_bytes = 1024 + p->stages * stage2 + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+    } else {
+      p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
     }
-    p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
   }
   if (getenv("EGN_TC_VERBOSE") && !p->use_persist && !p->use_run)
     fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v1-tap n_tile=%d stages=%d smem=%zuKB tmem=%u\n", a.ksize, a.ksize,
@@ -2235,11 +2253,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   //   fp16x2, v3           [2 * Cout_p][w_tiles * 64]: rows [0, Cout_p) = w_hi, [Cout_p, 2 Cout_p) = w_lo, K index
   //                        tap * Cin_p + c (K16 slices packed densely, no per-tap padding; PersistParams "stacked")
   const bool pack = p->use_persist && p->pack_tail;
-  const bool v1_split = split && !p->use_persist && !p->use_run;
-  const bool v3_split = split && p->use_persist;
+  const bool v1_split = false;                                          // (the per-tap kernel shares the stacked matrix)
+  const bool v3_split = split && !p->use_run;                           // stacked matrix: persistent and per-tap kernels
   const int full_k = (p->kchunks - 1) * 64;              // channels of a tap that live in full 64-wide chunks
-  const size_t tap_k = v1_split ? (size_t)(p->kchunks + p->kchunks_h) * p->kc : (size_t)cin_k;
-  const size_t K = v3_split ? (size_t)p->w_tiles * 64
+  const size_t tap_k = (size_t)cin_k;
+  const size_t K = v3_split ? ((size_t)taps * a.Cin_p + 63) / 64 * 64
                             : (pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * tap_k);
   const size_t w_rows = v3_split ? 2 * (size_t)a.Cout_p : (size_t)a.Cout_p;
   std::vector<__half> w(w_rows * K, __float2half_rn(0.f));
@@ -2377,9 +2395,9 @@ static int device_setup() {
   auto opt_in = [&](const void* fn, int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   };
-  opt_in((const void*)conv_tc_kernel<128>, 200 * 1024);
-  opt_in((const void*)conv_tc_kernel<64>, 200 * 1024);
-  opt_in((const void*)conv_tc_kernel<32>, 200 * 1024);
+  opt_in((const void*)conv_tc_kernel<128>, 227 * 1024);
+  opt_in((const void*)conv_tc_kernel<64>, 227 * 1024);
+  opt_in((const void*)conv_tc_kernel<32>, 227 * 1024);
   opt_in((const void*)conv_run_kernel, 200 * 1024 + 2048);
   opt_in((const void*)conv_persist_kernel<false>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<true>, 227 * 1024);
@@ -2610,8 +2628,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   }
   TcParams tp{};
   tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
-  tp.split = p->split ? 1 : 0; tp.cin_a = p->cin_a; tp.kchunks_h = p->kchunks_h; tp.nh = p->Cin_p / 16;
-  tp.one_acc = p->one_acc ? 1 : 0;
+  tp.split = p->split ? 1 : 0; tp.cin_a = p->cin_a; tp.nh = p->Cin_p / 16;
   tp.taps = p->ksize * p->ksize; tp.ksize = p->ksize; tp.stride = p->stride; tp.pad = p->pad; tp.relu = a.relu;
   tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
   tp.tiles_w = ceil_div(p->OW, p->TW);
