@@ -718,7 +718,7 @@ __device__ __forceinline__ void epi_window_staged(const EpiStage& e, uint32_t tm
   auto item = [&](const uint32_t (&v)[16], const StageRow& sr, int cg) {
     if (!sr.valid || (e.dbg & 256)) return;
     const int col = 16 * cg;
-    const int blk = e.cb == 64 ? (col >> 6) : col / 48;
+    const int blk = e.cb == 64 ? (col >> 6) : col / e.cb;
     const uint32_t ch = (uint32_t)(col - blk * e.cb) >> 3;                    // first 16-byte chunk (even)
     const uint32_t rowb = e.base + (uint32_t)blk * e.blk_bytes + sr.srow * pitch;
     const uint32_t sw = e.cb == 64 ? (sr.srow & 7u) : 0u;
@@ -1010,6 +1010,254 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// v4: "tap window" kernel for stride-1 3x3 convs on small maps (16x16, 32x32 with many channels)
+//
+// The per-tap kernel (v1) fetches the activation tile once per filter tap and its ring can only keep a fixed number
+// of bytes in flight, so it ends up bound by the L2 -> SM traffic (96 channels, fp16x2: 756 KB per 128-pixel tile,
+// ~28 B / cycle / SM = two thirds of the measured L2 cap).  Here the output tile is an 8 x 16-pixel block of one
+// image; for each kc-channel chunk the CTA loads the block PLUS its halo once (one TMA box of 10 x 18 pixels per
+// plane; out-of-image pixels zero-filled = the conv padding) into an A ring slot and runs all nine taps from it:
+// tap (r, s) is the same buffer with the descriptor start shifted by (r * 10 + s) rows and the 8-row groups one
+// window row (10 pixels) apart (stride byte offset = 10 * SW bytes, see PersistParams::blk).  Only the weight tile of
+// (chunk, tap) streams through the B ring.  A traffic drops 9x -> 2.5x the tile (halo), e.g. 393 KB instead of
+// 756 KB per tile for 96 channels.  fp16x2 operands as in the per-tap kernel's fat stages: an A slot holds the
+// x_hi and the x_lo box, a B stage the row-stacked [w_hi | w_lo] tile.
+// ---------------------------------------------------------------------------
+constexpr int kTwMaxA = 4, kTwMaxB = 8;
+constexpr int kTwWp = 10, kTwHp = 18;        // window = (8 + 2) x (16 + 2) pixels
+
+struct TapWinParams {
+  int B, H, W, Cout_p, Cout, Cin_p, relu;
+  int tiles_x, tiles_y;      // 8 x 16 blocks per image
+  int n_tile, kc, kchunks;   // UMMA N, channels per chunk (SW / 2), chunks of the logical input channels
+  int na, nb;                // A ring slots, B ring stages
+  int tap_k;                 // K stride between taps in the weight matrix (dense stacked: Cin_p; plain: padded cin_k)
+  uint32_t a_bytes, b_bytes; // one activation box (180 * SW), one plane's weight rows (n_tile * SW)
+  uint32_t tmem_cols;
+  int split, nh;             // fp16x2 storage; K16 slices per plane (plain fp16: all slices)
+  const float* bias;
+  const __half* res;
+  __half* out;
+  float* heatmap;            // head1 extras of the shared epilogue (EpiArgs)
+  const float* xs;
+  const float* ys;
+  int coord_maps;
+  unsigned long long* ts;    // optional [grid][8] globaltimer stamps (EGN_TC_TS=1)
+  // Staged TMA epilogue (see epi_window_staged): once the last MMA has completed the operand rings are dead, so the
+  // residual block arrives by TMA at the start of shared memory ([block][8 x 16 pixels][cb channels], hi blocks then
+  // lo blocks), every epilogue thread converts its row in place and the block leaves by TMA tensor stores, which
+  // also clip ragged tiles.  The direct epilogue (one uncoalesced 16-byte access per lane and instruction) took
+  // 12-13 us per 128 x 96 / 192-channel fp16x2 tile -- as long as the MMA phase.
+  int staged, cb, nblk_plane;
+  uint32_t blk_bytes;
+};
+
+template <int SW>
+__global__ void __launch_bounds__(kTcThreads, 2)
+conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
+                   const TapWinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_plane = ((uint32_t)(kTwWp * kTwHp) * SW + 1023u) & ~1023u;
+  const uint32_t a_slot = p.split ? 2u * a_plane : a_plane;
+  const uint32_t b_stage = ((uint32_t)p.n_tile * SW * (p.split ? 2u : 1u) + 1023u) & ~1023u;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.na * a_slot;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.nb * b_stage);
+  uint64_t* a_empty = a_full + kTwMaxA;
+  uint64_t* b_full = a_empty + kTwMaxA;
+  uint64_t* b_empty = b_full + kTwMaxB;
+  uint64_t* tmem_full_bar = b_empty + kTwMaxB;
+  uint64_t* res_full = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [n_tile]; offset 26 * 8 + 16 = 224: 16-byte aligned
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int b0 = tile / p.tiles_y;
+  const int x0 = tx * 8, y0 = ty * 16;
+  const int n0 = blockIdx.y * p.n_tile;
+  if (threadIdx.x == 0) EGN_TS(0);
+  if (p.staged)
+    for (int i = threadIdx.x; i < p.n_tile; i += (int)blockDim.x) s_bias[i] = __ldg(p.bias + n0 + i);
+
+  if (threadIdx.x == 0) {
+    pdl_trigger();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.staged) {
+      tma_prefetch_desc(&map_res);
+      tma_prefetch_desc(&map_out);
+    }
+    for (int i = 0; i < kTwMaxA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kTwMaxB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(res_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
+  if (threadIdx.x == 0) EGN_TS(1);
+
+  if (warp == 0) {
+    // ===================== TMA producer: A chunk windows + the weight tile of every (chunk, tap) =====================
+    auto load_a = [&](int c) {
+      const int slot = c % p.na;
+      mbar_wait(&a_empty[slot], (uint32_t)(((c / p.na) & 1) ^ 1));
+      if (elect_one()) {
+        uint8_t* sa = smem_a + (size_t)slot * a_slot;
+        mbar_expect_tx(&a_full[slot], (p.split ? 2u : 1u) * p.a_bytes);
+        tma_load_4d(sa, &map_a, &a_full[slot], c * p.kc, x0 - 1, y0 - 1, b0);
+        if (p.split) tma_load_4d(sa + a_plane, &map_a, &a_full[slot], p.Cin_p + c * p.kc, x0 - 1, y0 - 1, b0);
+      }
+    };
+    load_a(0);
+    uint32_t stage = 0, phase = 0;
+    for (int c = 0; c < p.kchunks; ++c) {
+      for (int tap = 0; tap < 9; ++tap) {
+        if (tap == 1 && c + 1 < p.kchunks) load_a(c + 1);      // next chunk's window, ~8 weight tiles ahead of its use
+        mbar_wait(&b_empty[stage], phase ^ 1u);
+        if (elect_one()) {
+          uint8_t* sb = smem_b + (size_t)stage * b_stage;
+          mbar_expect_tx(&b_full[stage], (p.split ? 2u : 1u) * p.b_bytes);
+          tma_load_2d(sb, &map_b, &b_full[stage], tap * p.tap_k + c * p.kc, n0);
+          if (p.split) tma_load_2d(sb + p.b_bytes, &map_b, &b_full[stage], tap * p.tap_k + c * p.kc, p.Cout_p + n0);
+        }
+        if (++stage == (uint32_t)p.nb) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    if (p.staged && p.res) {
+      // every MMA has completed (tmem_full_bar): the rings are dead, the residual block lands on top of them
+      mbar_wait(tmem_full_bar, 0);
+      if (elect_one()) {
+        const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
+        mbar_expect_tx(res_full, (uint32_t)nblk * (uint32_t)(128 * p.cb * 2));
+        for (int k = 0; k < nblk; ++k) {
+          const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
+          tma_load_4d(smem + (size_t)k * p.blk_bytes, &map_res, res_full, ch, x0, y0, b0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_w = (1u << 4) | ((uint32_t)(p.n_tile >> 2) << 17) | ((128u >> 4) << 24);   // N = 2 n_tile
+    const bool wide = p.split && 2 * p.n_tile <= 256;
+    const uint64_t desc_hi = make_smem_desc(0, SW);
+    // A: 8-row groups one window row apart
+    const uint64_t desc_hi_a = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(((uint32_t)kTwWp * SW) >> 4) << 32);
+    const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
+    uint32_t stage = 0, phase = 0;
+    for (int c = 0; c < p.kchunks; ++c) {
+      const int slot = c % p.na;
+      mbar_wait(&a_full[slot], (uint32_t)((c / p.na) & 1));
+      tc_fence_after();
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_wait(&b_full[stage], phase);
+        tc_fence_after();
+        if (c == 0 && tap == 0 && lane == 0) EGN_TS(2);
+        const int r = tap / 3, q = tap - 3 * r;
+        const uint64_t adesc = desc_hi_a | (uint64_t)(((a_addr0 + (uint32_t)slot * a_slot + (uint32_t)(r * kTwWp + q) * SW) & 0x3FFFFu) >> 4);
+        const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
+        if (elect_one()) {
+          const uint64_t adesc_lo = adesc + (uint64_t)(a_plane >> 4);
+          const uint64_t bdesc_lo = bdesc + (uint64_t)(p.b_bytes >> 4);
+#pragma unroll
+          for (int k = 0; k < SW / 32; ++k) {
+            if (c * (SW / 32) + k >= p.nh) continue;               // padding slice of the last chunk
+            const uint32_t acc = (c | tap | k) ? 1u : 0u;          // the very first MMA initialises the accumulators
+            const uint64_t ko = (uint64_t)(2 * k);
+            if (!p.split) {
+              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);
+            } else if (wide) {
+              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc_w, acc);                               // [H | L] += x_hi [w_hi | w_lo]
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
+            } else {
+              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                                 // H += x_hi w_hi
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);         // L += x_hi w_lo
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
+            }
+          }
+          umma_commit(&b_empty[stage]);
+          if (tap == 8) umma_commit(&a_empty[slot]);
+        }
+        if (++stage == (uint32_t)p.nb) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    if (lane == 0) EGN_TS(3);
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;     // accumulator row -> pixel (row & 7, row >> 3) of the block
+    EpiRow er;
+    er.b = b0;
+    er.oh = y0 + (row >> 3);
+    er.ow = x0 + (row & 7);
+    er.valid = er.b < p.B && er.oh < p.H && er.ow < p.W;
+    er.pix = ((size_t)er.b * p.H + er.oh) * p.W + er.ow;
+    if (p.staged) {
+      const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
+      const EpiStage es{smem_u32(smem), smem_u32(s_bias), p.blk_bytes, p.cb, p.res != nullptr, p.relu, 0,
+                        p.split ? (uint32_t)p.nblk_plane * p.blk_bytes : 0u};
+      mbar_wait(tmem_full_bar, 0);
+      if (p.res) mbar_wait(res_full, 0);
+      tc_fence_after();
+      if ((threadIdx.x & 127) == 64) EGN_TS(4);
+      epi_window_staged<1>(es, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, 0, [&](int) {
+        StageRow sr;
+        sr.valid = true;                     // pixels past the image are clipped by the TMA store
+        sr.srow = (uint32_t)row;             // staging row = (row >> 3) * 8 + (row & 7): the block is row-major
+        return sr;
+      }, p.split ? 2 : 1, p.split);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+      if (warp == 2 && elect_one()) {
+        for (int k = 0; k < nblk; ++k) {
+          const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
+          tma_store_4d(&map_out, smem + (size_t)k * p.blk_bytes, ch, x0, y0, b0);
+        }
+        bulk_commit();
+        bulk_wait0();                          // shared memory is released (and the writes complete) before the CTA exits
+      }
+    } else {
+      EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, 0,
+                p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, p.split, (uint32_t)p.n_tile, 0u};
+      epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
+              [&](int) { return er; });
+    }
+    if ((threadIdx.x & 127) == 64) EGN_TS(5);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (lane == 0) EGN_TS(6);
   }
 }
 
@@ -1865,6 +2113,8 @@ struct TcConvPlan {
   // v2 (window run) configuration; use_run == false -> v1 per-tap kernel
   bool use_run = false;
   bool use_persist = false;   // v3: persistent one-CTA-per-SM variant of the window-run kernel
+  bool use_tapwin = false;    // v4: tap-window kernel (conv_tapwin_kernel)
+  int tw_na = 2, tw_nb = 4;   // its A ring slots / B ring stages
   bool use_pair = false;      // v3 with CTA pairs (cta_group::2) instead of an N split over blockIdx.y
   size_t pair_smem = 0;       // dynamic smem per CTA in pair mode
   bool pack_tail = false;     // weight matrix stored with the 32-channel tail chunks of two taps per tile (see PersistParams)
@@ -2057,8 +2307,13 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const int base_tiles = p->n_tiles;
       // Splitting the output channels over blockIdx.y (split = 2) lets each half keep its weights resident
       // when the whole matrix does not fit (96 channels: 2 x 108 KB); both halves then load the window.
-      for (int split = 1; split <= (getenv("EGN_TC_V3_NOSPLIT") ? 1 : 2); split *= 2) {
-        const int n_tiles = base_tiles * split;
+      // (fp16x2, EGN_TC_V3_NSPLIT=3: 96 channels as 3 x 32 keep 112 KB of stacked weights each -- measured 186 us
+      // against 156 us for the tap-window kernel with full-width N = 192 / 96 MMAs: off by default)
+      const int force_nsplit = getenv("EGN_TC_V3_NSPLIT") ? atoi(getenv("EGN_TC_V3_NSPLIT")) : 0;
+      for (int nsplit = 1; nsplit <= (getenv("EGN_TC_V3_NOSPLIT") ? 1 : (force_nsplit ? 4 : 2)); ++nsplit) {
+        if (force_nsplit && nsplit != force_nsplit) continue;
+        if (!split && nsplit == 3) continue;
+        const int n_tiles = base_tiles * nsplit;
         if (a.Cout_p % (16 * n_tiles)) continue;
         const int n_tile = a.Cout_p / n_tiles;
         if (n_tile > 256 / nacc || n_tile < 16) continue;
@@ -2133,7 +2388,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                                      : (double)a.H * a.W / ((double)windows * T * 128);
             if (force_T && T != force_T) continue;
             // staging buffers of the TMA epilogue: [block][TBW*THW*W pixels][cb channels]
-            const int cb = n_tile % 64 == 0 ? 64 : (n_tile % 48 == 0 ? 48 : 0);
+            const int cb = n_tile % 64 == 0 ? 64 : (n_tile % 48 == 0 ? 48 : (n_tile % 32 == 0 ? 32 : 0));
             const int rows_stage = blk ? BW * BH : TBW * THW * a.W;
             const size_t blk_bytes = cb ? (((size_t)rows_stage * cb * 2 + 1023) & ~(size_t)1023) : 0;
             const int nblk = cb ? n_tile / cb : 0;
@@ -2219,7 +2474,48 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
     // (A single accumulator for N = 192 tiles -- cross terms added to the hi*hi sum so that two CTAs fit per SM -- was
     // measured at +2 % end to end but 2.5x the error, past the 1e-4 bound on 3-D key-points: removed.)
     p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
-    if (split) {
+    // v4 tap-window kernel: stride-1 3x3 convs whose map tiles into 8 x 16 blocks without much waste
+    {
+      const char* e4 = getenv("EGN_TC_V4");
+      const int tiles = ceil_div(a.W, 8) * ceil_div(a.H, 16);
+      const double eff4 = (double)a.H * a.W / ((double)tiles * 128);
+      const int v4_mode = e4 ? atoi(e4) : 1;              // 0 off, 1 fp16x2 only, 2 plain fp16 too
+      if (a.ksize == 3 && a.stride == 1 && a.pad == 1 && eff4 >= 0.75 && v4_mode && (split || v4_mode == 2) && force_sw == 0) {
+        p->use_tapwin = true;
+        // 32-channel chunks where two CTAs share an SM (<= 256 TMEM columns), 64-channel chunks for the wide tiles
+        // (measured, batch 256: 96ch 156 vs 226 us, 192ch 138 vs 128 us)
+        p->sw = getenv("EGN_TC_V4_SW") ? atoi(getenv("EGN_TC_V4_SW")) : (p->tmem_cols <= 256 ? 64 : 128);
+        p->kc = p->sw / 2;
+        p->kchunks = ceil_div(a.Cin_p, p->kc);
+        const size_t a_plane = ((size_t)kTwWp * kTwHp * p->sw + 1023) & ~(size_t)1023;
+        const size_t a_slot = (split ? 2 : 1) * a_plane;
+        const size_t b_stage4 = ((size_t)p->n_tile * p->sw * (split ? 2 : 1) + 1023) & ~(size_t)1023;
+        const bool two = p->tmem_cols <= 256;
+        const size_t budget4 = getenv("EGN_TC_V4_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V4_BUDGET_KB")) * 1024
+                                                             : (two ? 106 * 1024 : 212 * 1024);
+        p->tw_na = getenv("EGN_TC_V4_NA") ? atoi(getenv("EGN_TC_V4_NA")) : 2;
+        p->tw_na = std::max(1, std::min(std::min(p->tw_na, kTwMaxA), std::max(1, p->kchunks)));
+        const size_t fixed4 = 1024 + (2 * kTwMaxA + 2 * kTwMaxB + 2) * sizeof(uint64_t) + 32 + (size_t)p->n_tile * 4;
+        long nb = ((long)budget4 - (long)fixed4 - (long)(p->tw_na * a_slot)) / (long)b_stage4;
+        p->tw_nb = (int)std::max<long>(2, std::min<long>(nb, kTwMaxB));
+        p->smem_bytes = fixed4 + p->tw_na * a_slot + p->tw_nb * b_stage4;
+        if (p->smem_bytes > 227 * 1024) p->use_tapwin = false;
+        // staged epilogue on top of the dead rings: [block][128 pixels][cb channels], hi blocks then lo blocks
+        p->cb = p->n_tile % 64 == 0 ? 64 : (p->n_tile % 48 == 0 ? 48 : (p->n_tile % 32 == 0 ? 32 : 0));
+        p->nblk = p->cb ? p->n_tile / p->cb : 0;
+        p->blk_bytes = (uint32_t)(128 * p->cb * 2);
+        p->n_stage = (p->cb && !(getenv("EGN_TC_V4_STAGED") && atoi(getenv("EGN_TC_V4_STAGED")) == 0) &&
+                      (size_t)(split ? 2 : 1) * p->nblk * p->blk_bytes <= p->tw_na * a_slot + p->tw_nb * b_stage4) ? 1 : 0;
+        p->blk = 1; p->BW = 8; p->BH = 16; p->TBW = 1;          // staging box of make_io_map
+        if (getenv("EGN_TC_VERBOSE") && p->use_tapwin)
+          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d\n",
+                  a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->sw, p->kchunks,
+                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb);
+      }
+    }
+    if (p->use_tapwin) {
+      // (geometry fixed above)
+    } else if (split) {
       // fat stages (TcParams): x_hi box + x_lo box + [w_hi | w_lo] rows per (tap, kc LOGICAL channels).  32-channel
       // stages by default (EGN_TC_V1_SW overrides): more, smaller stages in flight for the same bytes.  Tiles of at most
       // 256 TMEM columns: ~100 KB rings so that TWO CTAs share an SM (one CTA cannot hide the L2 latency of its own ring);
@@ -2238,7 +2534,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
     }
   }
-  if (getenv("EGN_TC_VERBOSE") && !p->use_persist && !p->use_run)
+  if (getenv("EGN_TC_VERBOSE") && !p->use_persist && !p->use_run && !p->use_tapwin)
     fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v1-tap n_tile=%d stages=%d smem=%zuKB tmem=%u\n", a.ksize, a.ksize,
             a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->stages, p->smem_bytes / 1024, p->tmem_cols);
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][K] fp16, zero padded to whole kc-channel chunks.
@@ -2354,7 +2650,9 @@ static int make_a_map(TcConvPlan* p, const void* in, int B, CUtensorMap* m) {
   } else if (p->stride == 1) {
     const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
     const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)p->kc, (cuuint32_t)p->TW, (cuuint32_t)p->TH, (cuuint32_t)p->TB};
+    const cuuint32_t box_v1[4] = {(cuuint32_t)p->kc, (cuuint32_t)p->TW, (cuuint32_t)p->TH, (cuuint32_t)p->TB};
+    const cuuint32_t box_v4[4] = {(cuuint32_t)p->kc, (cuuint32_t)kTwWp, (cuuint32_t)kTwHp, 1};      // block + halo
+    const cuuint32_t* box = p->use_tapwin ? box_v4 : box_v1;
     const cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p->sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -2399,6 +2697,8 @@ static int device_setup() {
   opt_in((const void*)conv_tc_kernel<64>, 227 * 1024);
   opt_in((const void*)conv_tc_kernel<32>, 227 * 1024);
   opt_in((const void*)conv_run_kernel, 200 * 1024 + 2048);
+  opt_in((const void*)conv_tapwin_kernel<128>, 227 * 1024);
+  opt_in((const void*)conv_tapwin_kernel<64>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<false>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<true>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<false, true>, 227 * 1024);
@@ -2623,6 +2923,76 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       fprintf(stderr, "[egn-ts] ctas=%zu span=%.2fus | avg since CTA start (us): init %.2f, A-ready %.2f, mma-issued %.2f, acc-ready %.2f, epi-done %.2f, dealloc %.2f\n",
               n_cta, (t1 - t0) * 1e-3, acc[1] / n_cta * 1e-3, acc[2] / n_cta * 1e-3, acc[3] / n_cta * 1e-3, acc[4] / n_cta * 1e-3,
               acc[5] / n_cta * 1e-3, acc[6] / n_cta * 1e-3);
+    }
+    return EGN_OK;
+  }
+  if (p->use_tapwin) {
+    TapWinParams wp{};
+    wp.B = a.B; wp.H = p->H; wp.W = p->W; wp.Cout_p = p->Cout_p; wp.Cout = p->Cout; wp.Cin_p = p->Cin_p; wp.relu = a.relu;
+    wp.tiles_x = ceil_div(p->W, 8); wp.tiles_y = ceil_div(p->H, 16);
+    wp.n_tile = p->n_tile; wp.kc = p->kc; wp.kchunks = p->kchunks; wp.na = p->tw_na; wp.nb = p->tw_nb;
+    wp.tap_k = p->split ? p->Cin_p : p->cin_k;
+    wp.a_bytes = (uint32_t)(kTwWp * kTwHp) * (uint32_t)p->sw;
+    wp.b_bytes = (uint32_t)p->n_tile * (uint32_t)p->sw;
+    wp.tmem_cols = p->tmem_cols;
+    wp.split = p->split ? 1 : 0;
+    wp.nh = p->Cin_p / 16;
+    wp.bias = a.bias;
+    wp.res = static_cast<const __half*>(a.res);
+    wp.out = static_cast<__half*>(a.out);
+    wp.heatmap = a.heatmap; wp.xs = a.xs; wp.ys = a.ys; wp.coord_maps = a.coord_maps;
+    CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
+    wp.staged = (p->n_stage && !a.heatmap && !a.coord_maps) ? 1 : 0;
+    if (wp.staged) {
+      wp.cb = p->cb; wp.nblk_plane = p->nblk; wp.blk_bytes = p->blk_bytes;
+      std::lock_guard<std::mutex> lock(p->mu);
+      for (int which = 0; which < 2; ++which) {
+        const void* ptr = which ? a.out : a.res;
+        if (!ptr) continue;
+        auto key = std::make_pair(ptr, a.B);
+        auto it = p->io_maps.find(key);
+        if (it == p->io_maps.end()) {
+          if (p->io_maps.size() > 64) p->io_maps.clear();
+          CUtensorMap m;
+          if (int rc = make_io_map(p, ptr, a.B, &m)) return rc;
+          it = p->io_maps.emplace(key, m).first;
+        }
+        (which ? m_out : m_res) = it->second;
+      }
+      if (!a.res) m_res = m_out;
+    }
+    dim3 grid((unsigned)(wp.tiles_x * wp.tiles_y * a.B), (unsigned)p->n_tiles);
+    static unsigned long long* d_ts4 = nullptr;
+    const size_t n_cta = (size_t)grid.x * grid.y;
+    if (getenv("EGN_TC_TS") && n_cta <= 8192) {
+      if (!d_ts4) cudaMalloc(&d_ts4, 8192 * 8 * sizeof(unsigned long long));
+      cudaMemsetAsync(d_ts4, 0, 8192 * 8 * sizeof(unsigned long long), st);
+      wp.ts = d_ts4;
+    }
+    if (p->sw == 128)
+      EGN_CUDA_CHECK(launch_pdl(conv_tapwin_kernel<128>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, wp));
+    else
+      EGN_CUDA_CHECK(launch_pdl(conv_tapwin_kernel<64>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, wp));
+    EGN_LAUNCH_CHECK("conv_tapwin_kernel");
+    if (wp.ts && getenv("EGN_TC_TS_DUMP")) {
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> h(n_cta * 8);
+      cudaMemcpy(h.data(), d_ts4, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull, t1 = 0;
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (size_t c = 0; c < n_cta; ++c) {
+        t0 = std::min(t0, h[c * 8]);
+        t1 = std::max(t1, h[c * 8 + 6]);
+        for (int i = 1; i < 7; ++i) acc[i] += (double)(h[c * 8 + i] - h[c * 8]);
+      }
+      fprintf(stderr, "[egn-ts4] ctas=%zu span=%.2fus | avg since CTA start (us): init %.2f, first operands %.2f, mma-issued %.2f, acc-ready %.2f, epi-done %.2f, dealloc %.2f\n",
+              n_cta, (t1 - t0) * 1e-3, acc[1] / n_cta * 1e-3, acc[2] / n_cta * 1e-3, acc[3] / n_cta * 1e-3, acc[4] / n_cta * 1e-3,
+              acc[5] / n_cta * 1e-3, acc[6] / n_cta * 1e-3);
+      // the first CTAs in launch order, relative to the kernel's first stamp
+      for (size_t c = 0; c < 4 && c < n_cta; ++c)
+        fprintf(stderr, "[egn-ts4] cta %zu: start %.2f init %.2f first-operands %.2f mma-issued %.2f acc-ready %.2f epi-done %.2f dealloc %.2f (us)\n", c,
+                (h[c * 8] - t0) * 1e-3, (h[c * 8 + 1] - t0) * 1e-3, (h[c * 8 + 2] - t0) * 1e-3, (h[c * 8 + 3] - t0) * 1e-3,
+                (h[c * 8 + 4] - t0) * 1e-3, (h[c * 8 + 5] - t0) * 1e-3, (h[c * 8 + 6] - t0) * 1e-3);
     }
     return EGN_OK;
   }

@@ -17,7 +17,7 @@ def run_child(args):
     from egonet_b200 import _native as N
     B = args.batch
     out_rows = []
-    for (Cin, Cout, H, W, k, st, has_res) in SHAPES[:args.shapes]:
+    for (Cin, Cout, H, W, k, st, has_res) in SHAPES[args.first:args.shapes]:
         g = torch.Generator().manual_seed(1)
         Cip, Cop = (Cin + 15) // 16 * 16, (Cout + 15) // 16 * 16
         mul = 2 if args.dtype == 2 else 1          # fp16x2: [hi | lo] planes (random lo planes are fine for timing)
@@ -46,6 +46,7 @@ def main():
     ap.add_argument('--dtype', type=int, default=1, help='1 = fp16, 2 = fp16x2 split storage')
     ap.add_argument('--variants', default='', help='extra variants: name:ENV=V,ENV=V;name2:...')
     ap.add_argument('--shapes', type=int, default=len(SHAPES), help='only the first N shapes')
+    ap.add_argument('--first', type=int, default=0, help='skip the first N shapes')
     args = ap.parse_args()
     if args.child:
         return run_child(args)
@@ -58,12 +59,12 @@ def main():
     for label, env in variants:
         e = dict(os.environ, EGN_TC_VERBOSE='1', **env)
         r = subprocess.run([sys.executable, __file__, '--child', '--batch', str(args.batch), '--iters', str(args.iters),
-                            '--dtype', str(args.dtype), '--shapes', str(args.shapes)],
+                            '--dtype', str(args.dtype), '--shapes', str(args.shapes), '--first', str(args.first)],
                            capture_output=True, text=True, env=e)
         cfg = {}
         for l in r.stderr.splitlines():
             if l.startswith('[egn] conv '):
-                key = l[11:].split(':')[0]
+                key = l[11:].split(':')[0].replace(' fp16x2', '')
                 cfg[key] = l.split(': ', 1)[1]
         rows = [json.loads(l[7:]) for l in r.stdout.splitlines() if l.startswith('RESULT ')]
         if not rows:

@@ -7,6 +7,7 @@ import argparse, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ap = argparse.ArgumentParser()
 ap.add_argument('--shapes', type=int, default=1)
+ap.add_argument('--first', type=int, default=0)
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--dbg', default='0,64,8,72,1,3')
 ap.add_argument('--env', default='')
@@ -18,7 +19,7 @@ for dbg in [int(x) for x in a.dbg.split(',')]:
         if ts:
             e.update(EGN_TC_TS='1', EGN_TC_TS_DUMP='1')
         r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'layer_bench.py'), '--child', '--batch', str(a.batch),
-                            '--iters', '1' if ts else '20', '--dtype', '2', '--shapes', str(a.shapes)],
+                            '--iters', '1' if ts else '20', '--dtype', '2', '--shapes', str(a.shapes), '--first', str(a.first)],
                            capture_output=True, text=True, env=e)
         print('=== dbg', dbg, 'timeline' if ts else 'timing')
         if ts:
