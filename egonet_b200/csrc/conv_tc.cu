@@ -229,6 +229,31 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Two consecutive MMAs that read the SAME A tile (x_hi against w_hi, then against w_lo): the first keeps the tile
+// in the tensor core's A collector (SASS .A_KEEP), the second takes it from there (.A_REUSE) instead of reading
+// shared memory again -- an N = 192 MMA is close to the shared-memory read limit (A 4 KB + B 6 KB per 96 cycles).
+__device__ __forceinline__ void umma_f16_keep_a(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_reuse_a(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -848,11 +873,16 @@ struct TcParams {
   // one x_lo x w_hi -> L; wider tiles: x_hi x w_hi -> H, x_hi x w_lo -> L, x_lo x w_hi -> L.  H (hi*hi) lives in
   // TMEM columns [0, n_tile), L (cross terms) in [n_tile, 2 n_tile); the epilogue adds them.
   int split, cin_a, nh;
+  int keep_a;    // 3-MMA form: the second x_hi MMA takes the A tile from the collector (umma_f16_keep_a)
+  // staged TMA epilogue over the dead stage ring (TapWinParams::staged): staging box = the output tile TW x TH x TB
+  int staged, cb, nblk_plane;
+  uint32_t blk_bytes;
 };
 
 template <int SW>
 __global__ void __launch_bounds__(kTcThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (swizzle atoms are address based)
@@ -865,7 +895,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_full = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);       // [n_tile]; offset 18 * 8 + 8 = 152 ... +8 below: 16-byte aligned
+  s_bias += 2;                                                   // 160
 
   // warp index broadcast through a shuffle so the compiler can prove the role branches warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -878,16 +911,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tb_i = tile / p.tiles_h;
   const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH, b0 = tb_i * p.TB;
   const int n0 = blockIdx.y * p.n_tile;
+  if (p.staged)
+    for (int i = threadIdx.x; i < p.n_tile; i += (int)blockDim.x) s_bias[i] = __ldg(p.bias + n0 + i);
 
   if (threadIdx.x == 0) {
     pdl_trigger();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.staged) {
+      tma_prefetch_desc(&map_res);
+      tma_prefetch_desc(&map_out);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -939,6 +979,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
+    if (p.staged && p.res) {
+      // every MMA has completed: the stage ring is dead, the residual tile lands on top of it
+      mbar_wait(tmem_full_bar, 0);
+      if (elect_one()) {
+        const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
+        mbar_expect_tx(res_full, (uint32_t)nblk * (uint32_t)(p.TW * p.TH * p.TB * p.cb * 2));
+        for (int k = 0; k < nblk; ++k) {
+          const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
+          tma_load_4d(smem + (size_t)k * p.blk_bytes, &map_res, res_full, ch, ow0, oh0, b0);
+        }
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
@@ -972,8 +1024,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc_w, acc);                               // [H | L] += x_hi [w_hi | w_lo]
               umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
             } else {
-              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                                 // H += x_hi w_hi
-              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);         // L += x_hi w_lo
+              if (p.keep_a) {
+                umma_f16_keep_a(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                        // H += x_hi w_hi
+                umma_f16_reuse_a(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);   // L += x_hi w_lo
+              } else {
+                umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                               // H += x_hi w_hi
+                umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);       // L += x_hi w_lo
+              }
               umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
             }
           }
@@ -1000,10 +1057,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     er.ow = ow0 + tw;
     er.valid = row < p.TW * p.TH * p.TB && er.b < p.B && er.oh < p.OH && er.ow < p.OW;
     er.pix = ((size_t)er.b * p.OH + er.oh) * p.OW + er.ow;
-    EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr,
-              p.split, (uint32_t)p.n_tile, 0u};
-    epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
-            [&](int) { return er; });
+    if (p.staged) {
+      const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
+      const EpiStage es{smem_u32(smem), smem_u32(s_bias), p.blk_bytes, p.cb, p.res != nullptr, p.relu, 0,
+                        p.split ? (uint32_t)p.nblk_plane * p.blk_bytes : 0u};
+      mbar_wait(tmem_full_bar, 0);
+      if (p.res) mbar_wait(res_full, 0);
+      tc_fence_after();
+      epi_window_staged<1>(es, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, 0, [&](int) {
+        StageRow sr;
+        sr.valid = row < p.TW * p.TH * p.TB;       // pixels past the image / batch are clipped by the TMA store
+        sr.srow = (uint32_t)row;                   // the staging box is the tile, row-major [TB][TH][TW]
+        return sr;
+      }, p.split ? 2 : 1, p.split);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+      if (warp == 2 && elect_one()) {
+        for (int k = 0; k < nblk; ++k) {
+          const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
+          tma_store_4d(&map_out, smem + (size_t)k * p.blk_bytes, ch, ow0, oh0, b0);
+        }
+        bulk_commit();
+        bulk_wait0();
+      }
+    } else {
+      EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.OH, p.OW, 0, nullptr,
+                p.split, (uint32_t)p.n_tile, 0u};
+      epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
+              [&](int) { return er; });
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1054,6 +1136,7 @@ struct TapWinParams {
   // 12-13 us per 128 x 96 / 192-channel fp16x2 tile -- as long as the MMA phase.
   int staged, cb, nblk_plane;
   uint32_t blk_bytes;
+  int keep_a;    // 3-MMA form: the second x_hi MMA takes the A tile from the collector (umma_f16_keep_a)
 };
 
 template <int SW>
@@ -1194,8 +1277,13 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc_w, acc);                               // [H | L] += x_hi [w_hi | w_lo]
               umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
             } else {
-              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                                 // H += x_hi w_hi
-              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);         // L += x_hi w_lo
+              if (p.keep_a) {
+                umma_f16_keep_a(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                        // H += x_hi w_hi
+                umma_f16_reuse_a(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);   // L += x_hi w_lo
+              } else {
+                umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                               // H += x_hi w_hi
+                umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);       // L += x_hi w_lo
+              }
               umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
             }
           }
@@ -2203,7 +2291,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   size_t st_count = std::min<size_t>((size_t)kMaxStages, budget / stage);
   st_count = std::min<size_t>(st_count, (size_t)std::max(2, n_iters));
   p->stages = (int)std::max<size_t>(2, st_count);
-  p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+  p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 2) * sizeof(uint64_t) + 32 + 4 * (size_t)p->n_tile;
   // ---- v2 window-run configuration (stride-1 convs) ----
   {
     const char* env = getenv("EGN_TC_V2");
@@ -2280,7 +2368,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
                 p->smem_bytes / 1024, p->b_stages, p->tmem_cols);
       if (!p->use_run) {
         p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
-        p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+        p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 2) * sizeof(uint64_t) + 32 + 4 * (size_t)p->n_tile;
       }
     }
   }
@@ -2529,14 +2617,25 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       size_t st2 = std::min<size_t>((size_t)kMaxStages, budget2 / stage2);
       st2 = std::min<size_t>(st2, (size_t)std::max(2, a.ksize * a.ksize * p->kchunks));
       p->stages = (int)std::max<size_t>(2, st2);
-      p->smem_bytes = 1024 + p->stages * stage2 + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+      p->smem_bytes = 1024 + p->stages * stage2 + (2 * kMaxStages + 2) * sizeof(uint64_t) + 32 + 4 * (size_t)p->n_tile;
     } else {
-      p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 1) * sizeof(uint64_t) + 16;
+      p->smem_bytes = 1024 + p->stages * stage + (2 * kMaxStages + 2) * sizeof(uint64_t) + 32 + 4 * (size_t)p->n_tile;
     }
   }
+  if (!p->use_persist && !p->use_run && !p->use_tapwin) {
+    // staged TMA epilogue over the dead stage ring: [block][TW*TH*TB pixels][cb channels], hi blocks then lo blocks
+    const size_t a_st = 128 * (size_t)p->sw * (split ? 2 : 1);
+    const size_t b_st = ((size_t)p->n_tile * p->sw * (split ? 2 : 1) + 1023) & ~(size_t)1023;
+    p->cb = p->n_tile % 64 == 0 ? 64 : (p->n_tile % 48 == 0 ? 48 : (p->n_tile % 32 == 0 ? 32 : (p->n_tile % 16 == 0 ? 16 : 0)));
+    p->nblk = p->cb ? p->n_tile / p->cb : 0;
+    p->blk_bytes = (uint32_t)(((size_t)p->TW * p->TH * p->TB * p->cb * 2 + 1023) & ~(size_t)1023);
+    p->n_stage = (p->cb && !(getenv("EGN_TC_V1_STAGED") && atoi(getenv("EGN_TC_V1_STAGED")) == 0) &&
+                  (size_t)(split ? 2 : 1) * p->nblk * p->blk_bytes <= p->stages * (a_st + b_st)) ? 1 : 0;
+  }
   if (getenv("EGN_TC_VERBOSE") && !p->use_persist && !p->use_run && !p->use_tapwin)
-    fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v1-tap n_tile=%d stages=%d smem=%zuKB tmem=%u\n", a.ksize, a.ksize,
-            a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->stages, p->smem_bytes / 1024, p->tmem_cols);
+    fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v1-tap n_tile=%d sw=%d stages=%d smem=%zuKB tmem=%u staged=%d cb=%d\n", a.ksize, a.ksize,
+            a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->sw, p->stages, p->smem_bytes / 1024, p->tmem_cols,
+            p->n_stage, p->cb);
   // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][K] fp16, zero padded to whole kc-channel chunks.
   //   plain fp16           K = taps * cin_k, tap row = [w (Cin_p)]
   //   fp16x2, v2 / v3      K = taps * cin_k, tap row = [w_hi (Cin_p) | w_lo (Cin_p)]   (cross pairing by the issuer)
@@ -2620,8 +2719,9 @@ static int make_io_map(TcConvPlan* p, const void* ptr, int B, CUtensorMap* m) {
   const cuuint64_t C = (p->split ? 2 : 1) * p->Cout_p, W = p->OW, H = p->OH;     // fp16x2: [hi | lo] planes
   const cuuint64_t gdim[4] = {C, W, H, (cuuint64_t)B};
   const cuuint64_t gstr[3] = {C * 2, W * C * 2, H * W * C * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)p->cb, (cuuint32_t)(p->blk ? p->BW : p->OW), (cuuint32_t)(p->blk ? p->BH : p->THW),
-                             (cuuint32_t)p->TBW};
+  const bool v1 = !p->use_persist && !p->use_run && !p->use_tapwin;       // per-tap kernel: the output tile
+  const cuuint32_t box[4] = {(cuuint32_t)p->cb, (cuuint32_t)(v1 ? p->TW : (p->blk ? p->BW : p->OW)),
+                             (cuuint32_t)(v1 ? p->TH : (p->blk ? p->BH : p->THW)), (cuuint32_t)(v1 ? p->TB : p->TBW)};
   const cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, p->cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -2713,8 +2813,9 @@ static int device_setup() {
 }
 
 template <int SW>
-static int launch_sw(TcConvPlan* p, const CUtensorMap& ma, const TcParams& tp, dim3 grid, cudaStream_t st) {
-  EGN_CUDA_CHECK(launch_pdl(conv_tc_kernel<SW>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, tp));
+static int launch_sw(TcConvPlan* p, const CUtensorMap& ma, const CUtensorMap& m_res, const CUtensorMap& m_out, const TcParams& tp,
+                     dim3 grid, cudaStream_t st) {
+  EGN_CUDA_CHECK(launch_pdl(conv_tc_kernel<SW>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, tp));
   EGN_LAUNCH_CHECK("conv_tc_kernel");
   return EGN_OK;
 }
@@ -2941,6 +3042,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     wp.res = static_cast<const __half*>(a.res);
     wp.out = static_cast<__half*>(a.out);
     wp.heatmap = a.heatmap; wp.xs = a.xs; wp.ys = a.ys; wp.coord_maps = a.coord_maps;
+    wp.keep_a = (getenv("EGN_TC_KEEP_A") && atoi(getenv("EGN_TC_KEEP_A"))) ? 1 : 0;   // measured: no gain (128.6 vs 129.8 us), off
     CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
     wp.staged = (p->n_stage && !a.heatmap && !a.coord_maps) ? 1 : 0;
     if (wp.staged) {
@@ -2999,6 +3101,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   TcParams tp{};
   tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
   tp.split = p->split ? 1 : 0; tp.cin_a = p->cin_a; tp.nh = p->Cin_p / 16;
+  tp.keep_a = (getenv("EGN_TC_KEEP_A") && atoi(getenv("EGN_TC_KEEP_A"))) ? 1 : 0;
   tp.taps = p->ksize * p->ksize; tp.ksize = p->ksize; tp.stride = p->stride; tp.pad = p->pad; tp.relu = a.relu;
   tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
   tp.tiles_w = ceil_div(p->OW, p->TW);
@@ -3011,11 +3114,31 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   tp.res = static_cast<const __half*>(a.res);
   tp.out = static_cast<__half*>(a.out);
   tp.heatmap = a.heatmap; tp.xs = a.xs; tp.ys = a.ys; tp.coord_maps = a.coord_maps;
+  CUtensorMap m_res = ma, m_out = ma;          // placeholders when the epilogue is not staged
+  tp.staged = (p->n_stage && !a.heatmap && !a.coord_maps) ? 1 : 0;
+  if (tp.staged) {
+    tp.cb = p->cb; tp.nblk_plane = p->nblk; tp.blk_bytes = p->blk_bytes;
+    std::lock_guard<std::mutex> lock(p->mu);
+    for (int which = 0; which < 2; ++which) {
+      const void* ptr = which ? a.out : a.res;
+      if (!ptr) continue;
+      auto key = std::make_pair(ptr, a.B);
+      auto it = p->io_maps.find(key);
+      if (it == p->io_maps.end()) {
+        if (p->io_maps.size() > 64) p->io_maps.clear();
+        CUtensorMap m;
+        if (int rc = make_io_map(p, ptr, a.B, &m)) return rc;
+        it = p->io_maps.emplace(key, m).first;
+      }
+      (which ? m_out : m_res) = it->second;
+    }
+    if (!a.res) m_res = m_out;
+  }
   dim3 grid((unsigned)(tp.tiles_w * tp.tiles_h * ceil_div(a.B, p->TB)), (unsigned)p->n_tiles);
   switch (p->sw) {
-    case 128: return launch_sw<128>(p, ma, tp, grid, st);
-    case 64: return launch_sw<64>(p, ma, tp, grid, st);
-    default: return launch_sw<32>(p, ma, tp, grid, st);
+    case 128: return launch_sw<128>(p, ma, m_res, m_out, tp, grid, st);
+    case 64: return launch_sw<64>(p, ma, m_res, m_out, tp, grid, st);
+    default: return launch_sw<32>(p, ma, m_res, m_out, tp, grid, st);
   }
 }
 
