@@ -1137,6 +1137,11 @@ struct TapWinParams {
   int staged, cb, nblk_plane;
   uint32_t blk_bytes;
   int keep_a;    // 3-MMA form: the second x_hi MMA takes the A tile from the collector (umma_f16_keep_a)
+  // Persistent mode (tiles of <= 256 TMEM columns: two accumulator sets fit): one CTA per SM walks over tiles
+  // blockIdx.x, += gridDim.x; the rings run across tile boundaries, the MMAs of tile t+1 overlap the epilogue of tile t
+  // (acc_sets = 2) and the staging buffer is a region of its own behind the rings (stage_off != 0, stage_bytes).
+  int total_tiles, acc_sets;
+  uint32_t stage_off, stage_bytes;
 };
 
 template <int SW>
@@ -1151,23 +1156,32 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const uint32_t b_stage = ((uint32_t)p.n_tile * SW * (p.split ? 2u : 1u) + 1023u) & ~1023u;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.na * a_slot;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.nb * b_stage);
+  uint8_t* smem_stage = smem + p.stage_off;        // stage_off = 0: on top of the (then dead) rings, one tile per CTA
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.nb * b_stage + p.stage_bytes);
   uint64_t* a_empty = a_full + kTwMaxA;
   uint64_t* b_full = a_empty + kTwMaxA;
   uint64_t* b_empty = b_full + kTwMaxB;
-  uint64_t* tmem_full_bar = b_empty + kTwMaxB;
-  uint64_t* res_full = tmem_full_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [n_tile]; offset 26 * 8 + 16 = 224: 16-byte aligned
+  uint64_t* acc_full = b_empty + kTwMaxB;          // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint64_t* res_full = acc_empty + 2;
+  uint64_t* stage_free = res_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [n_tile]; offset 30 * 8 + 16 = 256: 16-byte aligned
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x;
-  tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y;
-  const int b0 = tile / p.tiles_y;
-  const int x0 = tx * 8, y0 = ty * 16;
   const int n0 = blockIdx.y * p.n_tile;
+  // tiles of this CTA: blockIdx.x, += gridDim.x (one tile per CTA unless persistent)
+  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool dedicated = p.stage_off != 0;         // staging buffer of its own (persistent mode)
+  auto tile_xyb = [&](int it, int& x0, int& y0, int& b0) {
+    int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = tile % p.tiles_x;
+    tile /= p.tiles_x;
+    x0 = tx * 8;
+    y0 = (tile % p.tiles_y) * 16;
+    b0 = tile / p.tiles_y;
+  };
+  const uint32_t set_cols = (uint32_t)((p.split ? 2 : 1) * p.n_tile);      // TMEM columns of one accumulator set
   if (threadIdx.x == 0) EGN_TS(0);
   if (p.staged)
     for (int i = threadIdx.x; i < p.n_tile; i += (int)blockDim.x) s_bias[i] = __ldg(p.bias + n0 + i);
@@ -1188,8 +1202,12 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);                 // one arrival per epilogue warp
+    }
     mbar_init(res_full, 1);
+    mbar_init(stage_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -1202,9 +1220,13 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer: A chunk windows + the weight tile of every (chunk, tap) =====================
-    auto load_a = [&](int c) {
-      const int slot = c % p.na;
-      mbar_wait(&a_empty[slot], (uint32_t)(((c / p.na) & 1) ^ 1));
+    // q numbers the (tile, chunk) pairs of this CTA: the A ring runs across tile boundaries
+    const int Q = my_tiles * p.kchunks;
+    auto load_a = [&](int q) {
+      const int slot = q % p.na, c = q % p.kchunks;
+      int x0, y0, b0;
+      tile_xyb(q / p.kchunks, x0, y0, b0);
+      mbar_wait(&a_empty[slot], (uint32_t)(((q / p.na) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* sa = smem_a + (size_t)slot * a_slot;
         mbar_expect_tx(&a_full[slot], (p.split ? 2u : 1u) * p.a_bytes);
@@ -1212,11 +1234,16 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (p.split) tma_load_4d(sa + a_plane, &map_a, &a_full[slot], p.Cin_p + c * p.kc, x0 - 1, y0 - 1, b0);
       }
     };
-    load_a(0);
+    // na - 1 chunk windows in flight ahead of the one being multiplied.  The refill is issued at tap 3: the slot was
+    // released by the previous chunk's last MMAs, whose commit has certainly arrived by then -- waiting for it at
+    // tap 0 / 1 blocks this warp and starves the weight ring (96ch@32x32, persistent: 139 -> 132 us).
+    const int D = p.na > 1 ? p.na - 1 : 1;
+    for (int q = 0; q < D && q < Q; ++q) load_a(q);
     uint32_t stage = 0, phase = 0;
-    for (int c = 0; c < p.kchunks; ++c) {
+    for (int q = 0; q < Q; ++q) {
+      const int c = q % p.kchunks;
       for (int tap = 0; tap < 9; ++tap) {
-        if (tap == 1 && c + 1 < p.kchunks) load_a(c + 1);      // next chunk's window, ~8 weight tiles ahead of its use
+        if (tap == (p.na > 1 ? 3 : 8) && q + D < Q) load_a(q + D);
         mbar_wait(&b_empty[stage], phase ^ 1u);
         if (elect_one()) {
           uint8_t* sb = smem_b + (size_t)stage * b_stage;
@@ -1229,16 +1256,24 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           phase ^= 1u;
         }
       }
-    }
-    if (p.staged && p.res) {
-      // every MMA has completed (tmem_full_bar): the rings are dead, the residual block lands on top of them
-      mbar_wait(tmem_full_bar, 0);
-      if (elect_one()) {
-        const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
-        mbar_expect_tx(res_full, (uint32_t)nblk * (uint32_t)(128 * p.cb * 2));
-        for (int k = 0; k < nblk; ++k) {
-          const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
-          tma_load_4d(smem + (size_t)k * p.blk_bytes, &map_res, res_full, ch, x0, y0, b0);
+      if (c == p.kchunks - 1 && p.staged && p.res) {
+        // residual block of this tile: into the staging buffer once it is free -- its own buffer: the previous tile's
+        // stores have been read out; on top of the rings: every MMA of the (only) tile has completed
+        const int it = q / p.kchunks;
+        if (dedicated) {
+          if (it > 0) mbar_wait(stage_free, (uint32_t)((it - 1) & 1));
+        } else {
+          mbar_wait(&acc_full[0], 0);
+        }
+        if (elect_one()) {
+          int x0, y0, b0;
+          tile_xyb(it, x0, y0, b0);
+          const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
+          mbar_expect_tx(res_full, (uint32_t)nblk * (uint32_t)(128 * p.cb * 2));
+          for (int k = 0; k < nblk; ++k) {
+            const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
+            tma_load_4d(smem_stage + (size_t)k * p.blk_bytes, &map_res, res_full, ch, x0, y0, b0);
+          }
         }
       }
     }
@@ -1252,93 +1287,117 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint64_t desc_hi_a = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(((uint32_t)kTwWp * SW) >> 4) << 32);
     const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
     uint32_t stage = 0, phase = 0;
-    for (int c = 0; c < p.kchunks; ++c) {
-      const int slot = c % p.na;
-      mbar_wait(&a_full[slot], (uint32_t)((c / p.na) & 1));
+    int q = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int set = p.acc_sets == 2 ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(p.acc_sets == 2 ? it >> 1 : it);
+      mbar_wait(&acc_empty[set], (use & 1u) ^ 1u);         // the epilogue has drained this accumulator set
       tc_fence_after();
-      for (int tap = 0; tap < 9; ++tap) {
-        mbar_wait(&b_full[stage], phase);
+      const uint32_t d_h = tmem_base + (uint32_t)set * set_cols, d_l = d_h + (uint32_t)p.n_tile;
+      for (int c = 0; c < p.kchunks; ++c, ++q) {
+        const int slot = q % p.na;
+        mbar_wait(&a_full[slot], (uint32_t)((q / p.na) & 1));
         tc_fence_after();
-        if (c == 0 && tap == 0 && lane == 0) EGN_TS(2);
-        const int r = tap / 3, q = tap - 3 * r;
-        const uint64_t adesc = desc_hi_a | (uint64_t)(((a_addr0 + (uint32_t)slot * a_slot + (uint32_t)(r * kTwWp + q) * SW) & 0x3FFFFu) >> 4);
-        const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
-        if (elect_one()) {
-          const uint64_t adesc_lo = adesc + (uint64_t)(a_plane >> 4);
-          const uint64_t bdesc_lo = bdesc + (uint64_t)(p.b_bytes >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[stage], phase);
+          tc_fence_after();
+          if (it == 0 && c == 0 && tap == 0 && lane == 0) EGN_TS(2);
+          const int r = tap / 3, qq = tap - 3 * r;
+          const uint64_t adesc = desc_hi_a | (uint64_t)(((a_addr0 + (uint32_t)slot * a_slot + (uint32_t)(r * kTwWp + qq) * SW) & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = desc_hi | (uint64_t)(((b_addr0 + stage * b_stage) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
+            const uint64_t adesc_lo = adesc + (uint64_t)(a_plane >> 4);
+            const uint64_t bdesc_lo = bdesc + (uint64_t)(p.b_bytes >> 4);
 #pragma unroll
-          for (int k = 0; k < SW / 32; ++k) {
-            if (c * (SW / 32) + k >= p.nh) continue;               // padding slice of the last chunk
-            const uint32_t acc = (c | tap | k) ? 1u : 0u;          // the very first MMA initialises the accumulators
-            const uint64_t ko = (uint64_t)(2 * k);
-            if (!p.split) {
-              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);
-            } else if (wide) {
-              umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc_w, acc);                               // [H | L] += x_hi [w_hi | w_lo]
-              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
-            } else {
-              if (p.keep_a) {
-                umma_f16_keep_a(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                        // H += x_hi w_hi
-                umma_f16_reuse_a(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);   // L += x_hi w_lo
+            for (int k = 0; k < SW / 32; ++k) {
+              if (c * (SW / 32) + k >= p.nh) continue;               // padding slice of the last chunk
+              const uint32_t acc = (c | tap | k) ? 1u : 0u;          // the first MMA of a tile initialises the accumulators
+              const uint64_t ko = (uint64_t)(2 * k);
+              if (!p.split) {
+                umma_f16(d_h, adesc + ko, bdesc + ko, idesc, acc);
+              } else if (wide) {
+                umma_f16(d_h, adesc + ko, bdesc + ko, idesc_w, acc);                   // [H | L] += x_hi [w_hi | w_lo]
+                umma_f16(d_l, adesc_lo + ko, bdesc + ko, idesc, 1u);                   // L += x_lo w_hi
               } else {
-                umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, acc);                               // H += x_hi w_hi
-                umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + ko, bdesc_lo + ko, idesc, acc);       // L += x_hi w_lo
+                if (p.keep_a) {
+                  umma_f16_keep_a(d_h, adesc + ko, bdesc + ko, idesc, acc);            // H += x_hi w_hi
+                  umma_f16_reuse_a(d_l, adesc + ko, bdesc_lo + ko, idesc, acc);        // L += x_hi w_lo
+                } else {
+                  umma_f16(d_h, adesc + ko, bdesc + ko, idesc, acc);                   // H += x_hi w_hi
+                  umma_f16(d_l, adesc + ko, bdesc_lo + ko, idesc, acc);                // L += x_hi w_lo
+                }
+                umma_f16(d_l, adesc_lo + ko, bdesc + ko, idesc, 1u);                   // L += x_lo w_hi
               }
-              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + ko, bdesc + ko, idesc, 1u);          // L += x_lo w_hi
             }
+            umma_commit(&b_empty[stage]);
+            if (tap == 8) umma_commit(&a_empty[slot]);
           }
-          umma_commit(&b_empty[stage]);
-          if (tap == 8) umma_commit(&a_empty[slot]);
-        }
-        if (++stage == (uint32_t)p.nb) {
-          stage = 0;
-          phase ^= 1u;
+          if (++stage == (uint32_t)p.nb) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
+      if (elect_one()) umma_commit(&acc_full[set]);
+      if (it == 0 && lane == 0) EGN_TS(3);
     }
-    if (elect_one()) umma_commit(tmem_full_bar);
-    if (lane == 0) EGN_TS(3);
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;     // accumulator row -> pixel (row & 7, row >> 3) of the block
-    EpiRow er;
-    er.b = b0;
-    er.oh = y0 + (row >> 3);
-    er.ow = x0 + (row & 7);
-    er.valid = er.b < p.B && er.oh < p.H && er.ow < p.W;
-    er.pix = ((size_t)er.b * p.H + er.oh) * p.W + er.ow;
-    if (p.staged) {
-      const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
-      const EpiStage es{smem_u32(smem), smem_u32(s_bias), p.blk_bytes, p.cb, p.res != nullptr, p.relu, 0,
-                        p.split ? (uint32_t)p.nblk_plane * p.blk_bytes : 0u};
-      mbar_wait(tmem_full_bar, 0);
-      if (p.res) mbar_wait(res_full, 0);
-      tc_fence_after();
-      if ((threadIdx.x & 127) == 64) EGN_TS(4);
-      epi_window_staged<1>(es, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, 0, [&](int) {
-        StageRow sr;
-        sr.valid = true;                     // pixels past the image are clipped by the TMA store
-        sr.srow = (uint32_t)row;             // staging row = (row >> 3) * 8 + (row & 7): the block is row-major
-        return sr;
-      }, p.split ? 2 : 1, p.split);
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
-      if (warp == 2 && elect_one()) {
-        for (int k = 0; k < nblk; ++k) {
-          const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
-          tma_store_4d(&map_out, smem + (size_t)k * p.blk_bytes, ch, x0, y0, b0);
+    const int nblk = (p.split ? 2 : 1) * p.nblk_plane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int set = p.acc_sets == 2 ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(p.acc_sets == 2 ? it >> 1 : it);
+      int x0, y0, b0;
+      tile_xyb(it, x0, y0, b0);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * set_cols;
+      if (p.staged) {
+        const EpiStage es{smem_u32(smem_stage), smem_u32(s_bias), p.blk_bytes, p.cb, p.res != nullptr, p.relu, 0,
+                          p.split ? (uint32_t)p.nblk_plane * p.blk_bytes : 0u};
+        if (p.res) mbar_wait(res_full, (uint32_t)(it & 1));
+        else if (dedicated && it > 0) mbar_wait(stage_free, (uint32_t)((it - 1) & 1));      // previous stores read out
+        mbar_wait(&acc_full[set], use & 1u);
+        tc_fence_after();
+        if (it == 0 && (threadIdx.x & 127) == 64) EGN_TS(4);
+        epi_window_staged<1>(es, tbase, 1, p.n_tile, 0, [&](int) {
+          StageRow sr;
+          sr.valid = true;                     // pixels past the image are clipped by the TMA store
+          sr.srow = (uint32_t)row;             // staging row = (row >> 3) * 8 + (row & 7): the block is row-major
+          return sr;
+        }, p.split ? 2 : 1, p.split);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[set]);          // accumulator set may be overwritten
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
+        if (warp == 2 && elect_one()) {
+          for (int k = 0; k < nblk; ++k) {
+            const int ch = k < p.nblk_plane ? n0 + k * p.cb : p.Cout_p + n0 + (k - p.nblk_plane) * p.cb;
+            tma_store_4d(&map_out, smem_stage + (size_t)k * p.blk_bytes, ch, x0, y0, b0);
+          }
+          bulk_commit();
+          bulk_wait_read0();                                  // the buffer has been read: it may be refilled
+          if (dedicated) mbar_arrive(stage_free);
         }
-        bulk_commit();
-        bulk_wait0();                          // shared memory is released (and the writes complete) before the CTA exits
+      } else {
+        EpiRow er;
+        er.b = b0;
+        er.oh = y0 + (row >> 3);
+        er.ow = x0 + (row & 7);
+        er.valid = er.b < p.B && er.oh < p.H && er.ow < p.W;
+        er.pix = ((size_t)er.b * p.H + er.oh) * p.W + er.ow;
+        EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, 0,
+                  (p.ts && it == 0) ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, p.split, (uint32_t)p.n_tile,
+                  0u};
+        epi_run(e, tbase, 1, p.n_tile, n0, &acc_full[set], [&](int) { return er; }, use & 1u);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[set]);
       }
-    } else {
-      EpiArgs e{p.bias, p.res, p.out, p.heatmap, p.xs, p.ys, p.coord_maps, p.relu, p.Cout, p.Cout_p, p.H, p.W, 0,
-                p.ts ? p.ts + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr, p.split, (uint32_t)p.n_tile, 0u};
-      epi_run(e, tmem_base + ((uint32_t)(quarter * 32) << 16), 1, p.n_tile, n0, tmem_full_bar,
-              [&](int) { return er; });
+      if (it == 0 && (threadIdx.x & 127) == 64) EGN_TS(5);
     }
-    if ((threadIdx.x & 127) == 64) EGN_TS(5);
+    if (p.staged && warp == 2 && elect_one()) bulk_wait0();   // all output writes complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -2203,6 +2262,8 @@ struct TcConvPlan {
   bool use_persist = false;   // v3: persistent one-CTA-per-SM variant of the window-run kernel
   bool use_tapwin = false;    // v4: tap-window kernel (conv_tapwin_kernel)
   int tw_na = 2, tw_nb = 4;   // its A ring slots / B ring stages
+  bool tw_persist = false;    // persistent mode: two accumulator sets, staging buffer of its own (TapWinParams)
+  uint32_t tw_stage_off = 0, tw_stage_bytes = 0;
   bool use_pair = false;      // v3 with CTA pairs (cta_group::2) instead of an N split over blockIdx.y
   size_t pair_smem = 0;       // dynamic smem per CTA in pair mode
   bool pack_tail = false;     // weight matrix stored with the 32-channel tail chunks of two taps per tile (see PersistParams)
@@ -2579,26 +2640,34 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         const size_t a_slot = (split ? 2 : 1) * a_plane;
         const size_t b_stage4 = ((size_t)p->n_tile * p->sw * (split ? 2 : 1) + 1023) & ~(size_t)1023;
         const bool two = p->tmem_cols <= 256;
-        const size_t budget4 = getenv("EGN_TC_V4_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V4_BUDGET_KB")) * 1024
-                                                             : (two ? 106 * 1024 : 212 * 1024);
-        p->tw_na = getenv("EGN_TC_V4_NA") ? atoi(getenv("EGN_TC_V4_NA")) : 2;
-        p->tw_na = std::max(1, std::min(std::min(p->tw_na, kTwMaxA), std::max(1, p->kchunks)));
-        const size_t fixed4 = 1024 + (2 * kTwMaxA + 2 * kTwMaxB + 2) * sizeof(uint64_t) + 32 + (size_t)p->n_tile * 4;
-        long nb = ((long)budget4 - (long)fixed4 - (long)(p->tw_na * a_slot)) / (long)b_stage4;
-        p->tw_nb = (int)std::max<long>(2, std::min<long>(nb, kTwMaxB));
-        p->smem_bytes = fixed4 + p->tw_na * a_slot + p->tw_nb * b_stage4;
-        if (p->smem_bytes > 227 * 1024) p->use_tapwin = false;
-        // staged epilogue on top of the dead rings: [block][128 pixels][cb channels], hi blocks then lo blocks
+        // staged epilogue: [block][128 pixels][cb channels], hi blocks then lo blocks
         p->cb = p->n_tile % 64 == 0 ? 64 : (p->n_tile % 48 == 0 ? 48 : (p->n_tile % 32 == 0 ? 32 : 0));
         p->nblk = p->cb ? p->n_tile / p->cb : 0;
         p->blk_bytes = (uint32_t)(128 * p->cb * 2);
-        p->n_stage = (p->cb && !(getenv("EGN_TC_V4_STAGED") && atoi(getenv("EGN_TC_V4_STAGED")) == 0) &&
-                      (size_t)(split ? 2 : 1) * p->nblk * p->blk_bytes <= p->tw_na * a_slot + p->tw_nb * b_stage4) ? 1 : 0;
+        const size_t stage_bytes = (size_t)(split ? 2 : 1) * p->nblk * p->blk_bytes;
+        const bool want_staged = p->cb && !(getenv("EGN_TC_V4_STAGED") && atoi(getenv("EGN_TC_V4_STAGED")) == 0);
+        // persistent mode: two accumulator sets (<= 256 columns each) and the staging buffer behind the rings
+        p->tw_persist = two && want_staged && !(getenv("EGN_TC_V4_PERSIST") && atoi(getenv("EGN_TC_V4_PERSIST")) == 0);
+        const size_t fixed4 = 1024 + (2 * kTwMaxA + 2 * kTwMaxB + 6) * sizeof(uint64_t) + 32 + (size_t)p->n_tile * 4;
+        const size_t budget4 = getenv("EGN_TC_V4_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V4_BUDGET_KB")) * 1024
+                                                             : (p->tw_persist ? 225 * 1024 - stage_bytes : (two ? 106 * 1024 : 212 * 1024));
+        p->tw_na = getenv("EGN_TC_V4_NA") ? atoi(getenv("EGN_TC_V4_NA")) : 2;      // (3 measured equal once the refill moved to tap 3)
+        p->tw_na = std::max(1, std::min(std::min(p->tw_na, kTwMaxA), std::max(1, p->kchunks)));
+        long nb = ((long)budget4 - (long)fixed4 - (long)(p->tw_na * a_slot)) / (long)b_stage4;
+        if (getenv("EGN_TC_V4_NB")) nb = std::min<long>(nb, atoi(getenv("EGN_TC_V4_NB")));
+        p->tw_nb = (int)std::max<long>(2, std::min<long>(nb, kTwMaxB));
+        const size_t rings = p->tw_na * a_slot + p->tw_nb * b_stage4;
+        p->tw_stage_off = p->tw_persist ? (uint32_t)rings : 0u;
+        p->tw_stage_bytes = p->tw_persist ? (uint32_t)stage_bytes : 0u;
+        p->smem_bytes = fixed4 + rings + p->tw_stage_bytes;
+        if (p->smem_bytes > 227 * 1024) p->use_tapwin = false;
+        p->n_stage = (want_staged && (p->tw_persist || stage_bytes <= rings)) ? 1 : 0;
+        if (p->tw_persist) p->tmem_cols = pow2_cols(2 * (split ? 2 : 1) * p->n_tile);
         p->blk = 1; p->BW = 8; p->BH = 16; p->TBW = 1;          // staging box of make_io_map
         if (getenv("EGN_TC_VERBOSE") && p->use_tapwin)
-          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d\n",
+          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d persist=%d\n",
                   a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->sw, p->kchunks,
-                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb);
+                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb, p->tw_persist ? 1 : 0);
       }
     }
     if (p->use_tapwin) {
@@ -3063,7 +3132,13 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       }
       if (!a.res) m_res = m_out;
     }
-    dim3 grid((unsigned)(wp.tiles_x * wp.tiles_y * a.B), (unsigned)p->n_tiles);
+    wp.total_tiles = wp.tiles_x * wp.tiles_y * a.B;
+    const bool persist4 = p->tw_persist && wp.staged;
+    wp.acc_sets = persist4 ? 2 : 1;
+    wp.stage_off = persist4 ? p->tw_stage_off : 0u;
+    wp.stage_bytes = p->tw_stage_bytes;            // (the barrier block sits behind the region either way)
+    if (p->tw_persist && !persist4) wp.tmem_cols = p->tmem_cols;      // head extras: one tile per CTA, direct epilogue
+    dim3 grid((unsigned)(persist4 ? std::min(wp.total_tiles, num_sms) : wp.total_tiles), (unsigned)p->n_tiles);
     static unsigned long long* d_ts4 = nullptr;
     const size_t n_cta = (size_t)grid.x * grid.y;
     if (getenv("EGN_TC_TS") && n_cta <= 8192) {
