@@ -877,6 +877,7 @@ struct TcParams {
   // staged TMA epilogue over the dead stage ring (TapWinParams::staged): staging box = the output tile TW x TH x TB
   int staged, cb, nblk_plane;
   uint32_t blk_bytes;
+  int grouped;   // fp16x2: issue the MMAs of a stage grouped by accumulator
 };
 
 template <int SW>
@@ -1015,6 +1016,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else {
           const uint64_t adesc_lo = adesc + (uint64_t)(a_plane >> 4);
           const uint64_t bdesc_lo = bdesc + (uint64_t)(p.b_bytes >> 4);
+          if (p.grouped) {
+            // same-accumulator runs (see conv_tapwin_kernel)
+#pragma unroll
+            for (int k = 0; k < SW / 32; ++k) {
+              if (kcx * (SW / 32) + k >= p.nh) continue;
+              umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), wide ? idesc_w : idesc, (it | k) ? 1u : 0u);
+            }
+            if (!wide) {
+#pragma unroll
+              for (int k = 0; k < SW / 32; ++k) {
+                if (kcx * (SW / 32) + k >= p.nh) continue;
+                umma_f16(tmem_base + (uint32_t)p.n_tile, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < SW / 32; ++k) {
+              if (kcx * (SW / 32) + k >= p.nh) continue;
+              umma_f16(tmem_base + (uint32_t)p.n_tile, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < SW / 32; ++k) {
             if (kcx * (SW / 32) + k >= p.nh) continue;             // padding slice of the last chunk
@@ -1142,6 +1163,7 @@ struct TapWinParams {
   // (acc_sets = 2) and the staging buffer is a region of its own behind the rings (stage_off != 0, stage_bytes).
   int total_tiles, acc_sets;
   uint32_t stage_off, stage_bytes;
+  int grouped;   // fp16x2: issue the MMAs of a stage grouped by accumulator (all [H | L], then all L)
 };
 
 template <int SW>
@@ -1308,6 +1330,27 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (elect_one()) {
             const uint64_t adesc_lo = adesc + (uint64_t)(a_plane >> 4);
             const uint64_t bdesc_lo = bdesc + (uint64_t)(p.b_bytes >> 4);
+            if (p.split && p.grouped) {
+              // same-accumulator runs: alternating the destination between consecutive MMAs costs ~21 cycles per
+              // switch (profiles/r01k_umma_rate.log: N = 192 96 -> 118 cycles with two accumulators)
+#pragma unroll
+              for (int k = 0; k < SW / 32; ++k) {
+                if (c * (SW / 32) + k >= p.nh) continue;
+                umma_f16(d_h, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), wide ? idesc_w : idesc, (c | tap | k) ? 1u : 0u);
+              }
+              if (!wide) {
+#pragma unroll
+                for (int k = 0; k < SW / 32; ++k) {
+                  if (c * (SW / 32) + k >= p.nh) continue;
+                  umma_f16(d_l, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < SW / 32; ++k) {
+                if (c * (SW / 32) + k >= p.nh) continue;
+                umma_f16(d_l, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              }
+            } else
 #pragma unroll
             for (int k = 0; k < SW / 32; ++k) {
               if (c * (SW / 32) + k >= p.nh) continue;               // padding slice of the last chunk
@@ -1683,6 +1726,7 @@ struct PersistParams {
   // Chunk c of the next window reloads while the other phases run: the single slot behaves like a ring of chunks.
   // phase_end[c] = issue-table index one past phase c.
   int chunk_phase, phase_end[4];
+  int grouped;          // fp16x2: inside a phase, issue all full-width MMAs first, then all half-width ones
   // Block-shaped windows (3x3 convs): a window is BW x BH output pixels (BW = 8 * TX, BH = 16 * TY) plus the halo,
   // loaded as ONE TMA box of r.Wp = BW + 2 columns x r.Hw = BH + 2 rows.  An M tile is 8 columns x 16 rows: its 16
   // 8-row operand groups are one WINDOW ROW (r.Wp pixels) apart, which a K-major UMMA descriptor expresses directly
@@ -1757,17 +1801,31 @@ conv_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int i = threadIdx.x; i < n_mma; i += (int)blockDim.x) {
       int t = i % p.T, kk = i / p.T;
       int tap = kk / groups, g = kk - tap * groups;
-      if (pp.chunk_phase) {
-        // issue position -> (phase = chunk, tap, rank inside the phase) -> group g
+      if (pp.chunk_phase || (pp.split && pp.grouped)) {
+        // issue position -> (phase = chunk, [accumulator run], tap, rank inside the phase) -> group g.  Without chunk
+        // phasing the whole window is one phase.  Grouped (fp16x2): inside a phase all full-width MMAs ([H | L]) come
+        // first, then all half-width ones (L) -- alternating the destination costs ~21 cycles per switch.
         int ph = 0;
-        while (i >= pp.phase_end[ph]) ++ph;
-        const int base = ph ? pp.phase_end[ph - 1] : 0;
-        const int per = (pp.phase_end[ph] - base) / (p.taps * p.T);       // groups of a tap in this phase
-        const int kq = (i - base) / p.T;
-        tap = kq / per;
-        int rank = kq - tap * per;
+        if (pp.chunk_phase)
+          while (i >= pp.phase_end[ph]) ++ph;
+        const int base = (pp.chunk_phase && ph) ? pp.phase_end[ph - 1] : 0;
+        auto in_phase = [&](int gg) { return !pp.chunk_phase || slice_of(gg) / spc == ph; };
+        int per[2] = {0, 0};                              // groups of a tap in this phase: full-width, half-width
+        for (int gg = 0; gg < groups; ++gg)
+          if (in_phase(gg)) ++per[pp.split ? (gg & 1) : 0];
+        int j = i - base, want = -1;                      // want: 0 / 1 = accumulator run, -1 = tap-major order
+        int per_run = per[0] + per[1];
+        if (pp.split && pp.grouped) {
+          want = j < p.taps * per[0] * p.T ? 0 : 1;
+          if (want) j -= p.taps * per[0] * p.T;
+          per_run = per[want];
+        }
+        t = j % p.T;
+        const int kq = j / p.T;
+        tap = kq / per_run;
+        int rank = kq - tap * per_run;
         for (g = 0; g < groups; ++g)
-          if (slice_of(g) / spc == ph && rank-- == 0) break;
+          if (in_phase(g) && (want < 0 || (g & 1) == want) && rank-- == 0) break;
       }
       // A slice sa, weight slice sb; lo = 1: the half-width MMA x_lo * w_hi into L
       int sa = g, sb = g, lo = 0;
@@ -2937,6 +2995,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     pp.nh = p->Cin_p / 16;
     pp.a_slots = p->a_slots;
     pp.a_sw = p->a_sw;
+    pp.grouped = (getenv("EGN_TC_GROUPED") && atoi(getenv("EGN_TC_GROUPED")) == 0) ? 0 : 1;
     // L2 bulk prefetch of the residual rows by the A producer (direct, non-staged epilogue only):
     // EGN_TC_RES_PREFETCH = 2 (default) only when the output channels are not split over blockIdx.y, 1 always,
     // 0 never.  A split layer would prefetch the all-channel rows once per half -- 2x the residual DRAM traffic
@@ -3133,6 +3192,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       if (!a.res) m_res = m_out;
     }
     wp.total_tiles = wp.tiles_x * wp.tiles_y * a.B;
+    wp.grouped = (getenv("EGN_TC_GROUPED") && atoi(getenv("EGN_TC_GROUPED")) == 0) ? 0 : 1;
     const bool persist4 = p->tw_persist && wp.staged;
     wp.acc_sets = persist4 ? 2 : 1;
     wp.stage_off = persist4 ? p->tw_stage_off : 0u;
@@ -3177,6 +3237,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
   tp.B = a.B; tp.OH = p->OH; tp.OW = p->OW; tp.Cout_p = p->Cout_p; tp.Cout = p->Cout; tp.Cin_p = p->Cin_p;
   tp.split = p->split ? 1 : 0; tp.cin_a = p->cin_a; tp.nh = p->Cin_p / 16;
   tp.keep_a = (getenv("EGN_TC_KEEP_A") && atoi(getenv("EGN_TC_KEEP_A"))) ? 1 : 0;
+  tp.grouped = (getenv("EGN_TC_GROUPED") && atoi(getenv("EGN_TC_GROUPED")) == 0) ? 0 : 1;
   tp.taps = p->ksize * p->ksize; tp.ksize = p->ksize; tp.stride = p->stride; tp.pad = p->pad; tp.relu = a.relu;
   tp.TW = p->TW; tp.TH = p->TH; tp.TB = p->TB;
   tp.tiles_w = ceil_div(p->OW, p->TW);
