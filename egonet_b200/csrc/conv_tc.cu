@@ -1166,7 +1166,16 @@ struct TapWinParams {
   int grouped;   // fp16x2: issue the MMAs of a stage grouped by accumulator (all [H | L], then all L)
 };
 
-template <int SW>
+// kPair: the two CTAs of a cluster work as a pair (tcgen05 cta_group::2, M = 256): each CTA loads the windows of its
+//   own tile (tiles 2i and 2i + 1) and HALF of the rows of every weight tile -- [w_hi rows n0 + r n/2 .. | w_lo rows ..]
+//   at identical shared-memory offsets -- and the leader's MMA thread issues one M = 256 MMA for both.  The weight
+//   stream, which every 128-pixel tile has to pull through L2 in full (324 KB for 96 channels, 1.3 MB for 192: at the
+//   MMA rate that is ~40 B / cycle / SM, the measured L2 cap), halves per SM.  Barrier protocol as in
+//   conv_persist_kernel: a_full / b_full / acc_empty live in the LEADER (the peer's TMA transactions and epilogue
+//   arrivals are sent there); a_empty / b_empty / acc_full are signalled in both CTAs by multicast tcgen05.commit.
+//   fp16x2 uses the three-MMA form (x_hi w_hi -> H, x_hi w_lo -> L, x_lo w_hi -> L, N = n_tile each): the stacked
+//   full-width form would need w_hi in both CTAs at the offset where the peer keeps w_lo.
+template <int SW, bool kPair>
 __global__ void __launch_bounds__(kTcThreads, 2)
 conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
@@ -1175,7 +1184,9 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_plane = ((uint32_t)(kTwWp * kTwHp) * SW + 1023u) & ~1023u;
   const uint32_t a_slot = p.split ? 2u * a_plane : a_plane;
-  const uint32_t b_stage = ((uint32_t)p.n_tile * SW * (p.split ? 2u : 1u) + 1023u) & ~1023u;
+  const uint32_t b_rows = (uint32_t)(kPair ? p.n_tile / 2 : p.n_tile);       // weight rows per plane held by this CTA
+  const uint32_t b_stage = (b_rows * SW * (p.split ? 2u : 1u) + 1023u) & ~1023u;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;                    // 0 = leader of the pair
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.na * a_slot;
   uint8_t* smem_stage = smem + p.stage_off;        // stage_off = 0: on top of the (then dead) rings, one tile per CTA
@@ -1192,11 +1203,16 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.n_tile;
-  // tiles of this CTA: blockIdx.x, += gridDim.x (one tile per CTA unless persistent)
-  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // tiles of this CTA: blockIdx.x, += gridDim.x (one tile per CTA unless persistent); pairs: tiles 2q + rank of the
+  // pair's q-th pair of tiles (an odd last tile has a past-the-end partner: loads zero-filled, stores clipped)
+  const int n_units = kPair ? (p.total_tiles + 1) / 2 : p.total_tiles;
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int my_tiles = (n_units - unit0 + unit_step - 1) / unit_step;
   const bool dedicated = p.stage_off != 0;         // staging buffer of its own (persistent mode)
   auto tile_xyb = [&](int it, int& x0, int& y0, int& b0) {
-    int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    int tile = unit0 + it * unit_step;
+    if (kPair) tile = 2 * tile + (int)crank;
     const int tx = tile % p.tiles_x;
     tile /= p.tiles_x;
     x0 = tx * 8;
@@ -1226,13 +1242,18 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);                 // one arrival per epilogue warp
+      mbar_init(&acc_empty[i], kPair ? 8 : 4);     // one arrival per epilogue warp (of both CTAs)
     }
     mbar_init(res_full, 1);
     mbar_init(stage_free, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if constexpr (kPair) {
+    cluster_sync_all();                            // both CTAs' barriers initialised before any remote signal
+    if (warp == 1) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+  } else {
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1251,9 +1272,17 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_wait(&a_empty[slot], (uint32_t)(((q / p.na) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* sa = smem_a + (size_t)slot * a_slot;
-        mbar_expect_tx(&a_full[slot], (p.split ? 2u : 1u) * p.a_bytes);
-        tma_load_4d(sa, &map_a, &a_full[slot], c * p.kc, x0 - 1, y0 - 1, b0);
-        if (p.split) tma_load_4d(sa + a_plane, &map_a, &a_full[slot], p.Cin_p + c * p.kc, x0 - 1, y0 - 1, b0);
+        if constexpr (kPair) {
+          // both CTAs' windows are accounted for on the leader's barrier
+          if (crank == 0) mbar_expect_tx(&a_full[slot], 2u * (p.split ? 2u : 1u) * p.a_bytes);
+          const uint32_t bar = mapa_rank(&a_full[slot], 0);
+          tma_load_4d_pair(sa, &map_a, bar, c * p.kc, x0 - 1, y0 - 1, b0);
+          if (p.split) tma_load_4d_pair(sa + a_plane, &map_a, bar, p.Cin_p + c * p.kc, x0 - 1, y0 - 1, b0);
+        } else {
+          mbar_expect_tx(&a_full[slot], (p.split ? 2u : 1u) * p.a_bytes);
+          tma_load_4d(sa, &map_a, &a_full[slot], c * p.kc, x0 - 1, y0 - 1, b0);
+          if (p.split) tma_load_4d(sa + a_plane, &map_a, &a_full[slot], p.Cin_p + c * p.kc, x0 - 1, y0 - 1, b0);
+        }
       }
     };
     // na - 1 chunk windows in flight ahead of the one being multiplied.  The refill is issued at tap 3: the slot was
@@ -1269,9 +1298,18 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(&b_empty[stage], phase ^ 1u);
         if (elect_one()) {
           uint8_t* sb = smem_b + (size_t)stage * b_stage;
-          mbar_expect_tx(&b_full[stage], (p.split ? 2u : 1u) * p.b_bytes);
-          tma_load_2d(sb, &map_b, &b_full[stage], tap * p.tap_k + c * p.kc, n0);
-          if (p.split) tma_load_2d(sb + p.b_bytes, &map_b, &b_full[stage], tap * p.tap_k + c * p.kc, p.Cout_p + n0);
+          if constexpr (kPair) {
+            // this CTA's half of the rows of each plane (p.b_bytes = bytes of that half)
+            if (crank == 0) mbar_expect_tx(&b_full[stage], 2u * (p.split ? 2u : 1u) * p.b_bytes);
+            const uint32_t bar = mapa_rank(&b_full[stage], 0);
+            const int nr = n0 + (int)crank * (p.n_tile / 2);
+            tma_load_2d_pair(sb, &map_b, bar, tap * p.tap_k + c * p.kc, nr);
+            if (p.split) tma_load_2d_pair(sb + p.b_bytes, &map_b, bar, tap * p.tap_k + c * p.kc, p.Cout_p + nr);
+          } else {
+            mbar_expect_tx(&b_full[stage], (p.split ? 2u : 1u) * p.b_bytes);
+            tma_load_2d(sb, &map_b, &b_full[stage], tap * p.tap_k + c * p.kc, n0);
+            if (p.split) tma_load_2d(sb + p.b_bytes, &map_b, &b_full[stage], tap * p.tap_k + c * p.kc, p.Cout_p + n0);
+          }
         }
         if (++stage == (uint32_t)p.nb) {
           stage = 0;
@@ -1300,11 +1338,20 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    if (!kPair || crank == 0) {
+    // ===================== MMA issuer (pairs: the leader issues for both CTAs) =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | (((kPair ? 256u : 128u) >> 4) << 24);
     const uint32_t idesc_w = (1u << 4) | ((uint32_t)(p.n_tile >> 2) << 17) | ((128u >> 4) << 24);   // N = 2 n_tile
-    const bool wide = p.split && 2 * p.n_tile <= 256;
+    const bool wide = !kPair && p.split && 2 * p.n_tile <= 256;
     const uint64_t desc_hi = make_smem_desc(0, SW);
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+      if constexpr (kPair) umma_f16_pair(d, ad, bd, id, acc);
+      else umma_f16(d, ad, bd, id, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (kPair) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     // A: 8-row groups one window row apart
     const uint64_t desc_hi_a = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(((uint32_t)kTwWp * SW) >> 4) << 32);
     const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
@@ -1336,19 +1383,19 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
               for (int k = 0; k < SW / 32; ++k) {
                 if (c * (SW / 32) + k >= p.nh) continue;
-                umma_f16(d_h, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), wide ? idesc_w : idesc, (c | tap | k) ? 1u : 0u);
+                mma(d_h, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), wide ? idesc_w : idesc, (c | tap | k) ? 1u : 0u);
               }
               if (!wide) {
 #pragma unroll
                 for (int k = 0; k < SW / 32; ++k) {
                   if (c * (SW / 32) + k >= p.nh) continue;
-                  umma_f16(d_l, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
+                  mma(d_l, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
                 }
               }
 #pragma unroll
               for (int k = 0; k < SW / 32; ++k) {
                 if (c * (SW / 32) + k >= p.nh) continue;
-                umma_f16(d_l, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                mma(d_l, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
               }
             } else
 #pragma unroll
@@ -1357,23 +1404,23 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               const uint32_t acc = (c | tap | k) ? 1u : 0u;          // the first MMA of a tile initialises the accumulators
               const uint64_t ko = (uint64_t)(2 * k);
               if (!p.split) {
-                umma_f16(d_h, adesc + ko, bdesc + ko, idesc, acc);
+                mma(d_h, adesc + ko, bdesc + ko, idesc, acc);
               } else if (wide) {
-                umma_f16(d_h, adesc + ko, bdesc + ko, idesc_w, acc);                   // [H | L] += x_hi [w_hi | w_lo]
-                umma_f16(d_l, adesc_lo + ko, bdesc + ko, idesc, 1u);                   // L += x_lo w_hi
+                mma(d_h, adesc + ko, bdesc + ko, idesc_w, acc);                   // [H | L] += x_hi [w_hi | w_lo]
+                mma(d_l, adesc_lo + ko, bdesc + ko, idesc, 1u);                   // L += x_lo w_hi
               } else {
-                if (p.keep_a) {
+                if (p.keep_a && !kPair) {
                   umma_f16_keep_a(d_h, adesc + ko, bdesc + ko, idesc, acc);            // H += x_hi w_hi
                   umma_f16_reuse_a(d_l, adesc + ko, bdesc_lo + ko, idesc, acc);        // L += x_hi w_lo
                 } else {
-                  umma_f16(d_h, adesc + ko, bdesc + ko, idesc, acc);                   // H += x_hi w_hi
-                  umma_f16(d_l, adesc + ko, bdesc_lo + ko, idesc, acc);                // L += x_hi w_lo
+                  mma(d_h, adesc + ko, bdesc + ko, idesc, acc);                   // H += x_hi w_hi
+                  mma(d_l, adesc + ko, bdesc_lo + ko, idesc, acc);                // L += x_hi w_lo
                 }
-                umma_f16(d_l, adesc_lo + ko, bdesc + ko, idesc, 1u);                   // L += x_lo w_hi
+                mma(d_l, adesc_lo + ko, bdesc + ko, idesc, 1u);                   // L += x_lo w_hi
               }
             }
-            umma_commit(&b_empty[stage]);
-            if (tap == 8) umma_commit(&a_empty[slot]);
+            commit(&b_empty[stage]);
+            if (tap == 8) commit(&a_empty[slot]);
           }
           if (++stage == (uint32_t)p.nb) {
             stage = 0;
@@ -1381,8 +1428,9 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
         }
       }
-      if (elect_one()) umma_commit(&acc_full[set]);
+      if (elect_one()) commit(&acc_full[set]);
       if (it == 0 && lane == 0) EGN_TS(3);
+    }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -1411,7 +1459,10 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }, p.split ? 2 : 1, p.split);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[set]);          // accumulator set may be overwritten
+        if (lane == 0) {                                      // accumulator set may be overwritten
+          if constexpr (kPair) mbar_arrive_cluster(mapa_rank(&acc_empty[set], 0));
+          else mbar_arrive(&acc_empty[set]);
+        }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");        // the four epilogue warps
         if (warp == 2 && elect_one()) {
@@ -1436,7 +1487,10 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         epi_run(e, tbase, 1, p.n_tile, n0, &acc_full[set], [&](int) { return er; }, use & 1u);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[set]);
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_cluster(mapa_rank(&acc_empty[set], 0));
+          else mbar_arrive(&acc_empty[set]);
+        }
       }
       if (it == 0 && (threadIdx.x & 127) == 64) EGN_TS(5);
     }
@@ -1444,9 +1498,11 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();                    // the peer's smem / barriers stay valid until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
     if (lane == 0) EGN_TS(6);
   }
 }
@@ -2321,6 +2377,7 @@ struct TcConvPlan {
   bool use_tapwin = false;    // v4: tap-window kernel (conv_tapwin_kernel)
   int tw_na = 2, tw_nb = 4;   // its A ring slots / B ring stages
   bool tw_persist = false;    // persistent mode: two accumulator sets, staging buffer of its own (TapWinParams)
+  bool tw_pair = false;       // CTA pairs (cta_group::2): each CTA streams half of every weight tile
   uint32_t tw_stage_off = 0, tw_stage_bytes = 0;
   bool use_pair = false;      // v3 with CTA pairs (cta_group::2) instead of an N split over blockIdx.y
   size_t pair_smem = 0;       // dynamic smem per CTA in pair mode
@@ -2696,7 +2753,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         p->kchunks = ceil_div(a.Cin_p, p->kc);
         const size_t a_plane = ((size_t)kTwWp * kTwHp * p->sw + 1023) & ~(size_t)1023;
         const size_t a_slot = (split ? 2 : 1) * a_plane;
-        const size_t b_stage4 = ((size_t)p->n_tile * p->sw * (split ? 2 : 1) + 1023) & ~(size_t)1023;
+        // CTA pairs: half of the weight rows per CTA (EGN_TC_V4_PAIR=0 disables)
+        p->tw_pair = p->n_tile % 32 == 0 && !(getenv("EGN_TC_V4_PAIR") && atoi(getenv("EGN_TC_V4_PAIR")) == 0);
+        const size_t b_stage4 = ((size_t)(p->tw_pair ? p->n_tile / 2 : p->n_tile) * p->sw * (split ? 2 : 1) + 1023) & ~(size_t)1023;
         const bool two = p->tmem_cols <= 256;
         // staged epilogue: [block][128 pixels][cb channels], hi blocks then lo blocks
         p->cb = p->n_tile % 64 == 0 ? 64 : (p->n_tile % 48 == 0 ? 48 : (p->n_tile % 32 == 0 ? 32 : 0));
@@ -2723,9 +2782,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         if (p->tw_persist) p->tmem_cols = pow2_cols(2 * (split ? 2 : 1) * p->n_tile);
         p->blk = 1; p->BW = 8; p->BH = 16; p->TBW = 1;          // staging box of make_io_map
         if (getenv("EGN_TC_VERBOSE") && p->use_tapwin)
-          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d persist=%d\n",
+          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d persist=%d pair=%d\n",
                   a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->sw, p->kchunks,
-                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb, p->tw_persist ? 1 : 0);
+                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb, p->tw_persist ? 1 : 0, p->tw_pair ? 1 : 0);
       }
     }
     if (p->use_tapwin) {
@@ -2818,7 +2877,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)w_rows};
   const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)p->kc, (cuuint32_t)p->n_tile};
+  const cuuint32_t box[2] = {(cuuint32_t)p->kc, (cuuint32_t)(p->use_tapwin && p->tw_pair ? p->n_tile / 2 : p->n_tile)};
   const cuuint32_t es[2] = {1, 1};
   CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p->d_w, gdim, gstr, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p->sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -2924,8 +2983,10 @@ static int device_setup() {
   opt_in((const void*)conv_tc_kernel<64>, 227 * 1024);
   opt_in((const void*)conv_tc_kernel<32>, 227 * 1024);
   opt_in((const void*)conv_run_kernel, 200 * 1024 + 2048);
-  opt_in((const void*)conv_tapwin_kernel<128>, 227 * 1024);
-  opt_in((const void*)conv_tapwin_kernel<64>, 227 * 1024);
+  opt_in((const void*)conv_tapwin_kernel<128, false>, 227 * 1024);
+  opt_in((const void*)conv_tapwin_kernel<64, false>, 227 * 1024);
+  opt_in((const void*)conv_tapwin_kernel<128, true>, 227 * 1024);
+  opt_in((const void*)conv_tapwin_kernel<64, true>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<false>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<true>, 227 * 1024);
   opt_in((const void*)conv_persist_kernel<false, true>, 227 * 1024);
@@ -3162,7 +3223,7 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     wp.n_tile = p->n_tile; wp.kc = p->kc; wp.kchunks = p->kchunks; wp.na = p->tw_na; wp.nb = p->tw_nb;
     wp.tap_k = p->split ? p->Cin_p : p->cin_k;
     wp.a_bytes = (uint32_t)(kTwWp * kTwHp) * (uint32_t)p->sw;
-    wp.b_bytes = (uint32_t)p->n_tile * (uint32_t)p->sw;
+    wp.b_bytes = (uint32_t)(p->tw_pair ? p->n_tile / 2 : p->n_tile) * (uint32_t)p->sw;
     wp.tmem_cols = p->tmem_cols;
     wp.split = p->split ? 1 : 0;
     wp.nh = p->Cin_p / 16;
@@ -3199,6 +3260,11 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     wp.stage_bytes = p->tw_stage_bytes;            // (the barrier block sits behind the region either way)
     if (p->tw_persist && !persist4) wp.tmem_cols = p->tmem_cols;      // head extras: one tile per CTA, direct epilogue
     dim3 grid((unsigned)(persist4 ? std::min(wp.total_tiles, num_sms) : wp.total_tiles), (unsigned)p->n_tiles);
+    if (p->tw_pair) {
+      // clusters of two CTAs along x: tiles 2q, 2q + 1 per pair (an odd last tile gets a past-the-end partner)
+      const int units = (wp.total_tiles + 1) / 2;
+      grid.x = 2u * (unsigned)(persist4 ? std::min(units, num_sms / 2) : units);
+    }
     static unsigned long long* d_ts4 = nullptr;
     const size_t n_cta = (size_t)grid.x * grid.y;
     if (getenv("EGN_TC_TS") && n_cta <= 8192) {
@@ -3206,10 +3272,15 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
       cudaMemsetAsync(d_ts4, 0, 8192 * 8 * sizeof(unsigned long long), st);
       wp.ts = d_ts4;
     }
-    if (p->sw == 128)
-      EGN_CUDA_CHECK(launch_pdl(conv_tapwin_kernel<128>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, wp));
+    if (p->tw_pair) {
+      if (p->sw == 128)
+        EGN_CUDA_CHECK(launch_pdl_cluster(conv_tapwin_kernel<128, true>, grid, dim3(kTcThreads), p->smem_bytes, st, 2, ma, p->map_b, m_res, m_out, wp));
+      else
+        EGN_CUDA_CHECK(launch_pdl_cluster(conv_tapwin_kernel<64, true>, grid, dim3(kTcThreads), p->smem_bytes, st, 2, ma, p->map_b, m_res, m_out, wp));
+    } else if (p->sw == 128)
+      EGN_CUDA_CHECK(launch_pdl(conv_tapwin_kernel<128, false>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, wp));
     else
-      EGN_CUDA_CHECK(launch_pdl(conv_tapwin_kernel<64>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, wp));
+      EGN_CUDA_CHECK(launch_pdl(conv_tapwin_kernel<64, false>, grid, dim3(kTcThreads), p->smem_bytes, st, ma, p->map_b, m_res, m_out, wp));
     EGN_LAUNCH_CHECK("conv_tapwin_kernel");
     if (wp.ts && getenv("EGN_TC_TS_DUMP")) {
       cudaStreamSynchronize(st);
