@@ -1130,7 +1130,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // 756 KB per tile for 96 channels.  fp16x2 operands as in the per-tap kernel's fat stages: an A slot holds the
 // x_hi and the x_lo box, a B stage the row-stacked [w_hi | w_lo] tile.
 // ---------------------------------------------------------------------------
-constexpr int kTwMaxA = 4, kTwMaxB = 8;
+constexpr int kTwMaxA = 4, kTwMaxB = 16;
 constexpr int kTwWp = 10, kTwHp = 18;        // window = (8 + 2) x (16 + 2) pixels
 
 struct TapWinParams {
@@ -1199,7 +1199,7 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* res_full = acc_empty + 2;
   uint64_t* stage_free = res_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [n_tile]; offset 30 * 8 + 16 = 256: 16-byte aligned
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [n_tile]; offset (2 * 4 + 2 * 16 + 6) * 8 + 16 = 384: 16-byte aligned
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.n_tile;
@@ -2746,15 +2746,17 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const int v4_mode = e4 ? atoi(e4) : 1;              // 0 off, 1 fp16x2 only, 2 plain fp16 too
       if (a.ksize == 3 && a.stride == 1 && a.pad == 1 && eff4 >= 0.75 && v4_mode && (split || v4_mode == 2) && force_sw == 0) {
         p->use_tapwin = true;
-        // 32-channel chunks where two CTAs share an SM (<= 256 TMEM columns), 64-channel chunks for the wide tiles
-        // (measured, batch 256: 96ch 156 vs 226 us, 192ch 138 vs 128 us)
-        p->sw = getenv("EGN_TC_V4_SW") ? atoi(getenv("EGN_TC_V4_SW")) : (p->tmem_cols <= 256 ? 64 : 128);
+        // CTA pairs: half of the weight rows per CTA (EGN_TC_V4_PAIR=0 disables)
+        p->tw_pair = p->n_tile % 32 == 0 && !(getenv("EGN_TC_V4_PAIR") && atoi(getenv("EGN_TC_V4_PAIR")) == 0);
+        // 64-channel chunks, except 32-channel ones for single CTAs of <= 256 TMEM columns (two per SM or persistent with
+        // 12 KB stages; measured, batch 256: 96ch 156 vs 226 us unpaired, 192ch 138 vs 128 us).  The kernel is bound by
+        // the bytes its weight ring keeps in flight against the ~1.2 us L2 -> smem latency under load: paired 96ch
+        // 118 / 114 / 113 us with 8 / 12 / 16 stages of 6 KB, 110 us with 6 stages of 12 KB.
+        p->sw = getenv("EGN_TC_V4_SW") ? atoi(getenv("EGN_TC_V4_SW")) : ((p->tmem_cols <= 256 && !p->tw_pair) ? 64 : 128);
         p->kc = p->sw / 2;
         p->kchunks = ceil_div(a.Cin_p, p->kc);
         const size_t a_plane = ((size_t)kTwWp * kTwHp * p->sw + 1023) & ~(size_t)1023;
         const size_t a_slot = (split ? 2 : 1) * a_plane;
-        // CTA pairs: half of the weight rows per CTA (EGN_TC_V4_PAIR=0 disables)
-        p->tw_pair = p->n_tile % 32 == 0 && !(getenv("EGN_TC_V4_PAIR") && atoi(getenv("EGN_TC_V4_PAIR")) == 0);
         const size_t b_stage4 = ((size_t)(p->tw_pair ? p->n_tile / 2 : p->n_tile) * p->sw * (split ? 2 : 1) + 1023) & ~(size_t)1023;
         const bool two = p->tmem_cols <= 256;
         // staged epilogue: [block][128 pixels][cb channels], hi blocks then lo blocks
@@ -2767,7 +2769,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         p->tw_persist = two && want_staged && !(getenv("EGN_TC_V4_PERSIST") && atoi(getenv("EGN_TC_V4_PERSIST")) == 0);
         const size_t fixed4 = 1024 + (2 * kTwMaxA + 2 * kTwMaxB + 6) * sizeof(uint64_t) + 32 + (size_t)p->n_tile * 4;
         const size_t budget4 = getenv("EGN_TC_V4_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V4_BUDGET_KB")) * 1024
-                                                             : (p->tw_persist ? 225 * 1024 - stage_bytes : (two ? 106 * 1024 : 212 * 1024));
+                                                             : (p->tw_persist ? 225 * 1024 - stage_bytes : (two ? 106 * 1024 : 224 * 1024));
         p->tw_na = getenv("EGN_TC_V4_NA") ? atoi(getenv("EGN_TC_V4_NA")) : 2;      // (3 measured equal once the refill moved to tap 3)
         p->tw_na = std::max(1, std::min(std::min(p->tw_na, kTwMaxA), std::max(1, p->kchunks)));
         long nb = ((long)budget4 - (long)fixed4 - (long)(p->tw_na * a_slot)) / (long)b_stage4;
@@ -3569,5 +3571,109 @@ extern "C" int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift,
   double acc = 0;
   for (long long v : h) acc += (double)v;
   *cycles_per_mma = acc / ctas / ((double)iters * 4 * nacc);
+  return EGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Hardware probe: cost of the MMA SEQUENCES the fp16x2 kernels issue (no TMA, no epilogue, operands resident):
+//   pattern 0: N = n into one accumulator;  1: stacked pair per K16 slice, full-width N = 2n -> [H | L] then
+//   half-width N = n -> L;  2: three-MMA form (H, L, L), N = n each;  3: as 1 but grouped per two slices (two
+//   full-width, then two half-width).  The A descriptor uses `a_sw`-byte rows with its 8-row groups `sbo_rows`
+//   rows apart (8 = the plain atom, 10 / 18 = block-shaped windows) and a start row that walks over the nine tap
+//   shifts, as in the conv kernels.  Returns SM cycles per K16 slice.
+// ---------------------------------------------------------------------------
+namespace egn {
+__global__ void __launch_bounds__(128)
+umma_seq_kernel(int n, int pattern, int iters, int a_sw, int sbo_rows, long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                 // 640 rows x 128 B
+  uint8_t* sb = smem + 640 * 128;     // 512 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + 512 * 128);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  for (int i = threadIdx.x; i < (640 + 512) * 128 / 4; i += 128) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    reinterpret_cast<uint32_t*>(smem)[i] = (h & 0x83FF83FFu) | 0x38003800u;
+  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *slot, 0);
+  if (warp == 1) {
+    const uint32_t idesc_n = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_w = (1u << 4) | ((uint32_t)(n >> 2) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_b = make_smem_desc(0, 128) | (uint64_t)((smem_u32(sb) & 0x3FFFFu) >> 4);
+    const uint64_t desc_a_hi = (make_smem_desc(0, (uint32_t)a_sw) & ~((uint64_t)0x3FFF << 32)) |
+                               ((uint64_t)(((uint32_t)sbo_rows * (uint32_t)a_sw) >> 4) << 32);
+    const uint32_t a0 = smem_u32(sa);
+    const int spc = a_sw / 32;                         // K16 slices per row
+    long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        const int tap = it % 9, r = tap / 3, q = tap - 3 * r;
+        const uint32_t row = (uint32_t)(r * sbo_rows + q);
+        const uint64_t ad = desc_a_hi | (uint64_t)(((a0 + row * (uint32_t)a_sw) & 0x3FFFFu) >> 4);
+        const uint64_t ad_lo = ad + (uint64_t)((320u * 128u) >> 4);       // the "lo plane" box
+        const uint64_t bd_lo = desc_b + (uint64_t)((256u * 128u) >> 4);
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t ko = (uint64_t)(2 * (k % spc));
+          if (pattern == 0) {
+            umma_f16(tmem, ad + ko, desc_b + ko, idesc_n, 1u);
+          } else if (pattern == 1) {
+            umma_f16(tmem, ad + ko, desc_b + ko, idesc_w, 1u);
+            umma_f16(tmem + (uint32_t)n, ad_lo + ko, desc_b + ko, idesc_n, 1u);
+          } else if (pattern == 2) {
+            umma_f16(tmem, ad + ko, desc_b + ko, idesc_n, 1u);
+            umma_f16(tmem + (uint32_t)n, ad + ko, bd_lo + ko, idesc_n, 1u);
+            umma_f16(tmem + (uint32_t)n, ad_lo + ko, desc_b + ko, idesc_n, 1u);
+          }
+        }
+        if (pattern == 3) {
+          for (int k = 0; k < 2; ++k) umma_f16(tmem, ad + (uint64_t)(2 * (k % spc)), desc_b + (uint64_t)(2 * (k % spc)), idesc_w, 1u);
+          for (int k = 0; k < 2; ++k) umma_f16(tmem + (uint32_t)n, ad_lo + (uint64_t)(2 * (k % spc)), desc_b + (uint64_t)(2 * (k % spc)), idesc_n, 1u);
+        }
+      }
+      umma_commit(&bar[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[0], 0);
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out_cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace egn
+
+extern "C" int egn_debug_umma_seq(int n, int pattern, int iters, int a_sw, int sbo_rows, int ctas, double* cycles_per_slice) {
+  using namespace egn;
+  EGN_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && pattern >= 0 && pattern <= 3 && iters > 0 && ctas >= 1 && ctas <= 1024 &&
+                  (a_sw == 128 || a_sw == 64) && sbo_rows >= 8 && sbo_rows <= 18 && (pattern == 0 || pattern == 2 || 2 * n <= 256) &&
+                  2 * n <= 512 && cycles_per_slice,
+              "egn_debug_umma_seq: bad arguments");
+  if (int rc = require_device()) return rc;
+  long long* d = nullptr;
+  EGN_CUDA_CHECK(cudaMalloc(&d, ctas * sizeof(long long)));
+  EGN_CUDA_CHECK(cudaMemset(d, 0, ctas * sizeof(long long)));
+  const size_t smem = 1024 + (640 + 512) * 128 + 64;
+  EGN_CUDA_CHECK(cudaFuncSetAttribute(umma_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_seq_kernel<<<ctas, 128, smem>>>(n, pattern, iters, a_sw, sbo_rows, d);
+  EGN_LAUNCH_CHECK("umma_seq_kernel");
+  EGN_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<long long> h(ctas);
+  cudaMemcpy(h.data(), d, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  double acc = 0;
+  for (long long v : h) acc += (double)v;
+  *cycles_per_slice = acc / ctas / ((double)iters * 2);
   return EGN_OK;
 }

@@ -164,6 +164,11 @@ EGN_API int egn_debug_conv_acc(int impl, const void* in, const float* w_oihw_hos
  * CTAs each issue iters*4*nacc MMAs of width n, rotating over nacc accumulators. */
 EGN_API int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift, int ctas, double* cycles_per_mma);
 
+/* Hardware probe (debug): SM cycles per K16 slice of the MMA sequences the fp16x2 conv kernels issue (pattern 0: one
+ * N = n MMA; 1: full-width N = 2n + half-width N = n; 2: three N = n MMAs into H, L, L; 3: as 1, grouped per two
+ * slices), operands resident in shared memory, A rows of a_sw bytes (128 / 64) with 8-row groups sbo_rows rows apart. */
+EGN_API int egn_debug_umma_seq(int n, int pattern, int iters, int a_sw, int sbo_rows, int ctas, double* cycles_per_slice);
+
 /* Hardware probe (debug): one 128 x KC x KC UMMA whose A descriptor starts `row_off` rows into a
  * TMA-written swizzled tile; bo_mode selects the descriptor base-offset encoding under test.
  * a: device fp16 [256][KC], b: device fp16 [KC][KC], out: device fp32 [128][KC], KC = swizzle/2. */
