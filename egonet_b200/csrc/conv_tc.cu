@@ -2824,20 +2824,18 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
     fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v1-tap n_tile=%d sw=%d stages=%d smem=%zuKB tmem=%u staged=%d cb=%d\n", a.ksize, a.ksize,
             a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->sw, p->stages, p->smem_bytes / 1024, p->tmem_cols,
             p->n_stage, p->cb);
-  // weights: folded [tap][Cin_p][Cout_p] fp32 -> [Cout_p][K] fp16, zero padded to whole kc-channel chunks.
-  //   plain fp16           K = taps * cin_k, tap row = [w (Cin_p)]
-  //   fp16x2, v2 / v3      K = taps * cin_k, tap row = [w_hi (Cin_p) | w_lo (Cin_p)]   (cross pairing by the issuer)
-  //   fp16x2, v1           K = taps * (kchunks + kchunks_h) * kc, tap row = [w_hi | w_hi] chunks, then [w_lo] chunks
-  //                        (stage order of conv_tc_kernel: A = [x_hi | x_lo] then A = x_hi again)
-  // w_hi = rn16(w), w_lo = rn16(w - w_hi).
+  // weights: folded [tap][Cin_p][Cout_p] fp32 -> fp16 matrices, w_hi = rn16(w), w_lo = rn16(w - w_hi):
+  //   plain fp16                 [Cout_p][taps * cin_k], tap row = [w (Cin_p)] zero padded to whole kc-channel chunks
+  //                              (persistent kernel: 32-channel tail chunks of two taps packed per tile, pack_tail)
+  //   fp16x2, v1 / v3 / v4       the STACKED matrix [2 * Cout_p][taps * Cin_p rounded up to 64]: rows [0, Cout_p) = w_hi,
+  //                              [Cout_p, 2 Cout_p) = w_lo, K index tap * Cin_p + c (K16 slices packed densely, no per-tap
+  //                              padding; PersistParams / TcParams / TapWinParams)
+  //   fp16x2, v2 (window-run)    [Cout_p][taps * cin_k], tap row = [w_hi (Cin_p) | w_lo (Cin_p)] (cross pairing by the issuer)
   const int taps = a.ksize * a.ksize;
   const int cin_k = p->kchunks * p->kc;
   p->cin_k = cin_k;
-  //   fp16x2, v3           [2 * Cout_p][w_tiles * 64]: rows [0, Cout_p) = w_hi, [Cout_p, 2 Cout_p) = w_lo, K index
-  //                        tap * Cin_p + c (K16 slices packed densely, no per-tap padding; PersistParams "stacked")
   const bool pack = p->use_persist && p->pack_tail;
-  const bool v1_split = false;                                          // (the per-tap kernel shares the stacked matrix)
-  const bool v3_split = split && !p->use_run;                           // stacked matrix: persistent and per-tap kernels
+  const bool v3_split = split && !p->use_run;                           // the stacked matrix
   const int full_k = (p->kchunks - 1) * 64;              // channels of a tap that live in full 64-wide chunks
   const size_t tap_k = (size_t)cin_k;
   const size_t K = v3_split ? ((size_t)taps * a.Cin_p + 63) / 64 * 64
@@ -2861,13 +2859,9 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
           w[((size_t)a.Cout_p + o) * K + (size_t)t * a.Cin_p + c] = lo;
         } else if (!split) {
           put(c, hi);
-        } else if (!v1_split) {
-          put(c, hi);
-          put(a.Cin_p + c, lo);
         } else {
           put(c, hi);
-          put(a.Cin_p + c, hi);
-          put(p->kchunks * p->kc + c, lo);
+          put(a.Cin_p + c, lo);
         }
       }
   p->w_bytes = w.size() * sizeof(__half);
