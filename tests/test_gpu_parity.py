@@ -382,6 +382,8 @@ CONV_CASES = [
     (35, 66, 64, 64, 3, 2, 2), (35, 66, 64, 64, 1, 2, 2), (66, 66, 4, 4, 3, 1, 5), (48, 33, 64, 64, 1, 1, 2),
     (32, 32, 64, 48, 3, 1, 2), (64, 64, 32, 24, 3, 1, 3), (128, 256, 16, 12, 3, 2, 3), (16, 16, 32, 32, 3, 1, 1),
     (96, 96, 32, 32, 3, 1, 40),     # 440 windows: several iterations per CTA pair, last pair iteration ragged
+    (96, 96, 16, 8, 3, 1, 3),       # tap-window kernel: 3 tiles -- the last CTA pair has a past-the-end partner tile
+    (48, 48, 16, 24, 3, 1, 1),      # 3 tiles of one image, persistent pair mode with fewer tiles than CTAs
 ]
 
 
