@@ -1164,6 +1164,10 @@ struct TapWinParams {
   int total_tiles, acc_sets;
   uint32_t stage_off, stage_bytes;
   int grouped;   // fp16x2: issue the MMAs of a stage grouped by accumulator (all [H | L], then all L)
+  // N fold (persistent mode): layers wider than 128 channels run as n_fold parts of n_tile channels each, a work unit
+  // is (tile, part) -- so that 192-channel layers get two accumulator sets, the cross-tile rings and no wave
+  // quantisation (512 tiles on 148 SMs) like the 96-channel ones; the parts of a tile re-load its windows (L2 hits)
+  int n_fold;
 };
 
 // kPair: the two CTAs of a cluster work as a pair (tcgen05 cta_group::2, M = 256): each CTA loads the windows of its
@@ -1202,16 +1206,19 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [n_tile]; offset (2 * 4 + 2 * 16 + 6) * 8 + 16 = 384: 16-byte aligned
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * p.n_tile;
-  // tiles of this CTA: blockIdx.x, += gridDim.x (one tile per CTA unless persistent); pairs: tiles 2q + rank of the
-  // pair's q-th pair of tiles (an odd last tile has a past-the-end partner: loads zero-filled, stores clipped)
-  const int n_units = kPair ? (p.total_tiles + 1) / 2 : p.total_tiles;
+  const int n_base = blockIdx.y * p.n_tile * p.n_fold;
+  // work units of this CTA: blockIdx.x, += gridDim.x (one per CTA unless persistent).  A unit is (tile, N part); pairs:
+  // (pair of tiles 2q + rank, N part) -- both CTAs of a pair work on the same part, they share its weight rows (an odd
+  // last tile has a past-the-end partner: loads zero-filled, stores clipped)
+  const int n_units = (kPair ? (p.total_tiles + 1) / 2 : p.total_tiles) * p.n_fold;
   const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int my_tiles = (n_units - unit0 + unit_step - 1) / unit_step;
   const bool dedicated = p.stage_off != 0;         // staging buffer of its own (persistent mode)
+  auto part_of = [&](int it) { return (unit0 + it * unit_step) % p.n_fold; };
+  auto n0_of = [&](int it) { return n_base + part_of(it) * p.n_tile; };
   auto tile_xyb = [&](int it, int& x0, int& y0, int& b0) {
-    int tile = unit0 + it * unit_step;
+    int tile = (unit0 + it * unit_step) / p.n_fold;
     if (kPair) tile = 2 * tile + (int)crank;
     const int tx = tile % p.tiles_x;
     tile /= p.tiles_x;
@@ -1222,7 +1229,7 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const uint32_t set_cols = (uint32_t)((p.split ? 2 : 1) * p.n_tile);      // TMEM columns of one accumulator set
   if (threadIdx.x == 0) EGN_TS(0);
   if (p.staged)
-    for (int i = threadIdx.x; i < p.n_tile; i += (int)blockDim.x) s_bias[i] = __ldg(p.bias + n0 + i);
+    for (int i = threadIdx.x; i < p.n_tile * p.n_fold; i += (int)blockDim.x) s_bias[i] = __ldg(p.bias + n_base + i);
 
   if (threadIdx.x == 0) {
     pdl_trigger();
@@ -1293,6 +1300,7 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint32_t stage = 0, phase = 0;
     for (int q = 0; q < Q; ++q) {
       const int c = q % p.kchunks;
+      const int n0 = n0_of(q / p.kchunks);
       for (int tap = 0; tap < 9; ++tap) {
         if (tap == (p.na > 1 ? 3 : 8) && q + D < Q) load_a(q + D);
         mbar_wait(&b_empty[stage], phase ^ 1u);
@@ -1442,9 +1450,10 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint32_t use = (uint32_t)(p.acc_sets == 2 ? it >> 1 : it);
       int x0, y0, b0;
       tile_xyb(it, x0, y0, b0);
+      const int n0 = n0_of(it);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * set_cols;
       if (p.staged) {
-        const EpiStage es{smem_u32(smem_stage), smem_u32(s_bias), p.blk_bytes, p.cb, p.res != nullptr, p.relu, 0,
+        const EpiStage es{smem_u32(smem_stage), smem_u32(s_bias + part_of(it) * p.n_tile), p.blk_bytes, p.cb, p.res != nullptr, p.relu, 0,
                           p.split ? (uint32_t)p.nblk_plane * p.blk_bytes : 0u};
         if (p.res) mbar_wait(res_full, (uint32_t)(it & 1));
         else if (dedicated && it > 0) mbar_wait(stage_free, (uint32_t)((it - 1) & 1));      // previous stores read out
@@ -2378,6 +2387,7 @@ struct TcConvPlan {
   int tw_na = 2, tw_nb = 4;   // its A ring slots / B ring stages
   bool tw_persist = false;    // persistent mode: two accumulator sets, staging buffer of its own (TapWinParams)
   bool tw_pair = false;       // CTA pairs (cta_group::2): each CTA streams half of every weight tile
+  int tw_fold = 1;            // N parts folded into the work units (TapWinParams::n_fold)
   uint32_t tw_stage_off = 0, tw_stage_bytes = 0;
   bool use_pair = false;      // v3 with CTA pairs (cta_group::2) instead of an N split over blockIdx.y
   size_t pair_smem = 0;       // dynamic smem per CTA in pair mode
@@ -2746,6 +2756,14 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
       const int v4_mode = e4 ? atoi(e4) : 1;              // 0 off, 1 fp16x2 only, 2 plain fp16 too
       if (a.ksize == 3 && a.stride == 1 && a.pad == 1 && eff4 >= 0.75 && v4_mode && (split || v4_mode == 2) && force_sw == 0) {
         p->use_tapwin = true;
+        // N fold: 129..256 output channels run as two parts of <= 128 so that two accumulator sets fit in TMEM and
+        // the tile loop can be persistent (EGN_TC_V4_FOLD=0 disables)
+        if (p->n_tile > 128 && p->n_tile <= 256 && (p->n_tile / 2) % 32 == 0 &&
+            !(getenv("EGN_TC_V4_FOLD") && atoi(getenv("EGN_TC_V4_FOLD")) == 0)) {
+          p->tw_fold = 2;
+          p->n_tile /= 2;
+          p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
+        }
         // CTA pairs: half of the weight rows per CTA (EGN_TC_V4_PAIR=0 disables)
         p->tw_pair = p->n_tile % 32 == 0 && !(getenv("EGN_TC_V4_PAIR") && atoi(getenv("EGN_TC_V4_PAIR")) == 0);
         // 64-channel chunks, except 32-channel ones for single CTAs of <= 256 TMEM columns (two per SM or persistent with
@@ -2767,7 +2785,7 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         const bool want_staged = p->cb && !(getenv("EGN_TC_V4_STAGED") && atoi(getenv("EGN_TC_V4_STAGED")) == 0);
         // persistent mode: two accumulator sets (<= 256 columns each) and the staging buffer behind the rings
         p->tw_persist = two && want_staged && !(getenv("EGN_TC_V4_PERSIST") && atoi(getenv("EGN_TC_V4_PERSIST")) == 0);
-        const size_t fixed4 = 1024 + (2 * kTwMaxA + 2 * kTwMaxB + 6) * sizeof(uint64_t) + 32 + (size_t)p->n_tile * 4;
+        const size_t fixed4 = 1024 + (2 * kTwMaxA + 2 * kTwMaxB + 6) * sizeof(uint64_t) + 32 + (size_t)p->n_tile * p->tw_fold * 4;
         const size_t budget4 = getenv("EGN_TC_V4_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V4_BUDGET_KB")) * 1024
                                                              : (p->tw_persist ? 225 * 1024 - stage_bytes : (two ? 106 * 1024 : 224 * 1024));
         p->tw_na = getenv("EGN_TC_V4_NA") ? atoi(getenv("EGN_TC_V4_NA")) : 2;      // (3 measured equal once the refill moved to tap 3)
@@ -2779,14 +2797,23 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         p->tw_stage_off = p->tw_persist ? (uint32_t)rings : 0u;
         p->tw_stage_bytes = p->tw_persist ? (uint32_t)stage_bytes : 0u;
         p->smem_bytes = fixed4 + rings + p->tw_stage_bytes;
-        if (p->smem_bytes > 227 * 1024) p->use_tapwin = false;
-        p->n_stage = (want_staged && (p->tw_persist || stage_bytes <= rings)) ? 1 : 0;
+        if (p->smem_bytes > 227 * 1024) {
+          // does not fit: back to the per-tap kernel with the full tile width
+          p->use_tapwin = false;
+          p->n_tile *= p->tw_fold;
+          p->tw_fold = 1;
+          p->tw_pair = p->tw_persist = false;
+          p->tmem_cols = pow2_cols((split ? 2 : 1) * p->n_tile);
+        }
+        p->n_stage = (p->use_tapwin && want_staged && (p->tw_persist || stage_bytes <= rings)) ? 1 : 0;
         if (p->tw_persist) p->tmem_cols = pow2_cols(2 * (split ? 2 : 1) * p->n_tile);
-        p->blk = 1; p->BW = 8; p->BH = 16; p->TBW = 1;          // staging box of make_io_map
+        if (p->use_tapwin) {
+          p->blk = 1; p->BW = 8; p->BH = 16; p->TBW = 1;        // staging box of make_io_map
+        }
         if (getenv("EGN_TC_VERBOSE") && p->use_tapwin)
-          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d persist=%d pair=%d\n",
+          fprintf(stderr, "[egn] conv %dx%d s%d %d->%d @%dx%d%s: v4-tapwin n_tile=%d sw=%d kchunks=%d na=%d nb=%d smem=%zuKB tmem=%u eff=%.2f staged=%d cb=%d persist=%d pair=%d fold=%d\n",
                   a.ksize, a.ksize, a.stride, a.Cin_p, a.Cout_p, a.H, a.W, split ? " fp16x2" : "", p->n_tile, p->sw, p->kchunks,
-                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb, p->tw_persist ? 1 : 0, p->tw_pair ? 1 : 0);
+                  p->tw_na, p->tw_nb, p->smem_bytes / 1024, p->tmem_cols, eff4, p->n_stage, p->cb, p->tw_persist ? 1 : 0, p->tw_pair ? 1 : 0, p->tw_fold);
       }
     }
     if (p->use_tapwin) {
@@ -3255,10 +3282,12 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
     wp.stage_off = persist4 ? p->tw_stage_off : 0u;
     wp.stage_bytes = p->tw_stage_bytes;            // (the barrier block sits behind the region either way)
     if (p->tw_persist && !persist4) wp.tmem_cols = p->tmem_cols;      // head extras: one tile per CTA, direct epilogue
-    dim3 grid((unsigned)(persist4 ? std::min(wp.total_tiles, num_sms) : wp.total_tiles), (unsigned)p->n_tiles);
+    wp.n_fold = p->tw_fold;
+    const int units1 = wp.total_tiles * wp.n_fold;           // work units: (tile, N part)
+    dim3 grid((unsigned)(persist4 ? std::min(units1, num_sms) : units1), (unsigned)p->n_tiles);
     if (p->tw_pair) {
       // clusters of two CTAs along x: tiles 2q, 2q + 1 per pair (an odd last tile gets a past-the-end partner)
-      const int units = (wp.total_tiles + 1) / 2;
+      const int units = (wp.total_tiles + 1) / 2 * wp.n_fold;
       grid.x = 2u * (unsigned)(persist4 ? std::min(units, num_sms / 2) : units);
     }
     static unsigned long long* d_ts4 = nullptr;
