@@ -22,12 +22,13 @@ from oracle import configs, egonet_ref, hrnet_ref  # noqa: E402
 CASES = [(48, 48, 32, 32, 3, 1, 2), (96, 96, 32, 32, 3, 1, 3), (64, 64, 16, 16, 3, 2, 2), (64, 256, 32, 32, 1, 1, 1),
          (192, 192, 16, 16, 3, 1, 1), (35, 66, 32, 32, 3, 2, 1), (96, 96, 24, 20, 3, 1, 3)]
 ENV_KEYS = ('EGN_TC_PAIR', 'EGN_TC_V3', 'EGN_TC_V2', 'EGN_TC_V2_SPLIT', 'EGN_TC_V4', 'EGN_TC_BLK', 'EGN_TC_V4_PERSIST',
-            'EGN_TC_V1_STAGED', 'EGN_TC_V4_STAGED', 'EGN_TC_V4_PAIR')
+            'EGN_TC_V1_STAGED', 'EGN_TC_V4_STAGED', 'EGN_TC_V4_PAIR', 'EGN_TC_V4_FOLD')
 VARIANTS = {'auto': {}, 'no_pair': {'EGN_TC_PAIR': '0'}, 'no_blk': {'EGN_TC_BLK': '0'},
             'no_v3': {'EGN_TC_V3': '0', 'EGN_TC_V2_SPLIT': '1'},
             'v4': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0', 'EGN_TC_V4': '2'},                      # tap-window kernel, persistent where it fits
             'v4_one_tile': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0', 'EGN_TC_V4': '2', 'EGN_TC_V4_PERSIST': '0'},
             'v4_nopair': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0', 'EGN_TC_V4': '2', 'EGN_TC_V4_PAIR': '0'},
+            'v4_nofold': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0', 'EGN_TC_V4': '2', 'EGN_TC_V4_FOLD': '0'},
             'v1_only': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0', 'EGN_TC_V4': '0'},                # per-tap kernel, staged epilogue
             'v1_direct': {'EGN_TC_V3': '0', 'EGN_TC_V2': '0', 'EGN_TC_V4': '0', 'EGN_TC_V1_STAGED': '0'}}
 
