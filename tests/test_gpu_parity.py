@@ -387,7 +387,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize('variant', ['auto', 'no_blk', 'no_pair', 'ksplit', 'no_v3', 'v4', 'v4_nopair', 'v1_only'])
+@pytest.mark.parametrize('variant', ['auto', 'no_blk', 'no_pair', 'ksplit', 'no_v3', 'v4', 'v4_nopair', 'v4_nofold', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
 def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
     """One fused conv (bias + residual + ReLU) through the tcgen05 and the CUDA-core kernels against
@@ -409,18 +409,22 @@ def test_conv_layer_tc_and_simt_vs_torch(case, variant, monkeypatch):
         if not (k == 3 and stride == 1 and W >= 24):
             pytest.skip('K-split accumulators only exist in the persistent kernel')
         monkeypatch.setenv('EGN_TC_KSPLIT', '2')
-    if variant in ('no_v3', 'v1_only', 'v4', 'v4_nopair'):
+    if variant in ('no_v3', 'v1_only', 'v4', 'v4_nopair', 'v4_nofold'):
         monkeypatch.setenv('EGN_TC_V3', '0')
-    if variant in ('v1_only', 'v4', 'v4_nopair'):
+    if variant in ('v1_only', 'v4', 'v4_nopair', 'v4_nofold'):
         monkeypatch.setenv('EGN_TC_V2', '0')
     if variant == 'v1_only':
         monkeypatch.setenv('EGN_TC_V4', '0')
-    if variant in ('v4', 'v4_nopair'):
+    if variant in ('v4', 'v4_nopair', 'v4_nofold'):
         if not (k == 3 and stride == 1):
             pytest.skip('the tap-window kernel only takes stride-1 3x3 convs')
         monkeypatch.setenv('EGN_TC_V4', '2')            # also for plain fp16 operands
     if variant == 'v4_nopair':
         monkeypatch.setenv('EGN_TC_V4_PAIR', '0')       # single CTAs (stacked full-width MMAs where N allows)
+    if variant == 'v4_nofold':
+        if Cout <= 128:
+            pytest.skip('the N fold only applies to tiles wider than 128 channels')
+        monkeypatch.setenv('EGN_TC_V4_FOLD', '0')       # full-width tiles, one accumulator set, one tile per CTA
     Cin, Cout, H, W, k, stride, B = case
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)
     x = torch.randn((B, Cin, H, W), generator=g).to(DEV)
@@ -471,7 +475,7 @@ def _unsplit(t, C):
     return (t[..., :C].double() + t[..., Cp:Cp + C].double()).permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize('variant', ['auto', 'no_blk', 'no_pair', 'no_v3', 'v4', 'v4_nopair', 'v1_only'])
+@pytest.mark.parametrize('variant', ['auto', 'no_blk', 'no_pair', 'no_v3', 'v4', 'v4_nopair', 'v4_nofold', 'v1_only'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=['c%dx%d_%dx%d_k%ds%d_b%d' % c for c in CONV_CASES])
 def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
     """One fused conv in fp16x2 split storage (three error-compensated tcgen05 MMAs per product, two TMEM
@@ -488,18 +492,22 @@ def test_conv_layer_split_precision_vs_torch_fp64(case, variant, monkeypatch):
         if not (k == 3 and stride == 1 and W >= 24):
             pytest.skip('CTA pairs only exist in the persistent kernel')
         monkeypatch.setenv('EGN_TC_PAIR', '0')
-    if variant in ('no_v3', 'v1_only', 'v4', 'v4_nopair'):
+    if variant in ('no_v3', 'v1_only', 'v4', 'v4_nopair', 'v4_nofold'):
         monkeypatch.setenv('EGN_TC_V3', '0')
     if variant == 'no_v3':
         monkeypatch.setenv('EGN_TC_V2_SPLIT', '1')         # the window-run kernel in split storage (off by default: slower)
-    if variant in ('v1_only', 'v4', 'v4_nopair'):
+    if variant in ('v1_only', 'v4', 'v4_nopair', 'v4_nofold'):
         monkeypatch.setenv('EGN_TC_V2', '0')
     if variant == 'v1_only':
         monkeypatch.setenv('EGN_TC_V4', '0')
-    if variant in ('v4', 'v4_nopair') and not (k == 3 and stride == 1):
+    if variant in ('v4', 'v4_nopair', 'v4_nofold') and not (k == 3 and stride == 1):
         pytest.skip('the tap-window kernel only takes stride-1 3x3 convs')
     if variant == 'v4_nopair':
         monkeypatch.setenv('EGN_TC_V4_PAIR', '0')
+    if variant == 'v4_nofold':
+        if Cout <= 128:
+            pytest.skip('the N fold only applies to tiles wider than 128 channels')
+        monkeypatch.setenv('EGN_TC_V4_FOLD', '0')
     g = torch.Generator().manual_seed(Cin * 1000 + Cout + k + stride)
     x = torch.randn((B, Cin, H, W), generator=g).to(DEV)
     w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5)
