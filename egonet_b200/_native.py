@@ -86,6 +86,7 @@ SIGNATURES = {
     'egn_conv2d_bench': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_int, POINTER(c_float)]),
     'egn_debug_umma_rate': (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_double)]),
     'egn_debug_umma_seq': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_double)]),
+    'egn_debug_conv_plan': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_char_p, c_int]),
     'egn_debug_umma_probe': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'egn_conv2d_fused': (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     'egn_debug_conv_acc': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),

@@ -1302,7 +1302,7 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int c = q % p.kchunks;
       const int n0 = n0_of(q / p.kchunks);
       for (int tap = 0; tap < 9; ++tap) {
-        if (tap == (p.na > 1 ? 3 : 8) && q + D < Q) load_a(q + D);
+        if (p.na > 1 && tap == 3 && q + D < Q) load_a(q + D);
         mbar_wait(&b_empty[stage], phase ^ 1u);
         if (elect_one()) {
           uint8_t* sb = smem_b + (size_t)stage * b_stage;
@@ -1324,6 +1324,9 @@ conv_tapwin_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           phase ^= 1u;
         }
       }
+      // a single window slot is refilled only AFTER the last weight tile of the chunk has been issued: its release
+      // (a_empty) is committed behind the tap-8 MMAs, which wait for that tile -- refilling earlier deadlocks
+      if (p.na == 1 && q + 1 < Q) load_a(q + 1);
       if (c == p.kchunks - 1 && p.staged && p.res) {
         // residual block of this tile: into the staging buffer once it is free -- its own buffer: the previous tile's
         // stores have been read out; on top of the rings: every MMA of the (only) tile has completed
@@ -2434,8 +2437,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
     set_error("tc_conv_plan_create: unsupported conv shape");
     return EGN_ERR_INVALID;
   }
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
+  // wf == nullptr: geometry only (kernel choice, tiling, shared-memory / TMEM budget) -- no driver, no device: the
+  // CPU test tier pins the plan of every HRNet layer shape through egn_debug_conv_plan
+  const bool dry = wf == nullptr;
+  EncodeTiledFn enc = dry ? nullptr : get_encode_fn();
+  if (!dry && !enc) {
     set_error("cuTensorMapEncodeTiled is not available from the installed driver");
     return EGN_ERR_CUDA;
   }
@@ -2789,7 +2795,10 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
         const size_t budget4 = getenv("EGN_TC_V4_BUDGET_KB") ? (size_t)atoi(getenv("EGN_TC_V4_BUDGET_KB")) * 1024
                                                              : (p->tw_persist ? 225 * 1024 - stage_bytes : (two ? 106 * 1024 : 224 * 1024));
         p->tw_na = getenv("EGN_TC_V4_NA") ? atoi(getenv("EGN_TC_V4_NA")) : 2;      // (3 measured equal once the refill moved to tap 3)
-        p->tw_na = std::max(1, std::min(std::min(p->tw_na, kTwMaxA), std::max(1, p->kchunks)));
+        // at most one slot per chunk of a tile -- but a persistent CTA walks over many tiles: never fewer than two slots
+        // there (a one-chunk layer would otherwise refill the slot it is still multiplying from)
+        p->tw_na = std::max(1, std::min(std::min(p->tw_na, kTwMaxA), std::max(p->tw_persist ? 2 : 1, p->kchunks)));
+        if (p->tw_persist) p->tw_na = std::max(2, p->tw_na);
         long nb = ((long)budget4 - (long)fixed4 - (long)(p->tw_na * a_slot)) / (long)b_stage4;
         if (getenv("EGN_TC_V4_NB")) nb = std::min<long>(nb, atoi(getenv("EGN_TC_V4_NB")));
         p->tw_nb = (int)std::max<long>(2, std::min<long>(nb, kTwMaxB));
@@ -2868,6 +2877,11 @@ int tc_conv_plan_create(const ConvArgs& a, const float* wf, TcConvPlan** out) {
   const size_t K = v3_split ? ((size_t)taps * a.Cin_p + 63) / 64 * 64
                             : (pack ? (size_t)taps * full_k + (size_t)((taps + 1) / 2) * 64 : (size_t)taps * tap_k);
   const size_t w_rows = v3_split ? 2 * (size_t)a.Cout_p : (size_t)a.Cout_p;
+  if (dry) {
+    p->w_bytes = w_rows * K * sizeof(__half);
+    *out = p;
+    return EGN_OK;
+  }
   std::vector<__half> w(w_rows * K, __float2half_rn(0.f));
   for (int o = 0; o < a.Cout_p; ++o)
     for (int t = 0; t < taps; ++t)
@@ -3375,6 +3389,45 @@ int launch_conv_tc(TcConvPlan* p, const ConvArgs& a, cudaStream_t st) {
 }
 
 }  // namespace egn
+
+// Plan of one fused conv as text (debug / tests): which kernel runs the shape and how it is tiled.  Geometry only:
+// works without a GPU (tc_conv_plan_create with no weights).
+extern "C" int egn_debug_conv_plan(int dtype, int Cin, int Cout, int H, int W, int ksize, int stride, char* out, int out_len) {
+  using namespace egn;
+  EGN_REQUIRE(out && out_len > 0, "egn_debug_conv_plan: null output");
+  EGN_REQUIRE((dtype == 1 || dtype == 2) && Cin > 0 && Cout > 0 && H > 0 && W > 0 && (ksize == 1 || ksize == 3) &&
+                  (stride == 1 || stride == 2),
+              "egn_debug_conv_plan: bad arguments");
+  ConvArgs a{};
+  a.B = 1; a.H = H; a.W = W;
+  a.Cin_p = round_up(Cin, 16);           // channel padding of the engine (hrnet_graph.h kChanAlign)
+  a.Cout_p = round_up(Cout, 16);
+  a.Cout = Cout;
+  a.ksize = ksize; a.stride = stride; a.pad = ksize == 3 ? 1 : 0;
+  a.OH = (H + 2 * a.pad - ksize) / stride + 1;
+  a.OW = (W + 2 * a.pad - ksize) / stride + 1;
+  a.split = dtype == 2 ? 1 : 0;
+  if (!tc_conv_supported(a)) {
+    snprintf(out, (size_t)out_len, "kernel=unsupported");
+    return EGN_OK;
+  }
+  TcConvPlan* p = nullptr;
+  if (int rc = tc_conv_plan_create(a, nullptr, &p)) return rc;
+  const char* kernel = p->use_persist ? "v3-persist" : (p->use_run ? "v2-run" : (p->use_tapwin ? "v4-tapwin" : "v1-tap"));
+  if (p->use_persist)
+    snprintf(out, (size_t)out_len, "kernel=%s n_tile=%d n_tiles=%d blk=%dx%d a_sw=%d a_slots=%d T=%d resident=%d stage=%d pair=%d smem=%zu tmem=%u",
+             kernel, p->n_tile, p->n_tiles, p->blk ? p->BW : 0, p->blk ? p->BH : 0, p->a_sw, p->a_slots, p->T, p->b_resident, p->n_stage,
+             p->use_pair ? 1 : 0, p->smem_bytes, p->tmem_cols);
+  else if (p->use_tapwin)
+    snprintf(out, (size_t)out_len, "kernel=%s n_tile=%d n_tiles=%d sw=%d kchunks=%d na=%d nb=%d staged=%d persist=%d pair=%d fold=%d smem=%zu tmem=%u",
+             kernel, p->n_tile, p->n_tiles, p->sw, p->kchunks, p->tw_na, p->tw_nb, p->n_stage, p->tw_persist ? 1 : 0, p->tw_pair ? 1 : 0,
+             p->tw_fold, p->smem_bytes, p->tmem_cols);
+  else
+    snprintf(out, (size_t)out_len, "kernel=%s n_tile=%d n_tiles=%d sw=%d kchunks=%d stages=%d staged=%d T=%d smem=%zu tmem=%u", kernel,
+             p->n_tile, p->n_tiles, p->sw, p->kchunks, p->stages, p->n_stage, p->T, p->smem_bytes, p->tmem_cols);
+  tc_conv_plan_destroy(p);
+  return EGN_OK;
+}
 
 // ---------------------------------------------------------------------------
 // Hardware probe: does a K-major swizzled UMMA descriptor whose start address is offset by an

@@ -164,6 +164,10 @@ EGN_API int egn_debug_conv_acc(int impl, const void* in, const float* w_oihw_hos
  * CTAs each issue iters*4*nacc MMAs of width n, rotating over nacc accumulators. */
 EGN_API int egn_debug_umma_rate(int n, int nacc, int iters, int a_rows_shift, int ctas, double* cycles_per_mma);
 
+/* Plan of one fused tcgen05 conv as text (debug / tests): which kernel runs the shape (v1-tap / v2-run / v3-persist /
+ * v4-tapwin) and how it is tiled.  dtype 1 = fp16, 2 = fp16x2.  Geometry only: no GPU needed. */
+EGN_API int egn_debug_conv_plan(int dtype, int Cin, int Cout, int H, int W, int ksize, int stride, char* out, int out_len);
+
 /* Hardware probe (debug): SM cycles per K16 slice of the MMA sequences the fp16x2 conv kernels issue (pattern 0: one
  * N = n MMA; 1: full-width N = 2n + half-width N = n; 2: three N = n MMAs into H, L, L; 3: as 1, grouped per two
  * slices), operands resident in shared memory, A rows of a_sw bytes (128 / 64) with 8-row groups sbo_rows rows apart. */

@@ -384,6 +384,8 @@ CONV_CASES = [
     (96, 96, 32, 32, 3, 1, 40),     # 440 windows: several iterations per CTA pair, last pair iteration ragged
     (96, 96, 16, 8, 3, 1, 3),       # tap-window kernel: 3 tiles -- the last CTA pair has a past-the-end partner tile
     (48, 48, 16, 24, 3, 1, 1),      # 3 tiles of one image, persistent pair mode with fewer tiles than CTAs
+    (32, 32, 16, 16, 3, 1, 160),    # one channel chunk per tile, 320 tiles: several tiles per persistent CTA (the window
+                                    # ring has to hold two slots: a single one would be refilled while still in use)
 ]
 
 
